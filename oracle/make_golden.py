@@ -1,0 +1,250 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the REFERENCE's own modules.
+
+Run in the build container only (needs /root/reference; it does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+
+Nothing is copied from the reference: its modules are imported, fed the deterministic synthetic
+weights/inputs of oracle/synth.py, and only their *outputs* are stored.  The script also asserts
+that oracle/synth.py's name/shape tables equal the reference modules' state_dict() entries, which
+pins the checkpoint key-name contract.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import sys
+import types
+from functools import partial
+from types import SimpleNamespace as NS
+
+import numpy as np
+import torch
+
+REF = os.environ.get("GROVE_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+from oracle import synth  # noqa: E402
+
+
+def _stub_mm():
+    """mmdet/mmcv/mmengine are imported by model/layers.py:8-10 only (dead region encoder)."""
+    for name, attrs in {"mmdet": {}, "mmdet.models": {"BaseRoIExtractor": object}, "mmcv": {}, "mmcv.cnn": {"ConvModule": object, "Linear": object},
+                        "mmcv.ops": {"RoIAlign": object}, "mmengine": {}, "mmengine.model": {"normal_init": lambda *a, **k: None}}.items():
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules.setdefault(name, m)
+
+
+def _functions_from_source(path, names, scope):
+    """exec only the named top-level functions of a reference script (its module-level code loads
+    BERT / CoreNLP and cannot be imported); nothing is written to the repo."""
+    tree = ast.parse(open(path).read())
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], []), path, "exec"), scope)
+    return scope
+
+
+def _check_shapes(module, shapes, strip):
+    sd = module.state_dict()
+    for k, shp in shapes.items():
+        rk = k[len(strip):]
+        assert rk in sd, f"reference has no key {rk}"
+        assert tuple(sd[rk].shape) == tuple(shp), (rk, tuple(sd[rk].shape), shp)
+
+
+def _load(module, sdict, strip):
+    missing, unexpected = module.load_state_dict({k[len(strip):]: v for k, v in sdict.items()}, strict=False)
+    assert not unexpected, unexpected
+    return missing
+
+
+def encoder_case(name, *, embed_dim, depth, heads, global_idx, img, verbatim_adapter, seed):
+    from model.SAM.modeling.image_encoder import ImageEncoderViT, SpatioTemporalConvAdapter
+    from einops import rearrange
+    G = img // 16
+    enc = ImageEncoderViT(depth=depth, embed_dim=embed_dim, img_size=img, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                          num_heads=heads, patch_size=16, qkv_bias=True, use_rel_pos=True, global_attn_indexes=global_idx,
+                          window_size=14, out_chans=256).eval()
+    if not verbatim_adapter:
+        # oracle-side generalisation of image_encoder.py:52 (h inferred instead of h=32); identical arithmetic
+        class _Adapter(SpatioTemporalConvAdapter):
+            def forward(self, x):
+                x = rearrange(x, '(b t) h w c -> b c t h w', t=8)
+                x = self.tanh(self.alpha) * self.relu(self.conv3d(x)) + x
+                return rearrange(x, 'b c t h w -> (b t) h w c')
+        enc.adapters = torch.nn.ModuleList([_Adapter(embed_dim, embed_dim, (3, 3, 3)) for _ in global_idx])
+    shapes = synth.encoder_param_shapes(embed_dim, depth, heads, global_idx, G)
+    _check_shapes(enc, shapes, "image_encoder.")
+    assert set(k[len("image_encoder."):] for k in shapes) == set(enc.state_dict().keys())
+    sdict = synth.synth_state_dict(shapes, seed)
+    assert not _load(enc, sdict, "image_encoder.")
+    images = synth.synth_tensor(name + ".images", (1, 3, 8, img, img), seed)
+    with torch.no_grad():
+        out = enc(images)
+        out64 = enc.double()(images.double())   # the reference itself in float64: the tight pin
+    # keep the fixture small: a strided sub-lattice (every 4th channel, every 2nd row/col) + per-channel sums
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), out_sub=out[:, ::4, ::2, ::2].numpy(),
+                        out_chan_sum=out.double().sum((2, 3)).numpy(), out64_sub=out64[:, ::4, ::2, ::2].numpy(),
+                        meta=np.array([embed_dim, depth, heads, img, seed] + list(global_idx)))
+    print(name, tuple(out.shape), float(out.abs().mean()), "ref fp32-vs-fp64 gap %.2e" % float((out - out64).abs().max()))
+
+
+def decoder_case(name, *, dim, mlp, G, frames, reps, seed):
+    from model.SAM.modeling import MaskDecoder, PromptEncoder, TwoWayTransformer
+    pe = PromptEncoder(embed_dim=dim, image_embedding_size=(G, G), input_image_size=(16 * G, 16 * G), mask_in_chans=16).eval()
+    md = MaskDecoder(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=dim, mlp_dim=mlp, num_heads=8),
+                     transformer_dim=dim, iou_head_depth=3, iou_head_hidden_dim=dim, decoding_type="query", use_temp_objectness=True).eval()
+    shapes = synth.decoder_param_shapes(dim, mlp)
+    _check_shapes(pe, {k: v for k, v in shapes.items() if k.startswith("prompt_encoder.")}, "prompt_encoder.")
+    _check_shapes(md, {k: v for k, v in shapes.items() if k.startswith("mask_decoder.")}, "mask_decoder.")
+    sdict = synth.synth_state_dict(shapes, seed)
+    _load(pe, {k: v for k, v in sdict.items() if k.startswith("prompt_encoder.")}, "prompt_encoder.")
+    _load(md, {k: v for k, v in sdict.items() if k.startswith("mask_decoder.")}, "mask_decoder.")
+    emb = synth.synth_tensor(name + ".emb", (frames, dim, G, G), seed)
+    txt = synth.synth_tensor(name + ".txt", (sum(reps), 1, dim), seed)
+    with torch.no_grad():
+        dense_pe = pe.get_dense_pe()
+        sparse, dense = pe(points=None, boxes=None, masks=None, text_embeds=txt)
+        boxes, logits = md(image_embeddings=emb, image_pe=dense_pe, sparse_prompt_embeddings=sparse,
+                           dense_prompt_embeddings=dense, multimask_output=False, reps=list(reps))
+        pe64, md64 = pe.double(), md.double()   # the reference itself in float64: the tight pin
+        sp64, de64 = pe64(points=None, boxes=None, masks=None, text_embeds=txt.double())
+        boxes64, logits64 = md64(image_embeddings=emb.double(), image_pe=pe64.get_dense_pe(), sparse_prompt_embeddings=sp64.double(),
+                                 dense_prompt_embeddings=de64, multimask_output=False, reps=list(reps))
+        pe.float(), md.float()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), boxes=boxes.numpy(), logits=logits.numpy(),
+                        boxes64=boxes64.numpy(), logits64=logits64.numpy(),
+                        dense_pe_sample=dense_pe[0, :, ::max(G // 4, 1), ::max(G // 4, 1)].numpy(),
+                        meta=np.array([dim, mlp, G, frames, seed]), reps=np.array(reps))
+    print(name, tuple(boxes.shape), "min|logit|", float(logits.abs().min()), "ref fp32-vs-fp64 gap: boxes %.2e logits %.2e"
+          % (float((boxes - boxes64).abs().max()), float((logits - logits64).abs().max())))
+    return pe, md, sdict
+
+
+def glue_case(name, seed):
+    """GROVE-level methods called unbound with a duck-typed self."""
+    _stub_mm()
+    torch.Tensor.cuda = lambda self, *a, **k: self  # GROVE.py:203,260 hard-code .cuda()
+    import model.GROVE as RG
+    C = RG.GROVEForCausalLM
+    dim, mlp, G, T, hidden, L = 64, 128, 8, 8, 96, 600
+    pe, md, sdict = decoder_case(name + "_dec", dim=dim, mlp=mlp, G=G, frames=2 * T, reps=[3] * T + [2] * T, seed=seed)
+    fshapes = synth.text_fcs_shapes(hidden, dim)
+    fsd = synth.synth_state_dict(fshapes, seed)
+    fcs = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(hidden, hidden), torch.nn.ReLU(inplace=True),
+                                                   torch.nn.Linear(hidden, dim), torch.nn.Dropout(0.0))])
+    _check_shapes(fcs, fshapes, "text_hidden_fcs.")
+    _load(fcs, fsd, "text_hidden_fcs.")
+    self = NS(model=NS(text_hidden_fcs=fcs, grounding_encoder=NS(prompt_encoder=pe, mask_decoder=md)),
+              config=NS(num_frames=T, use_temp_objectness=True, temp_objectness_threshold=0.5),
+              ce_loss_weight=1.0, giou_loss_weight=2.0, temp_objectness_loss_weight=2.0, det_token_idx=32005)
+    ids = torch.full((2, L - 575), 7, dtype=torch.long)
+    pos = [synth.det_positions(L, 3, seed), synth.det_positions(L, 2, seed + 1)]
+    for v, pp in enumerate(pos):
+        for p in pp:
+            ids[v, p - 575 + 1] = 32005  # mask = ids[:,1:] shifted by the 575 pad
+    hid = synth.synth_tensor(name + ".hidden", (2, L, hidden), seed)
+    emb = synth.synth_tensor(name + "_dec.emb", (2 * T, dim, G, G), seed)
+    with torch.no_grad():
+        mask = C._create_det_token_mask(self, ids)
+        assert [int(i) for i in mask[0].nonzero().flatten()] == pos[0]
+        _, pred_list = C._process_hidden_states(self, [hid], mask, None)
+        dense_pe = pe.get_dense_pe()
+        tb, tl = C._generate_and_postprocess_masks(self, pred_list, emb, [(1280, 720), (640, 360)], dense_pe, infer=False)
+        ib, il = C._generate_and_postprocess_masks(self, pred_list, emb, [(1280, 720), (640, 360)], dense_pe, infer=True)
+        # ground truth for the loss: Bernoulli(.5) labels (float64 like HowTo100M.py:129), boxes for the positives
+        rng = np.random.Generator(np.random.PCG64([seed, 99]))
+        gt_b, gt_o = [], []
+        for v in range(2):
+            P = len(pos[v])
+            gb, go = [], []
+            for f in range(T):
+                o = (rng.uniform(size=P) < 0.5).astype(np.float64)
+                n = int(o.sum())
+                cxcy = rng.uniform(0.3, 0.7, (n, 2))
+                wh = rng.uniform(0.1, 0.4, (n, 2))
+                gb.append(torch.from_numpy(np.concatenate([cxcy, wh], 1)).float())
+                go.append(torch.from_numpy(o))
+            gt_b.append(gb)
+            gt_o.append(go)
+        loss = C._compute_loss_components_video(self, tb, tl, gt_b, gt_o, NS(loss=torch.tensor(0.25)))
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        det_mask=mask.numpy(), pred_embeddings=torch.cat(pred_list).numpy(), counts=np.array([p.shape[0] for p in pred_list]),
+        train_boxes=torch.cat([b for v in tb for b in v]).numpy(), train_logits=torch.cat([l for v in tl for l in v]).numpy(),
+        infer_boxes=torch.cat([b for v in ib for b in v]).numpy(), infer_counts=np.array([b.shape[0] for v in ib for b in v]),
+        gt_boxes=torch.cat([b for v in gt_b for b in v]).numpy(), gt_obj=torch.cat([o for v in gt_o for o in v]).numpy(),
+        losses=np.array([float(loss[k]) for k in ("loss", "ce_loss", "giou_loss", "l1_loss", "temp_objectness_loss")]))
+    print(name, {k: float(v) for k, v in loss.items()})
+
+
+def box_eval_case(name, seed):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_eval_vidstg", os.path.join(REF, "eval_vidstg.py"))
+    ev = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ev)
+    ig = _functions_from_source(os.path.join(REF, "eval_iground.py"), {"compute_iou", "compute_iou_matrix"}, {"np": np})
+    an = _functions_from_source(os.path.join(REF, "eval_anet.py"), {"bbox_overlaps_batch"}, {"np": np, "torch": torch})
+    sl = _functions_from_source(os.path.join(REF, "infer_iground.py"), {"sliding_segment_with_mask"}, {})
+    rng = np.random.Generator(np.random.PCG64([seed, 5]))
+
+    def boxes(n, lo=0, hi=200, integer=False):
+        xy = rng.uniform(lo, hi, (n, 2))
+        wh = rng.uniform(0, 80, (n, 2))
+        b = np.concatenate([xy, xy + wh], 1)
+        return np.round(b) if integer else b
+    b1, b2 = boxes(13), boxes(9)
+    b1[3] = b2[2]                      # exact overlap
+    b1[4] = [5, 5, 5, 5]               # zero-area
+    b2[5] = [300, 300, 310, 310]       # disjoint
+    iou64 = ev.np_box_iou(b1, b2)
+    iou32 = ev.np_box_iou(b1.astype(np.float32), b2.astype(np.float32))
+    p1, p2 = boxes(7, 0, 60, integer=True), boxes(6, 0, 60, integer=True)
+    p1[2] = p2[1]
+    mat = ig["compute_iou_matrix"](p1.tolist(), p2.tolist())
+    # greedy matcher: the reference loop (eval_iground.py:85-96) re-executed on the reference's matrix
+    sims = rng.uniform(0, 1, mat.shape)
+    ious, ts, matches = mat.copy(), sims.copy(), []
+    while ious.size > 0 and ts.size > 0:
+        m = np.unravel_index(np.argmax(ious), ious.shape)
+        if ious[m] < 0.3 or ts[m] < 0.2:
+            break
+        matches.append(m)
+        ious[m[0], :] = 0; ious[:, m[1]] = 0; ts[m[0], :] = 0; ts[:, m[1]] = 0
+    anc = np.concatenate([boxes(10, integer=True), np.arange(10)[:, None]], 1)[None].astype(np.float32)
+    gtb = np.concatenate([boxes(4, integer=True), rng.integers(0, 10, (4, 1))], 1)[None].astype(np.float32)
+    anc[0, 1, :4] = [7, 7, 7, 7]       # zero-area anchor -> -1
+    gtb[0, 2, :4] = [9, 9, 9, 9]       # zero-area gt -> 0
+    frm = (anc[0, :, 4][:, None] != gtb[0, :, 4][None, :]).astype(np.uint8)[None]
+    ov = an["bbox_overlaps_batch"](torch.from_numpy(anc), torch.from_numpy(gtb), torch.from_numpy(frm)).numpy()
+    ov_nomask = an["bbox_overlaps_batch"](torch.from_numpy(anc), torch.from_numpy(gtb), torch.from_numpy(np.zeros_like(frm))).numpy()
+    seg = {str(n): sl["sliding_segment_with_mask"](n, 8) for n in (8, 48, 50, 61, 128)}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), b1=b1, b2=b2, iou64=iou64, iou32=iou32, p1=p1, p2=p2, mat=mat, sims=sims,
+                        matches=np.array(matches, dtype=np.int64).reshape(-1, 2), anc=anc, gtb=gtb, frm=frm, ov=ov, ov_nomask=ov_nomask,
+                        **{f"seg_idx_{k}": np.array(sum(v[0], [])) for k, v in seg.items()},
+                        **{f"seg_mask_{k}": np.array(sum(v[1], [])) for k, v in seg.items()},
+                        **{f"seg_len_{k}": np.array([len(r) for r in v[0]]) for k, v in seg.items()})
+    print(name, "iou", iou64.shape, "matches", matches)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sys.path.insert(0, REF)
+    sys.dont_write_bytecode = True
+    torch.manual_seed(0)
+    # 512^2 = the reference's real operating point, reference adapter class VERBATIM (t=8,h=32 hard-coded)
+    encoder_case("enc_tiny512_verbatim", embed_dim=64, depth=3, heads=2, global_idx=(1, 2), img=512, verbatim_adapter=True, seed=1)
+    # 256^2 (G=16 -> windows padded 16->28) with the oracle-side generalised adapter
+    encoder_case("enc_tiny256_padded", embed_dim=96, depth=2, heads=3, global_idx=(1,), img=256, verbatim_adapter=False, seed=2)
+    # BASELINE config 1 at full size (64x64x256, 8 frames x 4 phrases)
+    decoder_case("dec_cfg1_full", dim=256, mlp=2048, G=64, frames=8, reps=[4] * 8, seed=3)
+    # ragged phrases incl. a frame with zero phrases
+    decoder_case("dec_ragged", dim=256, mlp=2048, G=32, frames=4, reps=[2, 0, 3, 1], seed=4)
+    glue_case("glue", seed=5)
+    box_eval_case("box_eval", seed=6)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+"""Pins the oracle (oracle/*.py) to outputs of the reference's own modules (tests/golden/*.npz,
+written by oracle/make_golden.py in the build container).  CPU only."""
+import os
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN
+from oracle import box_eval, grounding as og, synth
+
+
+def _g(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def _encoder_case(name):
+    g = _g(name)
+    D, depth, heads, img, seed, *gidx = [int(x) for x in g["meta"]]
+    sd = synth.synth_state_dict(synth.encoder_param_shapes(D, depth, heads, gidx, img // 16), seed)
+    images = synth.synth_tensor(name + ".images", (1, 3, 8, img, img), seed)
+    with torch.no_grad():
+        out = og.image_encoder(images, sd, depth=depth, heads=heads, global_idx=gidx, pre="image_encoder.")
+    np.testing.assert_allclose(out[:, ::4, ::2, ::2].numpy(), g["out_sub"], rtol=0, atol=2e-4)
+    with torch.no_grad():   # tight pin: oracle in float64 vs the reference in float64
+        sd64 = {k: v.double() for k, v in sd.items()}
+        out64 = og.image_encoder(synth.synth_tensor(name + ".images", (1, 3, 8, img, img), seed).double(), sd64,
+                                 depth=depth, heads=heads, global_idx=gidx, pre="image_encoder.")
+    np.testing.assert_allclose(out64[:, ::4, ::2, ::2].numpy(), g["out64_sub"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(out.double().sum((2, 3)).numpy(), g["out_chan_sum"], rtol=0, atol=2e-2)
+
+
+def test_encoder_512_verbatim_reference_adapter():
+    _encoder_case("enc_tiny512_verbatim")
+
+
+def test_encoder_256_padded_windows():
+    _encoder_case("enc_tiny256_padded")
+
+
+def _decoder_case(name):
+    g = _g(name)
+    dim, mlp, G, frames, seed = [int(x) for x in g["meta"]]
+    reps = [int(r) for r in g["reps"]]
+    sd = synth.synth_state_dict(synth.decoder_param_shapes(dim, mlp), seed)
+    emb = synth.synth_tensor(name + ".emb", (frames, dim, G, G), seed)
+    txt = synth.synth_tensor(name + ".txt", (sum(reps), 1, dim), seed)
+    with torch.no_grad():
+        pe = og.dense_pe(sd["prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"], G)
+        boxes, logits = og.box_decoder(emb, pe, txt, reps, sd)
+    st = max(G // 4, 1)
+    np.testing.assert_allclose(pe[0, :, ::st, ::st].numpy(), g["dense_pe_sample"], atol=1e-5)
+    # fp32 vs the reference's fp32 (both carry fp32 round-off; the reference's own fp32-vs-fp64 gap here is <1e-6) ...
+    np.testing.assert_allclose(boxes.numpy(), g["boxes"], atol=5e-6)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], atol=2e-5)
+    # ... and the tight pin is float64 oracle vs float64 reference
+    sd64 = {k: v.double() for k, v in sd.items()}
+    with torch.no_grad():
+        pe64 = og.dense_pe(sd64["prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"], G)
+        b64, l64 = og.box_decoder(emb.double(), pe64, txt.double(), reps, sd64)
+    np.testing.assert_allclose(b64.numpy(), g["boxes64"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(l64.numpy(), g["logits64"], rtol=0, atol=1e-9)
+    # decisions on the path are bit-exact against the reference's floats
+    assert ((torch.sigmoid(l64) > 0.5).numpy() == (torch.sigmoid(torch.from_numpy(g["logits64"])) > 0.5).numpy()).all()
+
+
+def test_decoder_config1_full_size():
+    _decoder_case("dec_cfg1_full")
+
+
+def test_decoder_ragged_with_empty_frame():
+    _decoder_case("dec_ragged")
+
+
+def test_glue_methods_and_losses():
+    g = _g("glue")
+    seed, dim, mlp, G, T, hidden, L = 5, 64, 128, 8, 8, 96, 600
+    pos = [synth.det_positions(L, 3, seed), synth.det_positions(L, 2, seed + 1)]
+    ids = torch.full((2, L - 575), 7, dtype=torch.long)
+    for v, pp in enumerate(pos):
+        for p in pp:
+            ids[v, p - 575 + 1] = 32005
+    mask = og.create_det_token_mask(ids, 32005)
+    assert (mask.numpy() == g["det_mask"]).all()
+    sd = synth.synth_state_dict({**synth.decoder_param_shapes(dim, mlp), **synth.text_fcs_shapes(hidden, dim)}, seed)
+    hid = synth.synth_tensor("glue.hidden", (2, L, hidden), seed)
+    emb = synth.synth_tensor("glue_dec.emb", (2 * T, dim, G, G), seed)
+    with torch.no_grad():
+        pred = og.process_hidden_states(hid, mask, sd, T)
+        assert [p.shape[0] for p in pred] == g["counts"].tolist()
+        np.testing.assert_allclose(torch.cat(pred).numpy(), g["pred_embeddings"], atol=1e-5)
+        reps = [p.shape[0] for p in pred]
+        pe = og.dense_pe(sd["prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"], G)
+        boxes, logits = og.box_decoder(emb, pe, torch.cat(pred).unsqueeze(1), reps, sd)
+        tb, tl = og.postprocess(boxes, logits, reps, T, None, infer=False)
+        ib, _ = og.postprocess(boxes, logits, reps, T, [(1280, 720), (640, 360)], infer=True)
+    np.testing.assert_allclose(torch.cat([b for v in tb for b in v]).numpy(), g["train_boxes"], atol=2e-5)
+    np.testing.assert_allclose(torch.cat([l for v in tl for l in v]).numpy(), g["train_logits"], atol=2e-4)
+    assert [b.shape[0] for v in ib for b in v] == g["infer_counts"].tolist()      # threshold decisions: exact
+    np.testing.assert_allclose(torch.cat([b for v in ib for b in v]).numpy(), g["infer_boxes"], atol=2e-2)
+    # losses on the reference's ground truth
+    gb_all, go_all = torch.from_numpy(g["gt_boxes"]), torch.from_numpy(g["gt_obj"])
+    gt_b, gt_o, ob, oo = [], [], 0, 0
+    for v in range(2):
+        P = len(pos[v])
+        fb, fo = [], []
+        for f in range(T):
+            o = go_all[oo:oo + P]
+            oo += P
+            n = int(o.sum())
+            fb.append(gb_all[ob:ob + n])
+            ob += n
+            fo.append(o)
+        gt_b.append(fb)
+        gt_o.append(fo)
+    loss = og.loss_components(tb, tl, gt_b, gt_o, torch.tensor(0.25), 1.0, 2.0, 2.0)
+    got = np.array([float(loss[k]) for k in ("loss", "ce_loss", "giou_loss", "l1_loss", "temp_objectness_loss")])
+    np.testing.assert_allclose(got, g["losses"], rtol=2e-5)
+
+
+def test_box_eval_utilities_bit_exact():
+    g = _g("box_eval")
+    assert np.array_equal(box_eval.np_box_iou(g["b1"], g["b2"]), g["iou64"], equal_nan=True)
+    assert np.array_equal(box_eval.np_box_iou(g["b1"].astype(np.float32), g["b2"].astype(np.float32)), g["iou32"], equal_nan=True)
+    mat = box_eval.compute_iou_matrix(g["p1"].tolist(), g["p2"].tolist())
+    assert np.array_equal(mat, g["mat"])
+    m = box_eval.greedy_match(mat, g["sims"], 0.3, 0.2)
+    assert np.array_equal(np.array(m, dtype=np.int64).reshape(-1, 2), g["matches"])
+    assert np.array_equal(box_eval.bbox_overlaps_batch(g["anc"], g["gtb"], g["frm"]), g["ov"])
+    assert np.array_equal(box_eval.bbox_overlaps_batch(g["anc"], g["gtb"], np.zeros_like(g["frm"])), g["ov_nomask"])
+    for n in (8, 48, 50, 61, 128):
+        idx, masks = box_eval.sliding_segment_with_mask(n, 8)
+        assert sum(idx, []) == g[f"seg_idx_{n}"].tolist()
+        assert sum(masks, []) == g[f"seg_mask_{n}"].tolist()
+        assert [len(r) for r in idx] == g[f"seg_len_{n}"].tolist()
