@@ -1,0 +1,76 @@
+"""ctypes binding of libgrove_b200.so (the C ABI declared in include/grove_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgrove_b200.so")
+
+
+class GemmEpilogue(C.Structure):
+    """mirror of `struct grove_gemm_epilogue`"""
+    _fields_ = [("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_row_mod", C.c_int), ("gate_alpha", C.c_void_p),
+                ("act", C.c_int), ("out_f32", C.c_int), ("out2_bf16", C.c_void_p), ("max_ctas", C.c_int)]
+
+
+_P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
+
+# name -> argtypes (every function returns int unless listed in _RESTYPES); the stream is always last
+SIGNATURES = {
+    "grove_abi_version": [],
+    "grove_last_error": [],
+    "grove_launch_count": [],
+    "grove_reset_launch_count": [],
+    "grove_gemm_bf16": [_P, _P, _P, _I, _I, _I, C.POINTER(GemmEpilogue), _P],
+    "grove_conv_gemm_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(GemmEpilogue), _P],
+    "grove_im2col_patch16": [_P, _P, _I, _I, _I, _I, _P],
+    "grove_layernorm": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "grove_attn_window_relpos_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_attn_global_relpos_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "grove_cast_f32_bf16": [_P, _P, _LL, _P],
+    "grove_tokens_to_nchw_bf16": [_P, _P, _I, _I, _I, _P],
+    "grove_nchw_to_tokens_bf16": [_P, _P, _I, _I, _I, _P],
+    "grove_gather_rows_bf16": [_P, _I, _P, _P, _I, _I, _P],
+    "grove_dense_pe": [_P, _P, _I, _I, _P],
+    "grove_add_rowvec_bf16": [_P, _P, _P, _LL, _I, _P],
+    "grove_decoder_t2i_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_decoder_i2t_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_decoder_keys_add_ln": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "grove_small_linear_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "grove_token_self_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "grove_add_layernorm_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "grove_box_postprocess": [_P, _P, _P, _F, _P, _P, _I, _P],
+    "grove_box_losses_fwd": [_P, _P, _P, _P, _P, _P, _I, _P],
+    "grove_box_iou": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P],
+    "grove_greedy_match": [_P, _P, _D, _D, _P, _P, _I, _I, _P],
+}
+_RESTYPES = {"grove_last_error": C.c_char_p, "grove_launch_count": C.c_longlong, "grove_reset_launch_count": None}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m grove_b200.build` "
+                               "(or __graft_entry__.build()); grove_b200 has no CPU / PyTorch fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        if l.grove_abi_version() != 1:
+            raise RuntimeError("libgrove_b200.so ABI version mismatch; rebuild")
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().grove_last_error().decode(errors="replace")
+        raise RuntimeError(f"grove_b200 {what} failed (code {rc}): {msg}")

@@ -1,0 +1,233 @@
+"""Box decoder ("MaskDecoder" with decoding_type="query") — reference: model/SAM/modeling/mask_decoder.py.
+
+Same constructor / forward contract as the reference (mask_decoder.py:19-134); only the query path that GROVE
+runs (:191-205) is built.  The two-way transformer (transformer.py:62-182) is lowered as:
+
+  image side  (N x 256 per instance, bf16 in HBM): k/v/q projections and the image->token out_proj on the tcgen05
+              GEMM; `keys + pe` is never materialised — (keys+pe)W = keys.W + (pe.W), and pe.W is added by the GEMM
+              epilogue as a row-periodic fp32 residual; layer-0 projections are computed once per FRAME because all
+              phrases of a frame share src = emb + no_mask until the first image->token update (:178-185);
+  token side  (6 x 256 per instance, fp32): small fused fp32 kernels.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple, Type
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .common import LayerNorm2d, PackCache, _ContainerOnly, bf16, f32
+
+
+class MLP(_ContainerOnly):
+    """mask_decoder.py:230-254 (only used by the mask / IoU heads that GROVE never runs)."""
+
+    def __init__(self, input_dim: int, hidden_dim: int, output_dim: int, num_layers: int, sigmoid_output: bool = False) -> None:
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+        self.sigmoid_output = sigmoid_output
+
+
+class MaskDecoder(nn.Module):
+    def __init__(self, *, transformer_dim: int, transformer: nn.Module, num_multimask_outputs: int = 3, activation: Type[nn.Module] = nn.GELU,
+                 iou_head_depth: int = 3, iou_head_hidden_dim: int = 256, decoding_type: str = "query", use_temp_objectness: bool = True) -> None:
+        super().__init__()
+        if decoding_type != "query":
+            raise NotImplementedError("grove_b200 builds the box ('query') decoding path only; the mask path never runs in GROVE")
+        self.transformer_dim = transformer_dim
+        self.transformer = transformer
+        self.num_multimask_outputs = num_multimask_outputs
+        self.iou_token = nn.Embedding(1, transformer_dim)
+        self.num_mask_tokens = num_multimask_outputs + 1
+        self.mask_tokens = nn.Embedding(self.num_mask_tokens, transformer_dim)
+        # unused by the query path; kept so reference checkpoints load key-for-key (mask_decoder.py:57-78)
+        self.output_upscaling = nn.Sequential(
+            nn.ConvTranspose2d(transformer_dim, transformer_dim // 4, kernel_size=2, stride=2), LayerNorm2d(transformer_dim // 4), activation(),
+            nn.ConvTranspose2d(transformer_dim // 4, transformer_dim // 8, kernel_size=2, stride=2), activation())
+        self.output_hypernetworks_mlps = nn.ModuleList([MLP(transformer_dim, transformer_dim, transformer_dim // 8, 3)
+                                                        for _ in range(self.num_mask_tokens)])
+        self.iou_prediction_head = MLP(transformer_dim, iou_head_hidden_dim, self.num_mask_tokens, iou_head_depth)
+        self.decoding_type = decoding_type
+        self.bbox_prediction_head = nn.Sequential(nn.Linear(transformer_dim, transformer_dim), nn.ReLU(), nn.Linear(transformer_dim, 4))
+        if use_temp_objectness:
+            self.temporal_objectness_head = nn.Linear(transformer_dim, 1)
+            self.use_temp_objectness = True
+        else:
+            self.use_temp_objectness = False
+        self._pack = PackCache()
+        self.max_instances_per_pass = 256  # bounds the per-instance key buffers (N x 256 bf16 + fp32 delta)
+
+    # ------------------------------------------------------------------ helpers
+    def _w32(self, key, lin):
+        return self._pack.get(key + ".w32", [lin.weight], f32), self._pack.get(key + ".b32", [lin.bias], f32)
+
+    def _w16(self, key, lin):
+        return self._pack.get(key + ".w16", [lin.weight], bf16), self._pack.get(key + ".b32", [lin.bias], f32)
+
+    def _ln(self, key, ln):
+        return self._pack.get(key + ".g", [ln.weight], f32), self._pack.get(key + ".b", [ln.bias], f32)
+
+    @staticmethod
+    def _tokens_of(x: torch.Tensor, dtype) -> torch.Tensor:
+        """[F,C,G,G] (NCHW or channels-last view) -> token-major [F, G*G, C] of `dtype`."""
+        Fr, C, G, _ = x.shape
+        if x.permute(0, 2, 3, 1).is_contiguous():
+            t = x.permute(0, 2, 3, 1).reshape(Fr, G * G, C)
+            return t if t.dtype == dtype else t.to(dtype)
+        if dtype == torch.bfloat16:
+            xc = x.to(torch.bfloat16).contiguous()
+            out = torch.empty(Fr, G * G, C, device=x.device, dtype=torch.bfloat16)
+            return ops.nchw_to_tokens(xc, out, Fr, G * G, C)
+        return x.permute(0, 2, 3, 1).reshape(Fr, G * G, C).to(dtype).contiguous()
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, image_embeddings: torch.Tensor, image_pe: torch.Tensor, sparse_prompt_embeddings: torch.Tensor,
+                dense_prompt_embeddings: torch.Tensor, multimask_output: bool, reps: List[int]):
+        """mask_decoder.py:91-134: returns (bbox_pred [B,4], temp_objectness_logits [B]) or bbox_pred."""
+        boxes, logits = self.predict_masks(image_embeddings=image_embeddings, image_pe=image_pe,
+                                           sparse_prompt_embeddings=sparse_prompt_embeddings,
+                                           dense_prompt_embeddings=dense_prompt_embeddings, reps=reps)
+        return (boxes, logits) if self.use_temp_objectness else boxes
+
+    @torch.no_grad()
+    def predict_masks(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, reps: List[int]):
+        """mask_decoder.py:155-205 (query path)."""
+        if not image_embeddings.is_cuda:
+            raise RuntimeError("grove_b200.MaskDecoder runs on CUDA only (no CPU fallback)")
+        Fr, C, G, _ = image_embeddings.shape
+        B = sparse_prompt_embeddings.shape[0]
+        if len(reps) != Fr or sum(reps) != B:
+            raise ValueError(f"reps must have one entry per frame summing to the number of prompts (got {len(reps)} entries, sum {sum(reps)}, "
+                             f"{Fr} frames, {B} prompts)")
+        if sparse_prompt_embeddings.shape[1] != 1:
+            raise NotImplementedError("one text token per prompt (GROVE.py:272)")
+        d = dense_prompt_embeddings
+        if d.dim() != 4 or (d.shape[0] > 0 and (d.stride(0) != 0 or d.stride(2) != 0 or d.stride(3) != 0)):
+            raise NotImplementedError("dense prompts other than the broadcast no-mask embedding are out of scope (prompt_encoder.py:182-184)")
+        out_dtype = sparse_prompt_embeddings.dtype
+        dev = image_embeddings.device
+        if B == 0:
+            return torch.zeros(0, 4, device=dev, dtype=out_dtype), torch.zeros(0, device=dev, dtype=out_dtype)
+        no_mask = d[0, :, 0, 0].to(torch.float32).contiguous()
+        N = G * G
+        emb = self._tokens_of(image_embeddings, torch.bfloat16)                       # [F,N,C]
+        pe = self._tokens_of(image_pe, torch.float32).reshape(N, C).contiguous()      # [N,C]
+        keys0 = torch.empty(Fr * N, C, device=dev, dtype=torch.bfloat16)
+        ops.add_rowvec_bf16(emb.reshape(Fr * N, C), no_mask, keys0)
+        text = sparse_prompt_embeddings.reshape(B, C).to(torch.float32)
+        out_tok = torch.cat([self.iou_token.weight, self.mask_tokens.weight], 0).to(torch.float32)
+        frame_of_all = torch.repeat_interleave(torch.arange(Fr), torch.tensor(reps)).to(torch.int32)
+        boxes = torch.empty(B, 4, device=dev, dtype=torch.float32)
+        logits = torch.empty(B, device=dev, dtype=torch.float32)
+        shared = self._layer0_shared(keys0, pe, N, C)
+        step = self.max_instances_per_pass
+        for s in range(0, B, step):
+            e = min(B, s + step)
+            tokens = torch.cat([out_tok.unsqueeze(0).expand(e - s, -1, -1), text[s:e].unsqueeze(1)], 1).contiguous()
+            b, l = self._decode(tokens, keys0, shared, pe, frame_of_all[s:e].to(dev), N, C)
+            boxes[s:e] = b
+            logits[s:e] = l
+        return boxes.to(out_dtype), logits.to(out_dtype)
+
+    # ------------------------------------------------------------------ the two-way transformer
+    def _pe_w(self, key, lin, pe):
+        """(pe . W^T) [N, internal] fp32 — the positional part of (keys + pe) W."""
+        w, _ = self._w32(key, lin)
+        return ops.small_linear(pe, w)
+
+    def _image_proj(self, key, lin, keys, pe, N):
+        """bf16 [rows, internal] = (keys (+pe)) W^T + b on the tcgen05 GEMM."""
+        w, b = self._w16(key, lin)
+        out = torch.empty(keys.shape[0], w.shape[0], device=keys.device, dtype=torch.bfloat16)
+        if pe is None:
+            return ops.gemm(keys, w, out, bias=b)
+        return ops.gemm(keys, w, out, bias=b, resid=self._pe_w(key, lin, pe), resid_row_mod=N)
+
+    def _layer0_shared(self, keys0, pe, N, C):
+        l0 = self.transformer.layers[0]
+        return {"k": self._image_proj("l0.t2i.k", l0.cross_attn_token_to_image.k_proj, keys0, pe, N),
+                "v": self._image_proj("l0.t2i.v", l0.cross_attn_token_to_image.v_proj, keys0, None, N),
+                "qi": self._image_proj("l0.i2t.q", l0.cross_attn_image_to_token.q_proj, keys0, pe, N)}
+
+    def _token_attn_out(self, key, attn, att, resid=None):
+        w, b = self._w32(key + ".o", attn.out_proj)
+        return ops.small_linear(att, w, b, resid=resid)
+
+    def _decode(self, tokens, keys0, shared, pe, frame_of, N, C):
+        tr = self.transformer
+        B, T, _ = tokens.shape
+        H = tr.num_heads
+        R = B * T
+        tok = tokens.reshape(R, C)
+        queries = tok
+        q_in = tok                           # queries + query_pe; layer 0 skips the PE (queries == tokens there)
+        keys, src_of = keys0, frame_of       # layer 0 reads the per-frame keys through the index
+        for li, layer in enumerate(tr.layers):
+            k = f"l{li}"
+            sa = layer.self_attn
+            # (1) token self-attention (transformer.py:155-161)
+            if layer.skip_first_layer_pe and li != 0:
+                raise NotImplementedError("skip_first_layer_pe is only meaningful on layer 0 (transformer.py:45-55)")
+            wq, bq = self._w32(k + ".sa.q", sa.q_proj); wk, bk = self._w32(k + ".sa.k", sa.k_proj); wv, bv = self._w32(k + ".sa.v", sa.v_proj)
+            q = ops.small_linear(q_in, wq, bq); kk = ops.small_linear(q_in, wk, bk); v = ops.small_linear(queries, wv, bv)
+            att = ops.token_self_attention(q, kk, v, B, T, H, sa.internal_dim // H)
+            o = self._token_attn_out(k + ".sa", sa, att)
+            g, b = self._ln(k + ".n1", layer.norm1)
+            queries, q_in = ops.add_layernorm(o, None if layer.skip_first_layer_pe else queries, g, b, eps=layer.norm1.eps, add2=tok)
+            # (2) token -> image cross attention (:164-169)
+            ca = layer.cross_attn_token_to_image
+            dh = ca.internal_dim // H
+            wq, bq = self._w32(k + ".t2i.q", ca.q_proj)
+            q = ops.small_linear(q_in, wq, bq)
+            if li == 0:
+                kp, vp = shared["k"], shared["v"]
+            else:
+                kp = self._image_proj(k + ".t2i.k", ca.k_proj, keys, pe, N)
+                vp = self._image_proj(k + ".t2i.v", ca.v_proj, keys, None, N)
+            att = ops.t2i_attention(q, kp, vp, src_of, B, T, N, H, dh).reshape(R, ca.internal_dim)
+            o = self._token_attn_out(k + ".t2i", ca, att)
+            g, b = self._ln(k + ".n2", layer.norm2)
+            queries = ops.add_layernorm(queries, o, g, b, eps=layer.norm2.eps)
+            # (3) MLP (:171-173)
+            w1, b1 = self._w32(k + ".m1", layer.mlp.lin1); w2, b2 = self._w32(k + ".m2", layer.mlp.lin2)
+            m = ops.small_linear(ops.small_linear(queries, w1, b1, act="relu"), w2, b2)
+            g, b = self._ln(k + ".n3", layer.norm3)
+            queries, q_in = ops.add_layernorm(queries, m, g, b, eps=layer.norm3.eps, add2=tok)
+            # (4) image -> token cross attention, updates the keys (:175-180)
+            ia = layer.cross_attn_image_to_token
+            wk, bk = self._w32(k + ".i2t.k", ia.k_proj); wv, bv = self._w32(k + ".i2t.v", ia.v_proj)
+            kt = ops.small_linear(q_in, wk, bk); vt = ops.small_linear(queries, wv, bv)
+            qi = shared["qi"] if li == 0 else self._image_proj(k + ".i2t.q", ia.q_proj, keys, pe, N)
+            ai = torch.empty(B * N, ia.internal_dim, device=tok.device, dtype=torch.bfloat16)
+            ops.i2t_attention(qi, kt, vt, src_of, ai, B, T, N, H, ia.internal_dim // H)
+            wo, bo = self._w16(k + ".i2t.o", ia.out_proj)
+            delta = torch.empty(B * N, C, device=tok.device, dtype=torch.float32)
+            ops.gemm(ai, wo, delta, bias=bo)
+            g, b = self._ln(k + ".n4", layer.norm4)
+            new_keys = torch.empty(B * N, C, device=tok.device, dtype=torch.bfloat16)
+            ops.keys_add_ln(keys, src_of, delta, g, b, new_keys, B, N, C, eps=layer.norm4.eps)
+            keys, src_of = new_keys, None
+            del delta, ai
+        # final token -> image attention (transformer.py:99-104)
+        fa = tr.final_attn_token_to_image
+        wq, bq = self._w32("f.q", fa.q_proj)
+        q = ops.small_linear(q_in, wq, bq)
+        kp = self._image_proj("f.k", fa.k_proj, keys, pe, N)
+        vp = self._image_proj("f.v", fa.v_proj, keys, None, N)
+        att = ops.t2i_attention(q, kp, vp, src_of, B, T, N, H, fa.internal_dim // H).reshape(R, fa.internal_dim)
+        o = self._token_attn_out("f", fa, att)
+        g, b = self._ln("f.n", tr.norm_final_attn)
+        hs = ops.add_layernorm(queries, o, g, b, eps=tr.norm_final_attn.eps)
+        # heads (mask_decoder.py:191-203): token index 1 + num_mask_tokens
+        qo = hs.view(B, T, C)[:, 1 + self.num_mask_tokens, :].contiguous()
+        w0, b0 = self._w32("h.0", self.bbox_prediction_head[0]); w2, b2 = self._w32("h.2", self.bbox_prediction_head[2])
+        boxes = ops.small_linear(ops.small_linear(qo, w0, b0, act="relu"), w2, b2, act="sigmoid")
+        if self.use_temp_objectness:
+            wt, bt = self._w32("h.t", self.temporal_objectness_head)
+            logits = ops.small_linear(qo, wt, bt).reshape(B)
+        else:
+            logits = torch.zeros(B, device=tok.device, dtype=torch.float32)
+        return boxes, logits

@@ -1,0 +1,142 @@
+/* grove_b200 — C ABI of the B200-native grounding path of GROVE (ekazakos/grove).
+ *
+ * The reference has no FFI: its boundary is the Python nn.Module API of model/SAM/modeling/*.py and the
+ * grounding methods of model/GROVE.py.  grove_b200/modeling/*.py mirrors that API and
+ * lowers every call onto the entry points below through ctypes (grove_b200/_lib.py); INTEGRATION.md
+ * shows the binding a reference maintainer would add.  Conventions:
+ *   - plain device pointers + sizes, no framework types; every function returns 0 on success or a
+ *     GROVE_ERR_* code, with a message retrievable from grove_last_error();
+ *   - no allocation inside: callers pass outputs and workspaces; all work is enqueued on `stream`;
+ *   - "bf16" = __nv_bfloat16 bits; token-major activations are [frames * G*G, channels] (NHWC).
+ * Each entry cites the reference code it replaces (file:line under the reference root).
+ */
+#ifndef GROVE_B200_H_
+#define GROVE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__CUDACC__) || defined(__CUDA_RUNTIME_H__)
+typedef cudaStream_t grove_stream_t;
+#else
+typedef void* grove_stream_t;
+#endif
+
+#define GROVE_B200_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int grove_abi_version(void);
+const char* grove_last_error(void);
+/* kernels launched by this library since the last reset (bench.py's gpu_launches) */
+long long grove_launch_count(void);
+void grove_reset_launch_count(void);
+
+/* ---- dense contractions on tcgen05 (gemm_tcgen05.cu) ------------------------------------------ */
+typedef struct grove_gemm_epilogue {
+  const float* bias;       /* [N] fp32 or NULL */
+  const float* resid;      /* fp32 [*, N] or NULL (may alias an fp32 `out`: in-place residual stream) */
+  int resid_row_mod;       /* >0: residual row = m % resid_row_mod (abs-pos embedding, image_encoder.py:176-177) */
+  const float* gate_alpha; /* non-NULL: multiply by tanh(*gate_alpha) (adapter gate, image_encoder.py:45,54) */
+  int act;                 /* 0 none | 1 exact-erf GELU (common.py:18) | 2 ReLU */
+  int out_f32;             /* 1: `out` is fp32, 0: bf16 */
+  void* out2_bf16;         /* optional second, bf16 copy of the output, or NULL */
+  int max_ctas;            /* 0 = one persistent CTA per SM; >0 caps the grid (tests) */
+} grove_gemm_epilogue;
+
+/* out[M,N] = resid + gate * act(A[M,K] . W[N,K]^T + bias).  A, W bf16 row-major (nn.Linear layout).
+ * Replaces nn.Linear / 1x1 conv calls: image_encoder.py:304 (qkv), :324 (proj), common.py:25-26 (MLP),
+ * image_encoder.py:484-491 (patch embed after grove_im2col_patch16), :153-158 (neck 1x1),
+ * GROVE.py:77-79 (text_hidden_fcs), transformer.py:205-208,227-229 (decoder projections).
+ * Requires N % 128 == 0, K % 8 == 0, 16-byte aligned pointers. */
+int grove_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int K, const grove_gemm_epilogue* epi,
+                    grove_stream_t stream);
+
+/* Implicit-GEMM 'same' convolution over token-major X[V,T,G,G,C] (bf16): kt=3 -> Conv3d 3x3x3
+ * (SpatioTemporalConvAdapter, image_encoder.py:40-59), kt=1 -> Conv2d 3x3 pad 1 (neck, image_encoder.py:160-166).
+ * Wp[N, taps*C] is the weight repacked tap-major ((kd,)kh,kw,C).  out[V*T*G*G, N] with the same epilogue. */
+int grove_conv_gemm_bf16(const void* X, const void* Wp, void* out, int V, int T, int G, int C, int N, int kt,
+                         const grove_gemm_epilogue* epi, grove_stream_t stream);
+
+/* ---- encoder element-wise / attention kernels (encoder_ops.cu, attention.cu) ------------------- */
+/* images[V,3,T,H,W] bf16 ('b c t h w', GROVE.py:162) -> patches[(V*T)*(H/16)*(W/16), 768], k=(c,py,px)
+ * (the im2col of PatchEmbed's Conv2d 16x16 stride 16, image_encoder.py:484-491). */
+int grove_im2col_patch16(const void* images, void* patches, int V, int T, int H, int W, grove_stream_t stream);
+/* y = LayerNorm(x) over the last dim D (image_encoder.py:245,257 eps 1e-6; common.py:31-43 as token-major rows).
+ * x fp32 [rows,D]; y bf16 or fp32 [rows,D]; gamma/beta fp32.  D % 128 == 0, D <= 1280. */
+int grove_layernorm(const float* x, const float* gamma, const float* beta, void* y, int y_f32, int rows, int D, float eps,
+                    grove_stream_t stream);
+/* Windowed attention with decomposed rel-pos bias on the UNPARTITIONED token-major qkv[F,G,G,3,heads,hd]
+ * (bf16): window_partition's zero padding after norm1 (image_encoder.py:245-249,344-348) is reproduced by
+ * giving pad tokens k = b_k, v = b_v (qkv_bias, bf16) — they receive softmax mass like in the reference —
+ * and window_unpartition's crop (:382-383) by not computing pad queries.  rel_pos_h/w: [2*ws-1, hd] bf16.
+ * out[F,G,G,heads*hd] bf16.  Replaces Attention.forward :301-326 + add_decomposed_rel_pos :420-458. */
+int grove_attn_window_relpos_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w,
+                                 void* out, int F, int G, int heads, int hd, int ws, grove_stream_t stream);
+/* Global attention over one frame's G*G tokens with decomposed rel-pos bias (tables [2G-1, hd] bf16). */
+int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
+                                 int heads, int hd, grove_stream_t stream);
+/* fp32 -> bf16 cast (n % 8 == 0) and token-major [F,N,C] bf16 -> NCHW [F,C,N] transposition helpers */
+int grove_cast_f32_bf16(const float* x, void* y, long long n, grove_stream_t stream);
+int grove_tokens_to_nchw_bf16(const void* tok, void* nchw, int F, int N, int C, grove_stream_t stream);
+int grove_nchw_to_tokens_bf16(const void* nchw, void* tok, int F, int N, int C, grove_stream_t stream);
+
+/* ---- text projection / prompt encoder / box decoder (decoder_ops.cu) --------------------------- */
+/* dst[i,:] = bf16(src[row_idx[i],:]) — gathers the [DET] rows BEFORE projecting them (GROVE.py:249-257 projects all
+ * L tokens and gathers afterwards; identical values for the kept rows, L/P times less work). */
+int grove_gather_rows_bf16(const void* src, int src_is_f32, const int* row_idx, void* dst, int n_rows, int D, grove_stream_t stream);
+/* PositionEmbeddingRandom.forward (prompt_encoder.py:203-229): pe[G*G, 2*F2] fp32 token-major, gauss [2,F2] fp32. */
+int grove_dense_pe(const float* gauss, float* pe, int G, int F2, grove_stream_t stream);
+/* y[r,:] = bf16(x[r,:] + vec[:]) — src = image_embeddings + dense no-mask embedding (mask_decoder.py:183,
+ * prompt_encoder.py:182-184), done once per FRAME: keys only become per-phrase after the first image-to-token update. */
+int grove_add_rowvec_bf16(const void* x, const float* vec, void* y, long long rows, int C, grove_stream_t stream);
+/* Token-to-image attention (transformer.py:231-240 inside cross_attn_token_to_image / final_attn_token_to_image):
+ * q fp32 [B,T,H*dh] (already projected), k,v bf16 [*,N,H*dh] (projected keys; instance b reads row block src_of[b],
+ * or b when src_of is NULL), out fp32 [B,T,H*dh] (before out_proj).  Built for T=6, dh=16. */
+int grove_decoder_t2i_attention(const float* q, const void* k, const void* v, const int* src_of, float* out, int B, int T, int N,
+                                int heads, int dh, grove_stream_t stream);
+/* Image-to-token attention (cross_attn_image_to_token, transformer.py:173-179): qi bf16 [*,N,H*dh] = q_proj(keys+pe),
+ * kt, vt fp32 [B,T,H*dh]; out bf16 [B,N,H*dh] (before out_proj). */
+int grove_decoder_i2t_attention(const void* qi, const float* kt, const float* vt, const int* src_of, void* out, int B, int T, int N,
+                                int heads, int dh, grove_stream_t stream);
+/* keys_out[b,n,:] = bf16(LayerNorm(keys_in[src_of[b],n,:] + delta[b,n,:]))  (norm4, transformer.py:180), C = 256. */
+int grove_decoder_keys_add_ln(const void* keys_in, const int* src_of, const float* delta, const float* g, const float* b, void* keys_out,
+                              int B, int N, int C, float eps, grove_stream_t stream);
+/* Token-side dense layer, all fp32: y[R,N] = act(x[R,K] . W[N,K]^T + b) (+ resid).  act: 0 none, 1 GELU, 2 ReLU, 3 sigmoid.
+ * (6-token projections / MLP of transformer.py:151-182, heads mask_decoder.py:80-85,198-203, PE.W products.) */
+int grove_small_linear_f32(const float* x, const float* W, const float* b, const float* resid, float* y, int R, int N, int K, int act,
+                           grove_stream_t stream);
+/* Self-attention among T <= 8 tokens (transformer.py:155-161): q,k,v,out fp32 [B,T,H*dh]. */
+int grove_token_self_attention(const float* q, const float* k, const float* v, float* out, int B, int T, int heads, int dh,
+                               grove_stream_t stream);
+/* y = LN(x (+ r)) rows of fp32 [R,C] (norm1-3, norm_final_attn; eps 1e-5); optional y2 = y + add2. */
+int grove_add_layernorm_f32(const float* x, const float* r, const float* g, const float* b, float* y, const float* add2, float* y2,
+                            int R, int C, float eps, grove_stream_t stream);
+
+/* ---- heads post-process, losses, box-IoU utilities (box_ops.cu) -------------------------------- */
+/* (cx,cy,w,h) in (0,1) -> scale by the video's (w,h) -> xyxy; keep = sigmoid(logit) > thr
+ * (GROVE.py:307-315, utils/bbox_utils.py:25-62).  size_wh fp32 [B,2] per box. */
+int grove_box_postprocess(const float* boxes, const float* logits, const float* size_wh, float thr, float* xyxy, uint8_t* keep, int B,
+                          grove_stream_t stream);
+/* Sums for _compute_loss_components_video (GROVE.py:339-381): sel[b] marks predictions that have a GT box gt[b]
+ * (cxcywh); labels[b] = objectness target.  sums[0..2] = sum GIoU loss (torchvision arithmetic, eps 1e-7), sum L1,
+ * sum BCE-with-logits. */
+int grove_box_losses_fwd(const float* boxes, const float* logits, const float* gt, const uint8_t* sel, const float* labels, float* sums,
+                         int B, grove_stream_t stream);
+/* IoU matrix out[n,m] of a[n, lda>=4] vs b[m, ldb>=4] (xyxy in the first 4 columns), fp64 when f64 != 0 else fp32,
+ * bit-exact with the reference's numpy / torch arithmetic:
+ *   mode 0: eval_vidstg.py:13-63 np_box_iou (no +1);  mode 1: eval_iground.py:39-56 compute_iou (+1, 0.0 on empty union);
+ *   mode 2: eval_anet.py:22-119 bbox_overlaps_batch 3-D branch (+1, frm_mask[n,m] 1 = different frame (may be NULL),
+ *           zero-area gt -> 0, zero-area anchor -> -1). */
+int grove_box_iou(const void* a, int lda, const void* b, int ldb, const uint8_t* frm_mask, void* out, int n, int m, int mode, int f64,
+                  grove_stream_t stream);
+/* Greedy one-to-one matching (eval_iground.py:85-96): iou, sim fp64 [n,m] (clobbered); pairs int32 [min(n,m),2]; count int32[1]. */
+int grove_greedy_match(double* iou, double* sim, double iou_thr, double sim_thr, int* pairs, int* count, int n, int m,
+                       grove_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GROVE_B200_H_ */

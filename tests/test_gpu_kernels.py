@@ -1,0 +1,185 @@
+"""Per-kernel parity on a B200: each C-ABI entry point against a plain fp32 PyTorch / oracle statement of the same op."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import grounding as og  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from grove_b200 import ops as _ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return _ops
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-12))
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K,max_ctas", [(128, 128, 64, 0), (256, 256, 128, 0), (1000, 768, 768, 0), (4096, 2304, 768, 7),
+                                            (8192, 3072, 768, 0), (4096, 768, 3072, 5), (300, 256, 4096, 0), (32768, 128, 256, 0)])
+def test_gemm_plain(ops, M, N, K, max_ctas):
+    a, w = _rand((M, K), 1, dtype=torch.bfloat16), _rand((N, K), 2, 1 / math.sqrt(K), dtype=torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    ops.gemm(a, w, out, max_ctas=max_ctas)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    assert _relerr(out, ref) < 2e-5, _relerr(out, ref)
+
+
+def test_gemm_epilogues(ops):
+    M, N, K = 1536, 768, 768
+    a, w = _rand((M, K), 3, dtype=torch.bfloat16), _rand((N, K), 4, 1 / math.sqrt(K), dtype=torch.bfloat16)
+    bias, resid = _rand((N,), 5), _rand((M, N), 6)
+    ref = a.float() @ w.float().t() + bias
+    # bias + GELU -> bf16
+    o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, o, bias=bias, act="gelu")
+    assert _relerr(o.float(), F.gelu(ref)) < 6e-3
+    # bias + in-place fp32 residual + bf16 side copy
+    x = resid.clone()
+    o2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, x, bias=bias, resid=x, out2=o2)
+    assert _relerr(x, resid + ref) < 2e-5
+    assert torch.equal(o2, x.to(torch.bfloat16))
+    # row-periodic residual (abs-pos embedding), relu, tanh gate
+    pos, alpha = _rand((512, N), 7), torch.tensor([0.5], device="cuda")
+    o3 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, w, o3, bias=bias, act="relu", gate_alpha=alpha, resid=pos, resid_row_mod=512)
+    ref3 = pos.repeat(3, 1) + math.tanh(0.5) * F.relu(ref)
+    assert _relerr(o3, ref3) < 2e-5
+
+
+@pytest.mark.parametrize("V,T,G,C,N,kt", [(1, 8, 64, 128, 256, 3), (2, 8, 32, 64, 128, 3), (3, 1, 64, 256, 256, 1), (1, 8, 16, 64, 128, 3)])
+def test_conv_implicit_gemm(ops, V, T, G, C, N, kt):
+    x = _rand((V, T, G, G, C), 8, dtype=torch.bfloat16)
+    bias = _rand((N,), 10)
+    if kt == 3:
+        w = _rand((N, C, 3, 3, 3), 9, 1 / math.sqrt(27 * C), dtype=torch.bfloat16)
+        wp = w.permute(0, 2, 3, 4, 1).reshape(N, -1).contiguous()
+        ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float(), bias, padding=1).permute(0, 2, 3, 4, 1).reshape(-1, N)
+    else:
+        w = _rand((N, C, 3, 3), 9, 1 / math.sqrt(9 * C), dtype=torch.bfloat16)
+        wp = w.permute(0, 2, 3, 1).reshape(N, -1).contiguous()
+        ref = F.conv2d(x.float().reshape(V * T, G, G, C).permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    out = torch.empty(V * T * G * G, N, device="cuda", dtype=torch.float32)
+    ops.conv_gemm(x, wp, out, V=V, T=T, G=G, kt=kt, bias=bias)
+    assert _relerr(out, ref) < 3e-5, _relerr(out, ref)
+
+
+# ------------------------------------------------------------------ HBM-bound encoder helpers
+def test_im2col_layernorm_transposes(ops):
+    img = _rand((2, 3, 8, 64, 64), 11, dtype=torch.bfloat16)
+    out = torch.empty(16 * 16, 768, device="cuda", dtype=torch.bfloat16)
+    ops.im2col_patch16(img, out)
+    fr = img.permute(0, 2, 1, 3, 4).reshape(16, 3, 64, 64)
+    ref = F.unfold(fr.float(), 16, stride=16).transpose(1, 2).reshape(-1, 768).to(torch.bfloat16)
+    assert torch.equal(out, ref)
+    for D in (256, 768, 1024, 1280):
+        x, g, b = _rand((1000, D), 12, 3.0) + 0.7, _rand((D,), 13) + 1.0, _rand((D,), 14)
+        y32 = torch.empty_like(x)
+        ops.layernorm(x, g, b, y32, 1e-6)
+        assert _relerr(y32, F.layer_norm(x, (D,), g, b, 1e-6)) < 1e-5
+        y16 = torch.empty(1000, D, device="cuda", dtype=torch.bfloat16)
+        ops.layernorm(x, g, b, y16, 1e-6)
+        assert _relerr(y16.float(), F.layer_norm(x, (D,), g, b, 1e-6)) < 5e-3
+    t = _rand((3, 1024, 256), 15, dtype=torch.bfloat16)
+    nchw = torch.empty(3, 256, 1024, device="cuda", dtype=torch.bfloat16)
+    ops.tokens_to_nchw(t, nchw, 3, 1024, 256)
+    assert torch.equal(nchw, t.transpose(1, 2).contiguous())
+    back = torch.empty_like(t)
+    ops.nchw_to_tokens(nchw, back, 3, 1024, 256)
+    assert torch.equal(back, t)
+
+
+# ------------------------------------------------------------------ attention with decomposed rel-pos bias
+def _ref_attention(qkv, rel_h, rel_w, B, S, heads, hd):
+    """Attention.forward without qkv/proj linears (image_encoder.py:306-323), fp32, on [B,S,S,3,heads,hd]."""
+    q, k, v = qkv.float().reshape(B, S * S, 3, heads, hd).permute(2, 0, 3, 1, 4).reshape(3, B * heads, S * S, hd).unbind(0)
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    Rh, Rw = og.rel_pos_table(S, rel_h.float()), og.rel_pos_table(S, rel_w.float())
+    rq = q.reshape(B * heads, S, S, hd)
+    attn = (attn.view(B * heads, S, S, S, S) + torch.einsum("bhwc,hkc->bhwk", rq, Rh)[..., :, None]
+            + torch.einsum("bhwc,wkc->bhwk", rq, Rw)[..., None, :]).view(B * heads, S * S, S * S)
+    o = attn.softmax(-1) @ v
+    return o.view(B, heads, S, S, hd).permute(0, 2, 3, 1, 4).reshape(B, S, S, heads * hd)
+
+
+@pytest.mark.parametrize("G,Fr,heads", [(64, 2, 3), (32, 3, 2)])
+def test_global_attention(ops, G, Fr, heads):
+    hd = 64
+    qkv = _rand((Fr, G, G, 3, heads, hd), 20, dtype=torch.bfloat16)
+    rh, rw = _rand((2 * G - 1, hd), 21, 0.1, dtype=torch.bfloat16), _rand((2 * G - 1, hd), 22, 0.1, dtype=torch.bfloat16)
+    out = torch.full((Fr, G, G, heads * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attn_global(qkv, rh, rw, out, F=Fr, G=G, heads=heads, hd=hd)
+    ref = _ref_attention(qkv, rh, rw, Fr, G, heads, hd)
+    err = float((out.float() - ref).abs().max())
+    assert err < 2e-2, err          # bf16 P and bf16 output on O(1) values
+    assert float((out.float() - ref).abs().mean()) < 2e-3
+
+
+@pytest.mark.parametrize("G,Fr,heads", [(64, 2, 2), (32, 1, 3), (28, 1, 1)])
+def test_window_attention_with_padding(ops, G, Fr, heads):
+    hd, ws = 64, 14
+    D = heads * hd
+    qkv_bias = _rand((3 * D,), 23, 0.5)
+    qkv = _rand((Fr, G, G, 3, heads, hd), 24, dtype=torch.bfloat16)
+    rh, rw = _rand((2 * ws - 1, hd), 25, 0.1, dtype=torch.bfloat16), _rand((2 * ws - 1, hd), 26, 0.1, dtype=torch.bfloat16)
+    out = torch.full((Fr, G, G, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attn_window(qkv, qkv_bias.to(torch.bfloat16), rh, rw, out, F=Fr, G=G, heads=heads, hd=hd, ws=ws)
+    # reference: pad tokens carry qkv = bias (x = 0 after norm1, image_encoder.py:245-249); partition, attend, unpartition
+    Gp = ((G + ws - 1) // ws) * ws
+    full = qkv_bias.to(torch.bfloat16).float().view(1, 1, 1, 3 * D).expand(Fr, Gp, Gp, 3 * D).clone()
+    full[:, :G, :G] = qkv.float().reshape(Fr, G, G, 3 * D)
+    win, pad_hw = og.window_partition(full, ws)
+    o = _ref_attention(win.reshape(-1, ws, ws, 3, heads, hd), rh, rw, win.shape[0], ws, heads, hd)
+    ref = og.window_unpartition(o, ws, pad_hw, (G, G))
+    err = float((out.float() - ref).abs().max())
+    assert err < 2e-2, err
+    assert float((out.float() - ref).abs().mean()) < 2e-3
+
+
+# ------------------------------------------------------------------ box utilities: bit-exact decisions
+def test_box_utilities_bit_exact(ops):
+    from conftest import GOLDEN
+    import os
+    from grove_b200 import box_eval as be
+    g = np.load(os.path.join(GOLDEN, "box_eval.npz"))
+    assert np.array_equal(be.np_box_iou(g["b1"], g["b2"]), g["iou64"], equal_nan=True)
+    assert np.array_equal(be.np_box_iou(g["b1"].astype(np.float32), g["b2"].astype(np.float32)), g["iou32"], equal_nan=True)
+    mat = be.compute_iou_matrix(g["p1"].tolist(), g["p2"].tolist())
+    assert np.array_equal(mat, g["mat"])
+    assert np.array_equal(np.array(be.greedy_matches(mat, g["sims"], 0.3, 0.2), dtype=np.int64).reshape(-1, 2), g["matches"])
+    assert np.array_equal(be.bbox_overlaps_batch(g["anc"], g["gtb"], g["frm"]).numpy(), g["ov"])
+    assert np.array_equal(be.bbox_overlaps_batch(g["anc"], g["gtb"], np.zeros_like(g["frm"])).numpy(), g["ov_nomask"])
+    # larger random problem against the oracle port, incl. threshold decisions
+    from oracle import box_eval as ob
+    rng = np.random.default_rng(0)
+    xy = rng.uniform(0, 100, (200, 2)); a = np.concatenate([xy, xy + rng.uniform(0, 60, (200, 2))], 1)
+    xy = rng.uniform(0, 100, (150, 2)); b = np.concatenate([xy, xy + rng.uniform(0, 60, (150, 2))], 1)
+    assert np.array_equal(be.np_box_iou(a, b), ob.np_box_iou(a, b))
+    assert np.array_equal(be.compute_iou_matrix(np.round(a), np.round(b)), ob.compute_iou_matrix(np.round(a), np.round(b)))
+    iou = ob.compute_iou_matrix(np.round(a[:40]), np.round(b[:30])); sim = rng.uniform(0, 1, iou.shape)
+    assert be.greedy_matches(iou, sim, 0.1, 0.3) == ob.greedy_match(iou, sim, 0.1, 0.3)
+    # post-process decisions: sigmoid(logit) > thr on a grid that straddles the threshold
+    logits = torch.cat([torch.linspace(-3, 3, 4001), torch.tensor([0.0, 1e-8, -1e-8, 1e-4, -1e-4])]).cuda()
+    boxes = torch.rand(logits.numel(), 4, device="cuda")
+    size = torch.tensor([[1280.0, 720.0]], device="cuda").expand(logits.numel(), 2).contiguous()
+    for thr in (0.5, 0.3, 0.7):
+        xyxy, keep = ops.box_postprocess(boxes, logits, size, thr)
+        assert torch.equal(keep.bool(), torch.sigmoid(logits) > thr)
+        ref = og.box_cxcywh_to_xyxy(og.unnormalize_bboxes(boxes, 1280.0, 720.0))
+        assert torch.equal(xyxy, ref)
