@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libgrove_b200.so")
 class GemmEpilogue(C.Structure):
     """mirror of `struct grove_gemm_epilogue`"""
     _fields_ = [("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_row_mod", C.c_int), ("gate_alpha", C.c_void_p),
-                ("act", C.c_int), ("out_f32", C.c_int), ("out2_bf16", C.c_void_p), ("max_ctas", C.c_int)]
+                ("act", C.c_int), ("out_f32", C.c_int), ("out2_bf16", C.c_void_p), ("max_ctas", C.c_int), ("force_ctas", C.c_int)]
 
 
 _P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double

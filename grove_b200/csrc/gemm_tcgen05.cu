@@ -36,24 +36,32 @@ struct GemmParams {
   __nv_bfloat16* out2; // optional extra bf16 copy of the output (feeds the next tensor-core op)
 };
 
-template <int BN>
+// CTAS = 1: one CTA owns a 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns a 256 x BN tile —
+// each CTA stages its own 128 A rows and HALF of the B tile (BN/2 rows), the leader issues UMMA 256 x BN x 16 that reads both
+// CTAs' shared memory, and each CTA keeps its 128 accumulator rows in its own TMEM.  Per CTA and k-block that is 32 KB of
+// L2->smem traffic instead of 48 KB for the same MMA work: these GEMMs are L2-bandwidth bound, not MMA bound.
+template <int BN, int CTAS>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBRows = BN / CTAS;           // B rows staged by one CTA
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two: 256 or 512)
+  static constexpr int kStageRowF = 68;              // epilogue staging: 32 rows x 64 fp32 columns per warp, padded row
+  static constexpr int kEpiBytes = 4 * 32 * kStageRowF * 4;
+  static constexpr int kStages = (200 * 1024 - kEpiBytes) / kStageBytes > 6 ? 6 : (200 * 1024 - kEpiBytes) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;           // two accumulator stages (power of two: 256 or 512)
 };
 
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem base slot
+  const uint32_t epi_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = epi_base + Cfg::kEpiBytes;
+  // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
@@ -62,7 +70,10 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;   // m-blocks of 128*CTAS rows
+  const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -73,26 +84,28 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), 4 * CTAS);   // one arrival per epilogue warp of every CTA in the pair
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols); tmem_relinquish_cg2(); }
+    else           { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one thread per CTA) =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = (tile / p.num_n_blocks) * CTAS + (int)cta_rank;   // this CTA's 128-row block
+        const int n_blk = tile % p.num_n_blocks;
         int f = 0, h0 = 0;
         if (p.conv) {
           f = m_blk / p.tiles_per_frame;
@@ -102,129 +115,191 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          if (!p.conv) {
-            tma_load_2d(sa, &tmap_a, full_bar(s), kb * BK, m_blk * BM);
+          const int brow = n_blk * BN + (int)cta_rank * Cfg::kBRows;
+          if (CTAS == 1) {
+            mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+            if (!p.conv) {
+              tma_load_2d(sa, &tmap_a, full_bar(s), kb * BK, m_blk * BM);
+            } else {
+              const int tap = kb / p.kc_blocks, c0 = (kb % p.kc_blocks) * BK;
+              int dt = 0, dh, dw;
+              if (p.kt == 3) { dt = tap / 9 - 1; dh = (tap / 3) % 3 - 1; dw = tap % 3 - 1; }
+              else           { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+              tma_load_5d(sa, &tmap_a, full_bar(s), c0, dw, h0 + dh, (f % p.T) + dt, f / p.T);
+            }
+            tma_load_2d(sb, &tmap_b, full_bar(s), kb * BK, brow);
           } else {
-            const int tap = kb / p.kc_blocks, c0 = (kb % p.kc_blocks) * BK;
-            int dt = 0, dh, dw;
-            if (p.kt == 3) { dt = tap / 9 - 1; dh = (tap / 3) % 3 - 1; dw = tap % 3 - 1; }
-            else           { dh = tap / 3 - 1; dw = tap % 3 - 1; }
-            tma_load_5d(sa, &tmap_a, full_bar(s), c0, dw, h0 + dh, (f % p.T) + dt, f / p.T);
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
+            if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
+            if (!p.conv) {
+              tma_load_2d_cg2(sa, &tmap_a, full_bar(s), kb * BK, m_blk * BM);
+            } else {
+              const int tap = kb / p.kc_blocks, c0 = (kb % p.kc_blocks) * BK;
+              int dt = 0, dh, dw;
+              if (p.kt == 3) { dt = tap / 9 - 1; dh = (tap / 3) % 3 - 1; dw = tap % 3 - 1; }
+              else           { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+              tma_load_5d_cg2(sa, &tmap_a, full_bar(s), c0, dw, h0 + dh, (f % p.T) + dt, f / p.T);
+            }
+            tma_load_2d_cg2(sb, &tmap_b, full_bar(s), kb * BK, brow);
           }
-          tma_load_2d(sb, &tmap_b, full_bar(s), kb * BK, n_blk * BN);
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-    uint32_t it = 0, tile_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
-      mbar_wait(tempty_bar(acc), acc_ph ^ 1u);  // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
-        const int s = it % Cfg::kStages;
-        const uint32_t ph = (it / Cfg::kStages) & 1u;
-        mbar_wait(full_bar(s), ph);
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN);
+      uint32_t it = 0, tile_it = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
+        const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);  // epilogues (of both CTAs) have drained this accumulator
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+            const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * 32);
-            const uint64_t db = umma_desc_sw128(sb + k * 32);
-            tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = umma_desc_sw128(sa + k * 32);
+              const uint64_t db = umma_desc_sw128(sb + k * 32);
+              if (CTAS == 2) tc_mma_f16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
+              else           tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
+            }
+            if (CTAS == 2) {
+              tc_commit_cg2(empty_bar(s), 3);                                   // frees the slot in both CTAs
+              if (kb == p.num_k_blocks - 1) tc_commit_cg2(tfull_bar(acc), 3);   // accumulators complete in both CTAs
+            } else {
+              tc_commit(empty_bar(s));
+              if (kb == p.num_k_blocks - 1) tc_commit(tfull_bar(acc));
+            }
           }
-          tc_commit(empty_bar(s));                                   // smem slot free once these MMAs retire
-          if (kb == p.num_k_blocks - 1) tc_commit(tfull_bar(acc));   // accumulator complete
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const float gate = p.gate_alpha ? tanhf(__ldg(p.gate_alpha)) : 1.0f;
+    const uint32_t stg = epi_base + quad * (32 * Cfg::kStageRowF * 4);
     uint32_t tile_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-      const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
+      const int m_blk = (tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
       const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
-      const int row = m_blk * BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-      const size_t out_off = (size_t)row * p.N;
-      const float* resid_row = nullptr;
-      if (p.resid) resid_row = p.resid + (size_t)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.N;
+      const int row_base = m_blk * BM + quad * 32;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + acc * BN + ch * 32 + ((uint32_t)(quad * 32) << 16), r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + ch * 32;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
+      for (int ch = 0; ch < BN / 64; ++ch) {
+        {
+          uint32_t r0[32], r1[32];
+          const uint32_t taddr = tmem_base + acc * BN + ch * 64 + ((uint32_t)(quad * 32) << 16);
+          tmem_ld_32x32b_x32(taddr, r0);
+          tmem_ld_32x32b_x32(taddr + 32, r1);
+          tmem_ld_wait();
+          const uint32_t wrow = stg + lane * (Cfg::kStageRowF * 4);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + j * 4), "r"(r0[j]), "r"(r0[j + 1]), "r"(r0[j + 2]), "r"(r0[j + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + 128 + j * 4), "r"(r1[j]), "r"(r1[j + 1]), "r"(r1[j + 2]), "r"(r1[j + 3]) : "memory");
           }
         }
-        if (p.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (p.act == 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        if (p.gate_alpha) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gate;
-        }
-        if (row_ok) {
-          if (resid_row) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(resid_row + col0 + j);
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        __syncwarp();
+        const int col0 = n_blk * BN + ch * 64;
+        if (p.out_f32) {
+          // 16 lanes x float4 cover one 64-column row segment (256 B); two rows per instruction
+          const int c = (lane & 15) * 4;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int rl = 2 * i + (lane >> 4);
+            const int row = row_base + rl;
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stg + (rl * Cfg::kStageRowF + c) * 4));
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if (p.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+            else if (p.act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (p.gate_alpha) { v.x *= gate; v.y *= gate; v.z *= gate; v.w *= gate; }
+            if (row < p.M) {
+              if (p.resid) {
+                const size_t rr = (size_t)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.N;
+                const float4 b = *reinterpret_cast<const float4*>(p.resid + rr + col0 + c);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              const size_t o = (size_t)row * p.N + col0 + c;
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = v;
+              if (p.out2) *reinterpret_cast<uint2*>(p.out2 + o) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
             }
           }
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + out_off + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                                            pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+        } else {
+          // 8 lanes x 8 columns (16 B of bf16) cover one 64-column row segment (128 B); four rows per instruction
+          const int c = (lane & 7) * 8;
+          float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+          if (p.bias) {
+            ba = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));
+            bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + 4));
           }
-          if (p.out2) {
-            __nv_bfloat16* o = p.out2 + out_off + col0;
+#pragma unroll 4
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + (lane >> 3);
+            const int row = row_base + rl;
+            float4 u, w;
+            const uint32_t a = stg + (rl * Cfg::kStageRowF + c) * 4;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(u.x), "=f"(u.y), "=f"(u.z), "=f"(u.w) : "r"(a));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(a + 16));
+            float v[8] = {u.x + ba.x, u.y + ba.y, u.z + ba.z, u.w + ba.w, w.x + bb.x, w.y + bb.y, w.z + bb.z, w.w + bb.w};
+            if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                                            pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+            } else if (p.act == 2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.gate_alpha) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= gate;
+            }
+            if (row < p.M) {
+              if (p.resid) {
+                const size_t rr = (size_t)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.N;
+                const float4 x0 = *reinterpret_cast<const float4*>(p.resid + rr + col0 + c);
+                const float4 x1 = *reinterpret_cast<const float4*>(p.resid + rr + col0 + c + 4);
+                v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w; v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
+              }
+              const size_t o = (size_t)row * p.N + col0 + c;
+              const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pk;
+              if (p.out2) *reinterpret_cast<uint4*>(p.out2 + o) = pk;
+            }
           }
         }
+        __syncwarp();   // staging buffer is reused by the next 64-column pass
       }
+      // accumulator drained (all tcgen05.ld of this warp completed before the smem staging): release it to the MMA warp
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (CTAS == 2) cluster_sync_all();   // the peer may still multicast into / read from this CTA's shared memory
+  if (warp == 1) {
+    if (CTAS == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------ host side: tensor maps
@@ -275,22 +350,54 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch_gemm(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb, int max_ctas, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
     attr_set = true;
   }
-  int grid = p.num_m_blocks * p.num_n_blocks;
+  int grid = p.num_m_blocks * p.num_n_blocks * CTAS;
   int cap = max_ctas > 0 ? max_ctas : num_sms();
+  cap -= cap % CTAS;
+  if (cap < CTAS) cap = CTAS;
   if (grid > cap) grid = cap;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(p, ta, tb);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS>, p, ta, tb);
   grove_count_launch();
+  if (e != cudaSuccess) { grove_set_error("gemm launch failed: %s", cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
+}
+
+// tile configuration: CTA pairs (256 x 256 tiles) whenever the problem has them, else single-CTA 128 x {256,128} tiles
+static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K_total, int N, int M, bool conv, const uint64_t* adims,
+                         const uint32_t* abox, int arank, int max_ctas, int force_ctas, cudaStream_t st) {
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  int ctas = (BN == 256 && M >= 256) ? 2 : 1;
+  if (force_ctas == 1 || force_ctas == 2) ctas = (force_ctas == 2 && BN == 256) ? 2 : 1;
+  p.num_m_blocks = (M + BM * ctas - 1) / (BM * ctas);
+  p.num_n_blocks = N / BN;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_bf16(&ta, A_or_X, arank, adims, abox))) return rc;
+  uint64_t db[2] = {(uint64_t)K_total, (uint64_t)N};
+  uint32_t bb[2] = {BK, (uint32_t)(BN / ctas)};
+  if ((rc = make_tmap_bf16(&tb, W, 2, db, bb))) return rc;
+  (void)conv;
+  if (ctas == 2) return launch_gemm<256, 2>(p, ta, tb, max_ctas, st);
+  return BN == 256 ? launch_gemm<256, 1>(p, ta, tb, max_ctas, st) : launch_gemm<128, 1>(p, ta, tb, max_ctas, st);
 }
 
 }  // namespace grove
@@ -316,25 +423,16 @@ extern "C" int grove_gemm_bf16(const void* A, const void* W, void* out, int M, i
   GROVE_CHECK_ARG(A && W && out && M > 0 && N > 0 && K > 0);
   GROVE_CHECK_ARG(N % 128 == 0 && K % 8 == 0);
   GROVE_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)out & 15) == 0);
-  const int BN = (N % 256 == 0) ? 256 : 128;
   GemmParams p{};
   p.M = M; p.N = N;
-  p.num_m_blocks = (M + BM - 1) / BM;
-  p.num_n_blocks = N / BN;
   p.num_k_blocks = (K + BK - 1) / BK;
   p.conv = 0;
   p.out = out;
   int rc = fill_epilogue(p, epi, M, N);
   if (rc) return rc;
-  CUtensorMap ta, tb;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
   uint32_t ba[2] = {BK, BM};
-  if ((rc = make_tmap_bf16(&ta, A, 2, da, ba))) return rc;
-  uint64_t db[2] = {(uint64_t)K, (uint64_t)N};
-  uint32_t bb[2] = {BK, (uint32_t)BN};
-  if ((rc = make_tmap_bf16(&tb, W, 2, db, bb))) return rc;
-  const int cap = epi ? epi->max_ctas : 0;
-  return BN == 256 ? launch_gemm<256>(p, ta, tb, cap, stream) : launch_gemm<128>(p, ta, tb, cap, stream);
+  return dispatch_gemm(p, A, W, K, N, M, false, da, ba, 2, epi ? epi->max_ctas : 0, epi ? epi->force_ctas : 0, stream);
 }
 
 extern "C" int grove_conv_gemm_bf16(const void* X, const void* Wp, void* out, int V, int T, int G, int C, int N, int kt,
@@ -344,25 +442,16 @@ extern "C" int grove_conv_gemm_bf16(const void* X, const void* Wp, void* out, in
   GROVE_CHECK_ARG(G <= 128 && 128 % G == 0 && (G * G) % 128 == 0);  // a 128-token M tile is whole grid rows of one frame
   GROVE_CHECK_ARG(C % 64 == 0 && N % 128 == 0);
   GROVE_CHECK_ARG(((uintptr_t)X & 15) == 0 && ((uintptr_t)Wp & 15) == 0 && ((uintptr_t)out & 15) == 0);
-  const int BN = (N % 256 == 0) ? 256 : 128;
   const int ntaps = kt * 9;
   GemmParams p{};
   p.M = V * T * G * G; p.N = N;
-  p.num_m_blocks = p.M / BM;
-  p.num_n_blocks = N / BN;
   p.kc_blocks = C / BK;
   p.num_k_blocks = ntaps * p.kc_blocks;
   p.conv = 1; p.G = G; p.rows_per_tile = BM / G; p.tiles_per_frame = G * G / BM; p.T = T; p.kt = kt;
   p.out = out;
   int rc = fill_epilogue(p, epi, p.M, N);
   if (rc) return rc;
-  CUtensorMap ta, tb;
   uint64_t da[5] = {(uint64_t)C, (uint64_t)G, (uint64_t)G, (uint64_t)T, (uint64_t)V};
   uint32_t ba[5] = {BK, (uint32_t)G, (uint32_t)(BM / G), 1, 1};
-  if ((rc = make_tmap_bf16(&ta, X, 5, da, ba))) return rc;
-  uint64_t db[2] = {(uint64_t)ntaps * C, (uint64_t)N};
-  uint32_t bb[2] = {BK, (uint32_t)BN};
-  if ((rc = make_tmap_bf16(&tb, Wp, 2, db, bb))) return rc;
-  const int cap = epi ? epi->max_ctas : 0;
-  return BN == 256 ? launch_gemm<256>(p, ta, tb, cap, stream) : launch_gemm<128>(p, ta, tb, cap, stream);
+  return dispatch_gemm(p, X, Wp, ntaps * C, N, p.M, true, da, ba, 5, epi ? epi->max_ctas : 0, epi ? epi->force_ctas : 0, stream);
 }

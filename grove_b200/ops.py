@@ -28,7 +28,7 @@ def _req(t: torch.Tensor, dtype, name: str):
     return t
 
 
-def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas):
+def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas=0):
     e = GemmEpilogue()
     e.bias = None if bias is None else _req(bias, F32, "bias").data_ptr()
     e.resid = None if resid is None else _req(resid, F32, "resid").data_ptr()
@@ -38,28 +38,29 @@ def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas):
     e.out_f32 = 1 if out.dtype == F32 else 0
     e.out2_bf16 = None if out2 is None else _req(out2, BF16, "out2").data_ptr()
     e.max_ctas = int(max_ctas)
+    e.force_ctas = int(force_ctas)
     return e
 
 
-def gemm(a, w, out, *, bias=None, resid=None, resid_row_mod=0, gate_alpha=None, act=None, out2=None, max_ctas=0):
+def gemm(a, w, out, *, bias=None, resid=None, resid_row_mod=0, gate_alpha=None, act=None, out2=None, max_ctas=0, force_ctas=0):
     """out[M,N] = resid + tanh(gate_alpha) * act(a[M,K] @ w[N,K]^T + bias)   (tcgen05 GEMM)"""
     _req(a, BF16, "a"); _req(w, BF16, "w")
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and out.shape == (M, N) and out.is_contiguous() and out.dtype in (BF16, F32)
-    e = _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas)
+    e = _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas)
     check(lib().grove_gemm_bf16(_p(a), _p(w), _p(out), M, N, K, C.byref(e), _stream(a)), "grove_gemm_bf16")
     return out
 
 
-def conv_gemm(x, wp, out, *, V, T, G, kt, bias=None, resid=None, gate_alpha=None, act=None, out2=None, max_ctas=0):
+def conv_gemm(x, wp, out, *, V, T, G, kt, bias=None, resid=None, gate_alpha=None, act=None, out2=None, max_ctas=0, force_ctas=0):
     """implicit-GEMM 'same' conv over token-major x[V,T,G,G,C]; wp[N, taps*C] tap-major"""
     _req(x, BF16, "x"); _req(wp, BF16, "wp")
     Cc = x.shape[-1]
     N = wp.shape[0]
     assert x.numel() == V * T * G * G * Cc and wp.shape[1] == 9 * kt * Cc
     assert out.shape == (V * T * G * G, N) and out.is_contiguous()
-    e = _epilogue(bias, resid, 0, gate_alpha, act, out, out2, max_ctas)
+    e = _epilogue(bias, resid, 0, gate_alpha, act, out, out2, max_ctas, force_ctas)
     check(lib().grove_conv_gemm_bf16(_p(x), _p(wp), _p(out), V, T, G, Cc, N, kt, C.byref(e), _stream(x)), "grove_conv_gemm_bf16")
     return out
 

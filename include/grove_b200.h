@@ -44,6 +44,7 @@ typedef struct grove_gemm_epilogue {
   int out_f32;             /* 1: `out` is fp32, 0: bf16 */
   void* out2_bf16;         /* optional second, bf16 copy of the output, or NULL */
   int max_ctas;            /* 0 = one persistent CTA per SM; >0 caps the grid (tests) */
+  int force_ctas;          /* 0 = auto; 1 = single-CTA tiles; 2 = CTA-pair (cta_group::2) tiles when N % 256 == 0 (tests) */
 } grove_gemm_epilogue;
 
 /* out[M,N] = resid + gate * act(A[M,K] . W[N,K]^T + bias).  A, W bf16 row-major (nn.Linear layout).

@@ -29,42 +29,46 @@ def _relerr(a, b):
 
 
 # ------------------------------------------------------------------ tcgen05 GEMM
-@pytest.mark.parametrize("M,N,K,max_ctas", [(128, 128, 64, 0), (256, 256, 128, 0), (1000, 768, 768, 0), (4096, 2304, 768, 7),
-                                            (8192, 3072, 768, 0), (4096, 768, 3072, 5), (300, 256, 4096, 0), (32768, 128, 256, 0)])
-def test_gemm_plain(ops, M, N, K, max_ctas):
+@pytest.mark.parametrize("force_ctas", [1, 2])
+@pytest.mark.parametrize("M,N,K,max_ctas", [(128, 128, 64, 0), (256, 256, 128, 0), (1100, 768, 768, 0), (4096, 2304, 768, 7),
+                                            (8192, 3072, 768, 0), (4096, 768, 3072, 6), (300, 256, 4096, 0), (32768, 128, 256, 0)])
+def test_gemm_plain(ops, M, N, K, max_ctas, force_ctas):
+    """force_ctas=1: single-CTA 128xBN tiles; force_ctas=2: CTA-pair (cta_group::2) 256x256 tiles when N % 256 == 0"""
     a, w = _rand((M, K), 1, dtype=torch.bfloat16), _rand((N, K), 2, 1 / math.sqrt(K), dtype=torch.bfloat16)
     out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
-    ops.gemm(a, w, out, max_ctas=max_ctas)
+    ops.gemm(a, w, out, max_ctas=max_ctas, force_ctas=force_ctas)
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t()
     assert _relerr(out, ref) < 2e-5, _relerr(out, ref)
 
 
-def test_gemm_epilogues(ops):
+@pytest.mark.parametrize("force_ctas", [1, 2])
+def test_gemm_epilogues(ops, force_ctas):
     M, N, K = 1536, 768, 768
     a, w = _rand((M, K), 3, dtype=torch.bfloat16), _rand((N, K), 4, 1 / math.sqrt(K), dtype=torch.bfloat16)
     bias, resid = _rand((N,), 5), _rand((M, N), 6)
     ref = a.float() @ w.float().t() + bias
     # bias + GELU -> bf16
     o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(a, w, o, bias=bias, act="gelu")
+    ops.gemm(a, w, o, bias=bias, act="gelu", force_ctas=force_ctas)
     assert _relerr(o.float(), F.gelu(ref)) < 6e-3
     # bias + in-place fp32 residual + bf16 side copy
     x = resid.clone()
     o2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(a, w, x, bias=bias, resid=x, out2=o2)
+    ops.gemm(a, w, x, bias=bias, resid=x, out2=o2, force_ctas=force_ctas)
     assert _relerr(x, resid + ref) < 2e-5
     assert torch.equal(o2, x.to(torch.bfloat16))
     # row-periodic residual (abs-pos embedding), relu, tanh gate
     pos, alpha = _rand((512, N), 7), torch.tensor([0.5], device="cuda")
     o3 = torch.empty(M, N, device="cuda", dtype=torch.float32)
-    ops.gemm(a, w, o3, bias=bias, act="relu", gate_alpha=alpha, resid=pos, resid_row_mod=512)
+    ops.gemm(a, w, o3, bias=bias, act="relu", gate_alpha=alpha, resid=pos, resid_row_mod=512, force_ctas=force_ctas)
     ref3 = pos.repeat(3, 1) + math.tanh(0.5) * F.relu(ref)
     assert _relerr(o3, ref3) < 2e-5
 
 
+@pytest.mark.parametrize("force_ctas", [1, 2])
 @pytest.mark.parametrize("V,T,G,C,N,kt", [(1, 8, 64, 128, 256, 3), (2, 8, 32, 64, 128, 3), (3, 1, 64, 256, 256, 1), (1, 8, 16, 64, 128, 3)])
-def test_conv_implicit_gemm(ops, V, T, G, C, N, kt):
+def test_conv_implicit_gemm(ops, V, T, G, C, N, kt, force_ctas):
     x = _rand((V, T, G, G, C), 8, dtype=torch.bfloat16)
     bias = _rand((N,), 10)
     if kt == 3:
@@ -76,7 +80,7 @@ def test_conv_implicit_gemm(ops, V, T, G, C, N, kt):
         wp = w.permute(0, 2, 3, 1).reshape(N, -1).contiguous()
         ref = F.conv2d(x.float().reshape(V * T, G, G, C).permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
     out = torch.empty(V * T * G * G, N, device="cuda", dtype=torch.float32)
-    ops.conv_gemm(x, wp, out, V=V, T=T, G=G, kt=kt, bias=bias)
+    ops.conv_gemm(x, wp, out, V=V, T=T, G=G, kt=kt, bias=bias, force_ctas=force_ctas)
     assert _relerr(out, ref) < 3e-5, _relerr(out, ref)
 
 
