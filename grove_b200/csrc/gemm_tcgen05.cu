@@ -19,7 +19,8 @@ namespace grove {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kGemmThreads = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int kEpiWarps = 8;
 
 struct GemmParams {
   int M, N;
@@ -46,9 +47,9 @@ struct GemmCfg {
   static constexpr int kBRows = BN / CTAS;           // B rows staged by one CTA
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStageRowF = 68;              // epilogue staging: 32 rows x 64 fp32 columns per warp, padded row
-  static constexpr int kEpiBytes = 4 * 32 * kStageRowF * 4;
-  static constexpr int kStages = (200 * 1024 - kEpiBytes) / kStageBytes > 6 ? 6 : (200 * 1024 - kEpiBytes) / kStageBytes;
+  static constexpr int kStageRowF = 36;              // epilogue staging: 32 rows x 32 fp32 columns per warp, padded row (144 B)
+  static constexpr int kEpiBytes = kEpiWarps * 32 * kStageRowF * 4;
+  static constexpr int kStages = (224 * 1024 - kEpiBytes) / kStageBytes > 6 ? 6 : (224 * 1024 - kEpiBytes) / kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;           // two accumulator stages (power of two: 256 or 512)
 };
@@ -84,7 +85,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4 * CTAS);   // one arrival per epilogue warp of every CTA in the pair
+      mbar_init(tempty_bar(s), kEpiWarps * CTAS);   // one arrival per epilogue warp of every CTA in the pair
     }
     fence_barrier_init();
   }
@@ -186,70 +187,102 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // 8 warps: warp%4 selects the TMEM lane quadrant (32 accumulator rows), (warp-2)/4 the column half of the tile.
+    // Each pass moves a 32-row x 32-column block: one tcgen05.ld, a padded smem transpose, then row-contiguous
+    // 128-byte (fp32) / 64-byte (bf16) global segments.  Residual rows are fetched BEFORE the TMEM wait so their
+    // latency overlaps the accumulator read.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const float gate = p.gate_alpha ? tanhf(__ldg(p.gate_alpha)) : 1.0f;
-    const uint32_t stg = epi_base + quad * (32 * Cfg::kStageRowF * 4);
+    const uint32_t stg = epi_base + (warp - 2) * (32 * Cfg::kStageRowF * 4);
+    constexpr int kPasses = BN / 2 / 32;
     uint32_t tile_it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
       const int m_blk = (tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
       const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
-      mbar_wait(tfull_bar(acc), acc_ph);
-      tc_fence_after();
       const int row_base = m_blk * BM + quad * 32;
+      bool waited = false;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 64; ++ch) {
-        {
-          uint32_t r0[32], r1[32];
-          const uint32_t taddr = tmem_base + acc * BN + ch * 64 + ((uint32_t)(quad * 32) << 16);
-          tmem_ld_32x32b_x32(taddr, r0);
-          tmem_ld_32x32b_x32(taddr + 32, r1);
-          tmem_ld_wait();
-          const uint32_t wrow = stg + lane * (Cfg::kStageRowF * 4);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + j * 4), "r"(r0[j]), "r"(r0[j + 1]), "r"(r0[j + 2]), "r"(r0[j + 3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + 128 + j * 4), "r"(r1[j]), "r"(r1[j + 1]), "r"(r1[j + 2]), "r"(r1[j + 3]) : "memory");
-          }
-        }
-        __syncwarp();
-        const int col0 = n_blk * BN + ch * 64;
+      for (int ps = 0; ps < kPasses; ++ps) {
+        const int ccol = half * (BN / 2) + ps * 32;   // column offset inside the tile
+        const int col0 = n_blk * BN + ccol;
         if (p.out_f32) {
-          // 16 lanes x float4 cover one 64-column row segment (256 B); two rows per instruction
-          const int c = (lane & 15) * 4;
+          // lane -> (row 4i + lane/8, 4 columns at (lane%8)*4)
+          const int c = (lane & 7) * 4;
+          float4 res[8];
+          if (p.resid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = row_base + 4 * i + (lane >> 3);
+              res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < p.M) res[i] = *reinterpret_cast<const float4*>(p.resid + (size_t)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.N + col0 + c);
+            }
+          }
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int rl = 2 * i + (lane >> 4);
+          if (!waited) { mbar_wait(tfull_bar(acc), acc_ph); tc_fence_after(); waited = true; }
+          {
+            uint32_t r0[32];
+            tmem_ld_32x32b_x32(tmem_base + acc * BN + ccol + ((uint32_t)(quad * 32) << 16), r0);
+            tmem_ld_wait();
+            const uint32_t wrow = stg + lane * (Cfg::kStageRowF * 4);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + j * 4), "r"(r0[j]), "r"(r0[j + 1]), "r"(r0[j + 2]), "r"(r0[j + 3]) : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + (lane >> 3);
             const int row = row_base + rl;
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stg + (rl * Cfg::kStageRowF + c) * 4));
             v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-            if (p.act == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+            if (p.act == 1) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
             else if (p.act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             if (p.gate_alpha) { v.x *= gate; v.y *= gate; v.z *= gate; v.w *= gate; }
+            if (p.resid) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
             if (row < p.M) {
-              if (p.resid) {
-                const size_t rr = (size_t)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.N;
-                const float4 b = *reinterpret_cast<const float4*>(p.resid + rr + col0 + c);
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
               const size_t o = (size_t)row * p.N + col0 + c;
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = v;
               if (p.out2) *reinterpret_cast<uint2*>(p.out2 + o) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
             }
           }
         } else {
-          // 8 lanes x 8 columns (16 B of bf16) cover one 64-column row segment (128 B); four rows per instruction
-          const int c = (lane & 7) * 8;
+          // lane -> (row 8i + lane/4, 8 columns at (lane%4)*8)
+          const int c = (lane & 3) * 8;
+          float4 res[8];
+          if (p.resid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = row_base + 8 * i + (lane >> 2);
+              res[2 * i] = res[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < p.M) {
+                const float* rp = p.resid + (size_t)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.N + col0 + c;
+                res[2 * i] = *reinterpret_cast<const float4*>(rp);
+                res[2 * i + 1] = *reinterpret_cast<const float4*>(rp + 4);
+              }
+            }
+          }
           float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
           if (p.bias) {
             ba = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));
             bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + 4));
           }
-#pragma unroll 4
-          for (int i = 0; i < 8; ++i) {
-            const int rl = 4 * i + (lane >> 3);
+          if (!waited) { mbar_wait(tfull_bar(acc), acc_ph); tc_fence_after(); waited = true; }
+          {
+            uint32_t r0[32];
+            tmem_ld_32x32b_x32(tmem_base + acc * BN + ccol + ((uint32_t)(quad * 32) << 16), r0);
+            tmem_ld_wait();
+            const uint32_t wrow = stg + lane * (Cfg::kStageRowF * 4);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + j * 4), "r"(r0[j]), "r"(r0[j + 1]), "r"(r0[j + 2]), "r"(r0[j + 3]) : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = 8 * i + (lane >> 2);
             const int row = row_base + rl;
             float4 u, w;
             const uint32_t a = stg + (rl * Cfg::kStageRowF + c) * 4;
@@ -258,7 +291,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
             float v[8] = {u.x + ba.x, u.y + ba.y, u.z + ba.z, u.w + ba.w, w.x + bb.x, w.y + bb.y, w.z + bb.z, w.w + bb.w};
             if (p.act == 1) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+              for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
             } else if (p.act == 2) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -267,13 +300,11 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] *= gate;
             }
+            if (p.resid) {
+              v[0] += res[2 * i].x; v[1] += res[2 * i].y; v[2] += res[2 * i].z; v[3] += res[2 * i].w;
+              v[4] += res[2 * i + 1].x; v[5] += res[2 * i + 1].y; v[6] += res[2 * i + 1].z; v[7] += res[2 * i + 1].w;
+            }
             if (row < p.M) {
-              if (p.resid) {
-                const size_t rr = (size_t)(p.resid_mod > 0 ? row % p.resid_mod : row) * p.N;
-                const float4 x0 = *reinterpret_cast<const float4*>(p.resid + rr + col0 + c);
-                const float4 x1 = *reinterpret_cast<const float4*>(p.resid + rr + col0 + c + 4);
-                v[0] += x0.x; v[1] += x0.y; v[2] += x0.z; v[3] += x0.w; v[4] += x1.x; v[5] += x1.y; v[6] += x1.z; v[7] += x1.w;
-              }
               const size_t o = (size_t)row * p.N + col0 + c;
               const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
               *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pk;
@@ -281,7 +312,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
             }
           }
         }
-        __syncwarp();   // staging buffer is reused by the next 64-column pass
+        __syncwarp();   // staging buffer is reused by the next pass
       }
       // accumulator drained (all tcgen05.ld of this warp completed before the smem staging): release it to the MMA warp
       tc_fence_before();
