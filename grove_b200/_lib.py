@@ -31,6 +31,7 @@ SIGNATURES = {
     "grove_layernorm": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "grove_attn_window_relpos_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "grove_attn_global_relpos_fwd_mma": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_cast_f32_bf16": [_P, _P, _LL, _P],
     "grove_tokens_to_nchw_bf16": [_P, _P, _I, _I, _I, _P],
     "grove_nchw_to_tokens_bf16": [_P, _P, _I, _I, _I, _P],

@@ -455,11 +455,11 @@ constexpr int kWindowSmem = 3 * WQP * 128 + 2 * 32 * 128 + 2 * WQ * WS * 4 + 128
 }  // namespace grove
 using namespace grove;
 
-extern "C" int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
+extern "C" int grove_attn_global_relpos_fwd_mma(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
                                             int heads, int hd, cudaStream_t stream) {
   GROVE_CHECK_ARG(qkv && rel_pos_h && rel_pos_w && out && F > 0 && heads > 0);
   if (hd != 64 || (G != 64 && G != 32)) {
-    grove_set_error("grove_attn_global_relpos_fwd: only hd=64 and G in {32,64} are built (got hd=%d G=%d)", hd, G);
+    grove_set_error("grove_attn_global_relpos_fwd_mma: only hd=64 and G in {32,64} are built (got hd=%d G=%d)", hd, G);
     return GROVE_ERR_UNSUPPORTED;
   }
   GROVE_CHECK_ARG(F <= 65535 && heads <= 65535);

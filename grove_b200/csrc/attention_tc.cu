@@ -1,0 +1,320 @@
+// Global attention with decomposed rel-pos bias on tcgen05 / TMEM / TMA (image_encoder.py:301-326, 420-458).
+//
+// One CTA = 128 queries of one (frame, head).  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax
+// (one thread per query row = one TMEM lane, so the row softmax needs no cross-thread reduction).
+//   prologue  T_w = Q.Rw^T and T_h = Q.Rh^T as two UMMAs (128x128x64) -> each thread gathers its own
+//             rel_w[kw] = T_w[qw-kw+G-1] into registers and rel_h[kh] into shared memory (pre-scaled by log2 e)
+//   phase 1   S = Q.K^T per 128-key block (UMMA 128x128x64, double-buffered in TMEM) -> exact row max of
+//             scale*S + rel_h + rel_w                                (no exponentials, no P.V)
+//   phase 2   S again -> p = exp2(scale*S + bias - max) -> bf16 P written straight into the 128B-swizzled K-major
+//             smem layout UMMA expects -> O += P.V (UMMA 128x64x128, V consumed MN-major exactly as TMA lands it)
+// Knowing the exact max up front removes the online-softmax rescale of O (no TMEM round trip, no data-dependent
+// control flow); it costs one extra Q.K^T, which runs on an otherwise idle tensor pipe (the kernel is bound by the
+// 16 exp2/clk MUFU rate, not by MMA).  Scores never leave the SM.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "grove_b200.h"
+
+namespace grove {
+
+constexpr int kAttThreads = 192;
+constexpr int kKStages = 3, kVStages = 2;
+
+template <int G>
+__global__ void __launch_bounds__(kAttThreads, 1)
+attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_rh,
+                      const __grid_constant__ CUtensorMap tmap_rw, __nv_bfloat16* __restrict__ out, int heads) {
+  constexpr int N = G * G;
+  constexpr int NB = N / 128;          // key blocks
+  constexpr int NKW = G;               // rel_w entries per row
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = s0;                         // 16 KB   Q tile [128][64] bf16, SW128
+  const uint32_t sK = sQ + 16384;                 // 3 x 16 KB K ring
+  const uint32_t sV = sK + kKStages * 16384;      // 2 x 16 KB V ring; during the prologue: Rh | Rw tables
+  const uint32_t sP = sV + kVStages * 16384;      // 2 x 32 KB P buffers (two 64-key slabs each); prologue: fp32 staging [128][128]
+  const uint32_t sRelH = sP + 65536;              // [G][128] fp32
+  const uint32_t bar0 = sRelH + G * 128 * 4;
+  uint8_t* smem_al = smem_raw + (s0 - smem_u32(smem_raw));
+  float* stage_f = reinterpret_cast<float*>(smem_al + (sP - s0));
+  float* relh_f = reinterpret_cast<float*>(smem_al + (sRelH - s0));
+  enum { Q_FULL = 0, TAB_FREE, O_FULL, K_FULL, K_EMPTY = K_FULL + kKStages, V_FULL = K_EMPTY + kKStages, V_EMPTY = V_FULL + kVStages,
+         S_FULL = V_EMPTY + kVStages, S_EMPTY = S_FULL + 2, P_FULL = S_EMPTY + 2, P_EMPTY = P_FULL + 2, NUM_BARS = P_EMPTY + 2 };
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  const uint32_t tmem_slot = bar0 + 8u * NUM_BARS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, f = blockIdx.z;
+  const int D = heads * 64;
+  const int tok0 = f * N;                // first token row of this frame in the [F*N, 3D] qkv matrix
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    mbar_init(bar(Q_FULL), 1); mbar_init(bar(TAB_FREE), 1); mbar_init(bar(O_FULL), 1);
+    for (int i = 0; i < kKStages; ++i) { mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1); }
+    for (int i = 0; i < kVStages; ++i) { mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 4);
+      mbar_init(bar(P_FULL + i), 4); mbar_init(bar(P_EMPTY + i), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 256;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(bar(Q_FULL), 3 * 16384);
+      tma_load_2d(sQ, &tmap_qkv, bar(Q_FULL), h * 64, tok0 + q0);
+      tma_load_2d(sV, &tmap_rw, bar(Q_FULL), 0, 0);            // Rw table -> first V slot (rows >= 2G-1 zero-filled)
+      tma_load_2d(sV + 16384, &tmap_rh, bar(Q_FULL), 0, 0);    // Rh table -> second V slot
+      uint32_t kit = 0, vit = 0;
+      for (int b = 0; b < NB; ++b, ++kit) {                    // phase 1: K only
+        const int s = kit % kKStages;
+        mbar_wait(bar(K_EMPTY + s), ((kit / kKStages) & 1u) ^ 1u);
+        mbar_expect_tx(bar(K_FULL + s), 16384);
+        tma_load_2d(sK + s * 16384, &tmap_qkv, bar(K_FULL + s), D + h * 64, tok0 + b * 128);
+      }
+      mbar_wait(bar(TAB_FREE), 0);                             // prologue MMAs have finished reading the tables
+      for (int b = 0; b < NB; ++b, ++kit, ++vit) {             // phase 2: K and V
+        const int s = kit % kKStages;
+        mbar_wait(bar(K_EMPTY + s), ((kit / kKStages) & 1u) ^ 1u);
+        mbar_expect_tx(bar(K_FULL + s), 16384);
+        tma_load_2d(sK + s * 16384, &tmap_qkv, bar(K_FULL + s), D + h * 64, tok0 + b * 128);
+        const int v = vit % kVStages;
+        mbar_wait(bar(V_EMPTY + v), ((vit / kVStages) & 1u) ^ 1u);
+        mbar_expect_tx(bar(V_FULL + v), 16384);
+        tma_load_2d(sV + v * 16384, &tmap_qkv, bar(V_FULL + v), 2 * D + h * 64, tok0 + b * 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
+    uint32_t sit = 0, kit = 0, vit = 0;
+    auto issue_s = [&](uint32_t b_smem) {   // S[sit&1] = Q . B^T  (B: [128 rows][64] K-major)
+      const uint32_t sb = sit & 1u;
+      mbar_wait(bar(S_EMPTY + sb), ((sit >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_f16(tS0 + sb * 128, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(b_smem + k * 32), idesc_s, k != 0);
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar(Q_FULL), 0);
+    tc_fence_after();
+    issue_s(sV);                                       // T_w
+    if (lane == 0) tc_commit(bar(S_FULL + 0));
+    __syncwarp();
+    ++sit;
+    issue_s(sV + 16384);                               // T_h
+    if (lane == 0) { tc_commit(bar(S_FULL + 1)); tc_commit(bar(TAB_FREE)); }
+    __syncwarp();
+    ++sit;
+    for (int b = 0; b < NB; ++b, ++kit, ++sit) {       // phase 1
+      const int s = kit % kKStages;
+      mbar_wait(bar(K_FULL + s), (kit / kKStages) & 1u);
+      tc_fence_after();
+      issue_s(sK + s * 16384);
+      if (lane == 0) { tc_commit(bar(K_EMPTY + s)); tc_commit(bar(S_FULL + (sit & 1u))); }
+      __syncwarp();
+    }
+    // phase 2: S(b+1) is issued before P(b).V(b) so the softmax of block b+1 overlaps the P.V of block b
+    auto issue_qk2 = [&]() {
+      const int s = kit % kKStages;
+      mbar_wait(bar(K_FULL + s), (kit / kKStages) & 1u);
+      tc_fence_after();
+      issue_s(sK + s * 16384);
+      if (lane == 0) { tc_commit(bar(K_EMPTY + s)); tc_commit(bar(S_FULL + (sit & 1u))); }
+      __syncwarp();
+      ++kit; ++sit;
+    };
+    issue_qk2();
+    for (int b = 0; b < NB; ++b, ++vit) {
+      if (b + 1 < NB) issue_qk2();
+      const uint32_t pb = b & 1u;
+      const int v = vit % kVStages;
+      mbar_wait(bar(V_FULL + v), (vit / kVStages) & 1u);
+      mbar_wait(bar(P_FULL + pb), (b >> 1) & 1u);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = umma_desc_sw128(sP + pb * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32);
+          const uint64_t db = umma_desc_sw128(sV + v * 16384 + kk * 2048);
+          tc_mma_f16(tO, da, db, idesc_o, (b | kk) != 0);
+        }
+        tc_commit(bar(V_EMPTY + v));
+        tc_commit(bar(P_EMPTY + pb));
+        if (b == NB - 1) tc_commit(bar(O_FULL));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax warps: thread = query row =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                    // row inside the tile == TMEM lane
+    const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+    const int q = q0 + row;
+    const int qh = q / G, qw = q % G;
+    uint32_t sit = 0;
+    float relw[NKW];
+    // ---- prologue: rel_w -> registers, rel_h -> smem (both x log2 e)
+#pragma unroll
+    for (int which = 0; which < 2; ++which, ++sit) {
+      mbar_wait(bar(S_FULL + (sit & 1u)), (sit >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tS0 + (sit & 1u) * 128 + c * 32 + tlane, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage_f + row * 128 + c * 32 + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(S_EMPTY + (sit & 1u)));
+      if (which == 0) {
+#pragma unroll
+        for (int kw = 0; kw < NKW; ++kw) relw[kw] = stage_f[row * 128 + qw + (G - 1) - kw] * 1.4426950408889634f;
+      } else {
+        for (int kh = 0; kh < G; ++kh) relh_f[kh * 128 + row] = stage_f[row * 128 + qh + (G - 1) - kh] * 1.4426950408889634f;
+      }
+      __syncwarp();   // the staging row is rewritten by the next table
+    }
+    const float c_scale = 0.125f * 1.4426950408889634f;   // hd^-0.5 * log2(e), hd = 64
+    // ---- phase 1: exact row max
+    float m = -INFINITY;
+    for (int b = 0; b < NB; ++b, ++sit) {
+      const uint32_t sb = sit & 1u;
+      mbar_wait(bar(S_FULL + sb), (sit >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tS0 + sb * 128 + c * 32 + tlane, r);
+        tmem_ld_wait();
+        const int kh = (b * 128 + c * 32) / G;
+        constexpr int kPer = (G >= 32) ? 32 : G;
+        const int wbase = (c * 32) % G;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), c_scale, relw[wbase + j]));
+        m = fmaxf(m, mx + relh_f[kh * 128 + row]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
+    }
+    // ---- phase 2: probabilities and P.V
+    float lsum = 0.f;
+    for (int b = 0; b < NB; ++b, ++sit) {
+      const uint32_t sb = sit & 1u, pb = b & 1u;
+      mbar_wait(bar(S_FULL + sb), (sit >> 1) & 1u);
+      mbar_wait(bar(P_EMPTY + pb), ((b >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tS0 + sb * 128 + c * 32 + tlane, r);
+        tmem_ld_wait();
+        const int kh = (b * 128 + c * 32) / G;
+        const int wbase = (c * 32) % G;
+        const float off = relh_f[kh * 128 + row] - m;
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float p0, p1;
+          const float e0 = fmaf(__uint_as_float(r[j]), c_scale, relw[wbase + j]) + off;
+          const float e1 = fmaf(__uint_as_float(r[j + 1]), c_scale, relw[wbase + j + 1]) + off;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
+          lsum += p0 + p1;
+          pk[j >> 1] = pack_bf16(p0, p1);
+        }
+        // keys [c*32, c*32+32) of the block -> slab c/2, 16-byte chunks (c%2)*4 .. +3 of this row, XOR-swizzled by the row
+        const uint32_t prow = sP + pb * 32768 + (c >> 1) * 16384 + row * 128;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint32_t ch = (uint32_t)((c & 1) * 4 + k4) ^ (uint32_t)(row & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (ch << 4)), "r"(pk[4 * k4]), "r"(pk[4 * k4 + 1]), "r"(pk[4 * k4 + 2]),
+                       "r"(pk[4 * k4 + 3])
+                       : "memory");
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(S_EMPTY + sb)); mbar_arrive(bar(P_FULL + pb)); }
+    }
+    // ---- epilogue: O / l -> bf16 -> global
+    mbar_wait(bar(O_FULL), 0);
+    tc_fence_after();
+    const float inv = 1.f / lsum;
+    __nv_bfloat16* orow = out + ((size_t)tok0 + q) * D + h * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tO + c * 32 + tlane, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        *reinterpret_cast<uint4*>(orow + c * 32 + j) =
+            make_uint4(pack_bf16(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv), pack_bf16(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv),
+                       pack_bf16(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv), pack_bf16(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int G>
+constexpr int att_tc_smem() { return 16384 + kKStages * 16384 + kVStages * 16384 + 65536 + G * 128 * 4 + 1024 + 512; }
+
+int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows);
+
+}  // namespace grove
+using namespace grove;
+
+template <int G>
+static int launch_att_tc(const void* qkv, const void* rh, const void* rw, void* out, int F, int heads, cudaStream_t stream) {
+  const int N = G * G, D = heads * 64;
+  CUtensorMap tq, th, tw;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)3 * D, (uint64_t)F * N, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&th, rh, 64, 2 * G - 1, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tw, rw, 64, 2 * G - 1, 64, 128))) return rc;
+  constexpr int smem = att_tc_smem<G>();
+  cudaError_t e = cudaFuncSetAttribute(attn_global_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
+  attn_global_tc_kernel<G><<<dim3(N / 128, heads, F), kAttThreads, smem, stream>>>(tq, th, tw, (__nv_bfloat16*)out, heads);
+  grove_count_launch();
+  GROVE_CHECK_LAUNCH();
+  return GROVE_OK;
+}
+
+extern "C" int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G, int heads,
+                                            int hd, cudaStream_t stream) {
+  GROVE_CHECK_ARG(qkv && rel_pos_h && rel_pos_w && out && F > 0 && heads > 0);
+  if (hd != 64 || (G != 64 && G != 32)) {
+    grove_set_error("grove_attn_global_relpos_fwd: only hd=64 and G in {32,64} are built (got hd=%d G=%d)", hd, G);
+    return GROVE_ERR_UNSUPPORTED;
+  }
+  GROVE_CHECK_ARG(F <= 65535 && heads <= 65535);
+  GROVE_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)rel_pos_h & 15) == 0 && ((uintptr_t)rel_pos_w & 15) == 0);
+  return G == 64 ? launch_att_tc<64>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream)
+                 : launch_att_tc<32>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream);
+}

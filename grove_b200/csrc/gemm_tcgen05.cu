@@ -370,6 +370,12 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint
   return GROVE_OK;
 }
 
+int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
+  uint64_t d[2] = {inner, rows};
+  uint32_t b[2] = {box_inner, box_rows};
+  return make_tmap_bf16(m, base, 2, d, b);
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {

@@ -91,12 +91,12 @@ def attn_window(qkv, qkv_bias_bf16, rel_h, rel_w, out, *, F, G, heads, hd, ws=14
     return out
 
 
-def attn_global(qkv, rel_h, rel_w, out, *, F, G, heads, hd):
+def attn_global(qkv, rel_h, rel_w, out, *, F, G, heads, hd, legacy_mma=False):
     for t, n in ((qkv, "qkv"), (rel_h, "rel_pos_h"), (rel_w, "rel_pos_w"), (out, "out")):
         _req(t, BF16, n)
     assert qkv.numel() == F * G * G * 3 * heads * hd and rel_h.shape == (2 * G - 1, hd)
-    check(lib().grove_attn_global_relpos_fwd(_p(qkv), _p(rel_h), _p(rel_w), _p(out), F, G, heads, hd, _stream(qkv)),
-          "grove_attn_global_relpos_fwd")
+    fn = lib().grove_attn_global_relpos_fwd_mma if legacy_mma else lib().grove_attn_global_relpos_fwd
+    check(fn(_p(qkv), _p(rel_h), _p(rel_w), _p(out), F, G, heads, hd, _stream(qkv)), "grove_attn_global_relpos_fwd")
     return out
 
 

@@ -76,9 +76,14 @@ int grove_layernorm(const float* x, const float* gamma, const float* beta, void*
  * out[F,G,G,heads*hd] bf16.  Replaces Attention.forward :301-326 + add_decomposed_rel_pos :420-458. */
 int grove_attn_window_relpos_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w,
                                  void* out, int F, int G, int heads, int hd, int ws, grove_stream_t stream);
-/* Global attention over one frame's G*G tokens with decomposed rel-pos bias (tables [2G-1, hd] bf16). */
+/* Global attention over one frame's G*G tokens with decomposed rel-pos bias (tables [2G-1, hd] bf16): tcgen05/TMEM/TMA
+ * kernel (attention_tc.cu), exact two-phase softmax, scores never leave the SM.  qkv [F,G,G,3,heads,hd], out [F,G,G,heads*hd]. */
 int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
                                  int heads, int hd, grove_stream_t stream);
+/* Same contract on the legacy warp-level tensor path (mma.sync flash kernel, attention.cu) — kept as an independent
+ * cross-check for the tests; the modules never call it. */
+int grove_attn_global_relpos_fwd_mma(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
+                                     int heads, int hd, grove_stream_t stream);
 /* fp32 -> bf16 cast (n % 8 == 0) and token-major [F,N,C] bf16 -> NCHW [F,C,N] transposition helpers */
 int grove_cast_f32_bf16(const float* x, void* y, long long n, grove_stream_t stream);
 int grove_tokens_to_nchw_bf16(const void* tok, void* nchw, int F, int N, int C, grove_stream_t stream);

@@ -122,13 +122,16 @@ def _ref_attention(qkv, rel_h, rel_w, B, S, heads, hd):
     return o.view(B, heads, S, S, hd).permute(0, 2, 3, 1, 4).reshape(B, S, S, heads * hd)
 
 
+@pytest.mark.parametrize("legacy", [False, True])
 @pytest.mark.parametrize("G,Fr,heads", [(64, 2, 3), (32, 3, 2)])
-def test_global_attention(ops, G, Fr, heads):
+def test_global_attention(ops, G, Fr, heads, legacy):
+    """legacy=False: the tcgen05/TMEM kernel the modules use; legacy=True: the mma.sync cross-check kernel"""
     hd = 64
     qkv = _rand((Fr, G, G, 3, heads, hd), 20, dtype=torch.bfloat16)
     rh, rw = _rand((2 * G - 1, hd), 21, 0.1, dtype=torch.bfloat16), _rand((2 * G - 1, hd), 22, 0.1, dtype=torch.bfloat16)
     out = torch.full((Fr, G, G, heads * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
-    ops.attn_global(qkv, rh, rw, out, F=Fr, G=G, heads=heads, hd=hd)
+    ops.attn_global(qkv, rh, rw, out, F=Fr, G=G, heads=heads, hd=hd, legacy_mma=legacy)
+    torch.cuda.synchronize()
     ref = _ref_attention(qkv, rh, rw, Fr, G, heads, hd)
     err = float((out.float() - ref).abs().max())
     assert err < 2e-2, err          # bf16 P and bf16 output on O(1) values
