@@ -1,7 +1,8 @@
 // Global attention with decomposed rel-pos bias on tcgen05 / TMEM / TMA (image_encoder.py:301-326, 420-458).
 //
-// One CTA = 128 queries of one (frame, head).  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax
-// (one thread per query row = one TMEM lane, so the row softmax needs no cross-thread reduction).
+// One CTA = 128 queries of one (frame, head).  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 softmax:
+// two threads per query row (= TMEM lane), each owning the keys with kw in one half of the grid row, so the row softmax
+// needs only one max / one sum exchange per tile and every SM sub-partition has two softmax warps to hide latency.
 //   prologue  T_w = Q.Rw^T and T_h = Q.Rh^T as two UMMAs (128x128x64) -> each thread gathers its own
 //             rel_w[kw] = T_w[qw-kw+G-1] into registers and rel_h[kh] into shared memory (pre-scaled by log2 e)
 //   phase 1   S = Q.K^T per 128-key block (UMMA 128x128x64, double-buffered in TMEM) -> exact row max of
@@ -18,8 +19,8 @@
 
 namespace grove {
 
-constexpr int kAttThreads = 192;
-constexpr int kKStages = 3, kVStages = 2;
+constexpr int kAttThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two threads per query row)
+constexpr int kKStages = 4, kVStages = 2;
 
 template <int G>
 __global__ void __launch_bounds__(kAttThreads, 1)
@@ -31,14 +32,16 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
   extern __shared__ uint8_t smem_raw[];
   const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = s0;                         // 16 KB   Q tile [128][64] bf16, SW128
-  const uint32_t sK = sQ + 16384;                 // 3 x 16 KB K ring
+  const uint32_t sK = sQ + 16384;                 // kKStages x 16 KB K ring
   const uint32_t sV = sK + kKStages * 16384;      // 2 x 16 KB V ring; during the prologue: Rh | Rw tables
   const uint32_t sP = sV + kVStages * 16384;      // 2 x 32 KB P buffers (two 64-key slabs each); prologue: fp32 staging [128][128]
   const uint32_t sRelH = sP + 65536;              // [G][128] fp32
-  const uint32_t bar0 = sRelH + G * 128 * 4;
+  const uint32_t sXch = sRelH + G * 128 * 4;      // 2 x [2][128] fp32: max and sum exchange between the two threads of a row
+  const uint32_t bar0 = sXch + 2048;
   uint8_t* smem_al = smem_raw + (s0 - smem_u32(smem_raw));
   float* stage_f = reinterpret_cast<float*>(smem_al + (sP - s0));
   float* relh_f = reinterpret_cast<float*>(smem_al + (sRelH - s0));
+  float* xch_f = reinterpret_cast<float*>(smem_al + (sXch - s0));
   enum { Q_FULL = 0, TAB_FREE, O_FULL, K_FULL, K_EMPTY = K_FULL + kKStages, V_FULL = K_EMPTY + kKStages, V_EMPTY = V_FULL + kVStages,
          S_FULL = V_EMPTY + kVStages, S_EMPTY = S_FULL + 2, P_FULL = S_EMPTY + 2, P_EMPTY = P_FULL + 2, NUM_BARS = P_EMPTY + 2 };
   auto bar = [&](int i) { return bar0 + 8u * i; };
@@ -55,8 +58,8 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     for (int i = 0; i < kKStages; ++i) { mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1); }
     for (int i = 0; i < kVStages; ++i) { mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 4);
-      mbar_init(bar(P_FULL + i), 4); mbar_init(bar(P_EMPTY + i), 1);
+      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 8);
+      mbar_init(bar(P_FULL + i), 8); mbar_init(bar(P_EMPTY + i), 1);
     }
     fence_barrier_init();
   }
@@ -160,85 +163,99 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       __syncwarp();
     }
   } else {
-    // ===================== softmax warps: thread = query row =====================
+    // ===================== softmax warps: two threads per query row =====================
     const int quad = warp & 3;
+    const int hs = (warp - 2) >> 2;                      // 0: key chunks {0,2} of every block, 1: chunks {1,3}
     const int row = quad * 32 + lane;                    // row inside the tile == TMEM lane
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
     const int q = q0 + row;
     const int qh = q / G, qw = q % G;
+    constexpr float kL2e = 1.4426950408889634f;
+    auto softmax_sync = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // staging row with the float4 slots XOR-swizzled by the row (conflict-free 128-bit stores of 32 different rows)
+    auto stage_at = [&](int e) { return stage_f[row * 128 + ((((e >> 2) ^ (row & 7)) << 2) | (e & 3))]; };
     uint32_t sit = 0;
-    float relw[NKW];
+    float relw[32];                                      // this thread's kw half (G=64) / the whole grid row (G=32)
+    const int kw0 = (G == 64) ? hs * 32 : 0;
     // ---- prologue: rel_w -> registers, rel_h -> smem (both x log2 e)
 #pragma unroll
     for (int which = 0; which < 2; ++which, ++sit) {
       mbar_wait(bar(S_FULL + (sit & 1u)), (sit >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {                   // each thread of the pair moves half of the 128 table columns
+        const int c = 2 * cc + hs;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tS0 + (sit & 1u) * 128 + c * 32 + tlane, r);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stage_f + row * 128 + c * 32 + j) =
+          *reinterpret_cast<float4*>(stage_f + row * 128 + (((c * 8 + (j >> 2)) ^ (row & 7)) << 2)) =
               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(S_EMPTY + (sit & 1u)));
+      softmax_sync();                                    // both halves of every staging row are written
       if (which == 0) {
 #pragma unroll
-        for (int kw = 0; kw < NKW; ++kw) relw[kw] = stage_f[row * 128 + qw + (G - 1) - kw] * 1.4426950408889634f;
+        for (int j = 0; j < 32; ++j) relw[j] = stage_at(qw + (G - 1) - (kw0 + j)) * kL2e;
       } else {
-        for (int kh = 0; kh < G; ++kh) relh_f[kh * 128 + row] = stage_f[row * 128 + qh + (G - 1) - kh] * 1.4426950408889634f;
+        for (int kh = hs * (G / 2); kh < (hs + 1) * (G / 2); ++kh) relh_f[kh * 128 + row] = stage_at(qh + (G - 1) - kh) * kL2e;
       }
-      __syncwarp();   // the staging row is rewritten by the next table
+      softmax_sync();                                    // staging is rewritten by the next table / rel_h complete
     }
-    const float c_scale = 0.125f * 1.4426950408889634f;   // hd^-0.5 * log2(e), hd = 64
+    const float c_scale = 0.125f * kL2e;                 // hd^-0.5 * log2(e), hd = 64
     // ---- phase 1: exact row max
     float m = -INFINITY;
     for (int b = 0; b < NB; ++b, ++sit) {
       const uint32_t sb = sit & 1u;
       mbar_wait(bar(S_FULL + sb), (sit >> 1) & 1u);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tS0 + sb * 128 + c * 32 + tlane, r);
-        tmem_ld_wait();
-        const int kh = (b * 128 + c * 32) / G;
-        constexpr int kPer = (G >= 32) ? 32 : G;
-        const int wbase = (c * 32) % G;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), c_scale, relw[wbase + j]));
-        m = fmaxf(m, mx + relh_f[kh * 128 + row]);
-      }
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(tS0 + sb * 128 + hs * 32 + tlane, ra);
+      tmem_ld_32x32b_x32(tS0 + sb * 128 + (2 + hs) * 32 + tlane, rb);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
+      if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));     // S is in registers: the MMA warp may overwrite this buffer
+      const int kha = (b * 128 + hs * 32) / G, khb = (b * 128 + (2 + hs) * 32) / G;
+      float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        mxa = fmaxf(mxa, fmaf(__uint_as_float(ra[j]), c_scale, relw[j]));
+        mxb = fmaxf(mxb, fmaf(__uint_as_float(rb[j]), c_scale, relw[j]));
+      }
+      m = fmaxf(m, fmaxf(mxa + relh_f[kha * 128 + row], mxb + relh_f[khb * 128 + row]));
     }
+    xch_f[hs * 128 + row] = m;
+    softmax_sync();
+    m = fmaxf(m, xch_f[(hs ^ 1) * 128 + row]);
     // ---- phase 2: probabilities and P.V
     float lsum = 0.f;
     for (int b = 0; b < NB; ++b, ++sit) {
       const uint32_t sb = sit & 1u, pb = b & 1u;
       mbar_wait(bar(S_FULL + sb), (sit >> 1) & 1u);
-      mbar_wait(bar(P_EMPTY + pb), ((b >> 1) & 1u) ^ 1u);
       tc_fence_after();
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(tS0 + sb * 128 + hs * 32 + tlane, ra);
+      tmem_ld_32x32b_x32(tS0 + sb * 128 + (2 + hs) * 32 + tlane, rb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
+      mbar_wait(bar(P_EMPTY + pb), ((b >> 1) & 1u) ^ 1u);   // P.V of block b-2 has finished reading this P buffer
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tS0 + sb * 128 + c * 32 + tlane, r);
-        tmem_ld_wait();
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * cc + hs;
         const int kh = (b * 128 + c * 32) / G;
-        const int wbase = (c * 32) % G;
         const float off = relh_f[kh * 128 + row] - m;
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float p0, p1;
-          const float e0 = fmaf(__uint_as_float(r[j]), c_scale, relw[wbase + j]) + off;
-          const float e1 = fmaf(__uint_as_float(r[j + 1]), c_scale, relw[wbase + j + 1]) + off;
+          const float e0 = fmaf(__uint_as_float(cc ? rb[j] : ra[j]), c_scale, relw[j]) + off;
+          const float e1 = fmaf(__uint_as_float(cc ? rb[j + 1] : ra[j + 1]), c_scale, relw[j + 1]) + off;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
           lsum += p0 + p1;
@@ -254,24 +271,24 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
                        : "memory");
         }
       }
-      tc_fence_before();
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) { mbar_arrive(bar(S_EMPTY + sb)); mbar_arrive(bar(P_FULL + pb)); }
+      if (lane == 0) mbar_arrive(bar(P_FULL + pb));
     }
-    // ---- epilogue: O / l -> bf16 -> global
+    // ---- epilogue: O / l -> bf16 -> global (each thread of the pair stores 32 of the 64 head dims)
+    xch_f[256 + hs * 128 + row] = lsum;
+    softmax_sync();
+    const float inv = 1.f / (lsum + xch_f[256 + (hs ^ 1) * 128 + row]);
     mbar_wait(bar(O_FULL), 0);
     tc_fence_after();
-    const float inv = 1.f / lsum;
-    __nv_bfloat16* orow = out + ((size_t)tok0 + q) * D + h * 64;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    __nv_bfloat16* orow = out + ((size_t)tok0 + q) * D + h * 64 + hs * 32;
+    {
       uint32_t r[32];
-      tmem_ld_32x32b_x32(tO + c * 32 + tlane, r);
+      tmem_ld_32x32b_x32(tO + hs * 32 + tlane, r);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 8)
-        *reinterpret_cast<uint4*>(orow + c * 32 + j) =
+        *reinterpret_cast<uint4*>(orow + j) =
             make_uint4(pack_bf16(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv), pack_bf16(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv),
                        pack_bf16(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv), pack_bf16(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv));
     }
@@ -282,7 +299,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
 }
 
 template <int G>
-constexpr int att_tc_smem() { return 16384 + kKStages * 16384 + kVStages * 16384 + 65536 + G * 128 * 4 + 1024 + 512; }
+constexpr int att_tc_smem() { return 16384 + kKStages * 16384 + kVStages * 16384 + 65536 + G * 128 * 4 + 2048 /*xch*/ + 1024 /*align*/ + 512 /*barriers*/; }
 
 int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows);
 

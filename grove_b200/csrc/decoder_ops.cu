@@ -232,18 +232,18 @@ __global__ void __launch_bounds__(256) keys_add_ln_kernel(const __nv_bfloat16* _
 }
 
 // ---------------------------------------------------------------- token-side fp32 helpers
-// y[R,N] = act(x[R,K] . W[N,K]^T + b) (+ resid).  CTA = 8 rows x 64 outputs; x rows in smem; one warp per output column.
+// y[R,N] = act(x[R,K] . W[N,K]^T + b) (+ resid).  CTA = 8 rows x 16 outputs (two per warp); x rows in smem; lanes split K.
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                                                            const float* __restrict__ resid, float* __restrict__ y, int R, int N, int K, int act) {
   extern __shared__ float xs[];  // [8][K]
-  const int r0 = blockIdx.y * 8, n0 = blockIdx.x * 64;
+  const int r0 = blockIdx.y * 8, n0 = blockIdx.x * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 8 * K; i += 256) {
     const int r = r0 + i / K;
     xs[i] = r < R ? x[(size_t)r * K + i % K] : 0.f;
   }
   __syncthreads();
-  for (int j = warp; j < 64; j += 8) {
+  for (int j = warp; j < 16; j += 8) {
     const int n = n0 + j;
     if (n >= N) break;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -400,7 +400,7 @@ extern "C" int grove_small_linear_f32(const float* x, const float* W, const floa
     cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * (int)sizeof(float));
     attr = true;
   }
-  small_linear_kernel<<<dim3((N + 63) / 64, (R + 7) / 8), 256, smem, stream>>>(x, W, b, resid, y, R, N, K, act);
+  small_linear_kernel<<<dim3((N + 15) / 16, (R + 7) / 8), 256, smem, stream>>>(x, W, b, resid, y, R, N, K, act);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;

@@ -58,6 +58,7 @@ class MaskDecoder(nn.Module):
         else:
             self.use_temp_objectness = False
         self._pack = PackCache()
+        self._pew = {}
         self.max_instances_per_pass = 256  # bounds the per-instance key buffers (N x 256 bf16 + fp32 delta)
 
     # ------------------------------------------------------------------ helpers
@@ -114,7 +115,9 @@ class MaskDecoder(nn.Module):
         no_mask = d[0, :, 0, 0].to(torch.float32).contiguous()
         N = G * G
         emb = self._tokens_of(image_embeddings, torch.bfloat16)                       # [F,N,C]
-        pe = self._tokens_of(image_pe, torch.float32).reshape(N, C).contiguous()      # [N,C]
+        pe = self._tokens_of(image_pe, torch.float32).reshape(N, C)                   # [N,C] (a view of the caller's tensor when possible)
+        if not pe.is_contiguous():
+            pe = pe.contiguous()
         keys0 = torch.empty(Fr * N, C, device=dev, dtype=torch.bfloat16)
         ops.add_rowvec_bf16(emb.reshape(Fr * N, C), no_mask, keys0)
         text = sparse_prompt_embeddings.reshape(B, C).to(torch.float32)
@@ -134,9 +137,15 @@ class MaskDecoder(nn.Module):
 
     # ------------------------------------------------------------------ the two-way transformer
     def _pe_w(self, key, lin, pe):
-        """(pe . W^T) [N, internal] fp32 — the positional part of (keys + pe) W."""
+        """(pe . W^T) [N, internal] fp32 — the positional part of (keys + pe) W.  Cached per (weight, pe tensor); the cache
+        entry keeps `pe` alive, so its data pointer cannot be recycled for a different table while the entry exists."""
         w, _ = self._w32(key, lin)
-        return ops.small_linear(pe, w)
+        hit = self._pew.get(key)
+        sig = (lin.weight.data_ptr(), lin.weight._version, pe.data_ptr(), pe._version, tuple(pe.shape))
+        if hit is None or hit[0] != sig:
+            hit = (sig, pe, ops.small_linear(pe, w))
+            self._pew[key] = hit
+        return hit[2]
 
     def _image_proj(self, key, lin, keys, pe, N):
         """bf16 [rows, internal] = (keys (+pe)) W^T + b on the tcgen05 GEMM."""

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .common import LayerNorm2d, _ContainerOnly, f32
+from .common import LayerNorm2d, PackCache, _ContainerOnly, f32
 
 
 class PositionEmbeddingRandom(_ContainerOnly):
@@ -24,8 +24,11 @@ class PositionEmbeddingRandom(_ContainerOnly):
         self.register_buffer("positional_encoding_gaussian_matrix", scale * torch.randn((2, num_pos_feats)))
 
     def grid_tokens(self, G: int) -> torch.Tensor:
-        """token-major fp32 [G*G, 2*num_pos_feats]"""
-        return ops.dense_pe(f32(self.positional_encoding_gaussian_matrix), G)
+        """token-major fp32 [G*G, 2*num_pos_feats]; constant per (matrix, grid) -> computed once and reused (the reference
+        recomputes it every training step, GROVE.py:182, and hoists it in inference, infer_iground.py:157)."""
+        if not hasattr(self, "_pack"):
+            self._pack = PackCache()
+        return self._pack.get(("pe", G), [self.positional_encoding_gaussian_matrix], lambda g: ops.dense_pe(f32(g), G))
 
 
 class PromptEncoder(nn.Module):
@@ -53,7 +56,9 @@ class PromptEncoder(nn.Module):
         if self.image_embedding_size[1] != G:
             raise NotImplementedError("square embedding grids only")
         pe = self.pe_layer.grid_tokens(G)
-        return pe.view(1, G, G, self.embed_dim).permute(0, 3, 1, 2).to(self.pe_layer.positional_encoding_gaussian_matrix.dtype)
+        out = pe.view(1, G, G, self.embed_dim).permute(0, 3, 1, 2)   # a view: MaskDecoder recovers the cached token-major table
+        dt = self.pe_layer.positional_encoding_gaussian_matrix.dtype
+        return out if dt == torch.float32 else out.to(dt)
 
     def forward(self, points: Optional[Tuple[torch.Tensor, torch.Tensor]], boxes: Optional[torch.Tensor], masks: Optional[torch.Tensor],
                 text_embeds: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -1,0 +1,84 @@
+"""Sharding of the grounding path over the GPUs of one box.
+
+The path shards into independent units — one 8-frame window of one video (the Conv3d adapter couples the 8 frames of a
+window and nothing else, image_encoder.py:52-56) — so there is NO data-path collective.  The only exchange is the optional
+all-gather of packed per-frame records [frames, phrases, 5] = (cx, cy, w, h, objectness logit) when the windows of ONE video
+are split across ranks (BASELINE config 5); it replaces the reference's pickled `all_gather_object` of per-clip dicts
+(infer_iground.py:290-293).  Everything here is device-agnostic torch (NCCL on the B200 box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def sliding_segment_with_mask(num_frames: int = 48, num_segments: int = 8) -> Tuple[List[List[int]], List[List[int]]]:
+    """The reference's long-clip schedule (infer_iground.py:110-148): ceil(F/8) strided sparse windows
+    {i*(F//8) + off}, plus a 0/1 mask that drops frames already produced by an earlier window."""
+    seg, rem = num_frames // num_segments, num_frames % num_segments
+    all_idx, masks, seen = [], [], set()
+    for off in range(seg):
+        idx = [i * seg + off for i in range(num_segments)]
+        masks.append([0 if k in seen else 1 for k in idx])
+        all_idx.append(idx)
+        seen.update(idx)
+    for off in range(rem):
+        idx = [k for k in (i * seg + seg + off for i in range(num_segments)) if k < num_frames]
+        if idx:
+            masks.append([0 if k in seen else 1 for k in idx])
+            all_idx.append(idx)
+            seen.update(idx)
+    return all_idx, masks
+
+
+def units_of_rank(num_units: int, world: int, rank: int) -> List[int]:
+    """unit u -> rank u mod world (videos for configs 3/4, windows of one clip for config 5)."""
+    return list(range(rank, num_units, world))
+
+
+def ground_sharded_clip(window_fn: Callable[[List[int]], torch.Tensor], num_frames: int, num_phrases: int, *,
+                        group: Optional[dist.ProcessGroup] = None, device=None) -> torch.Tensor:
+    """Ground one long clip whose 8-frame windows are split across the ranks of `group`.
+
+    `window_fn(frame_ids) -> [8, P, 5]` runs the per-window hot path (encoder + decoder) on THIS rank and returns packed
+    records.  Returns, on every rank, the records of all frames in temporal order: [num_frames, P, 5] fp32.
+    One all-gather of a pre-packed buffer; no other communication."""
+    if num_frames % 8:
+        raise NotImplementedError("clips whose length is not a multiple of 8 produce windows of fewer than 8 frames, which the "
+                                  "reference's adapter cannot run either (image_encoder.py:52 hard-codes t=8)")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    windows, masks = sliding_segment_with_mask(num_frames, 8)
+    mine = units_of_rank(len(windows), world, rank)
+    per_rank = (len(windows) + world - 1) // world
+    buf = None
+    for slot, w in enumerate(mine):
+        rec = window_fn(windows[w])
+        if rec.shape != (8, num_phrases, 5):
+            raise ValueError(f"window_fn must return [8, {num_phrases}, 5], got {tuple(rec.shape)}")
+        if buf is None:
+            buf = torch.zeros(per_rank, 8, num_phrases, 5, dtype=torch.float32, device=rec.device)
+        buf[slot] = rec.float()
+    if buf is None:
+        buf = torch.zeros(per_rank, 8, num_phrases, 5, dtype=torch.float32, device=device or "cpu")
+    if world > 1:
+        gathered = torch.empty(world * per_rank, 8, num_phrases, 5, dtype=torch.float32, device=buf.device)
+        dist.all_gather_into_tensor(gathered, buf, group=group)
+    else:
+        gathered = buf
+    out = torch.zeros(num_frames, num_phrases, 5, dtype=torch.float32, device=buf.device)
+    for w, (idx, msk) in enumerate(zip(windows, masks)):
+        src = gathered[(w % world) * per_rank + w // world]
+        keep = [i for i, mk in enumerate(msk) if mk]
+        if keep:
+            out[[idx[i] for i in keep]] = src[keep]
+    return out
+
+
+def pack_records(boxes_nested, logits_nested) -> torch.Tensor:
+    """nested [V][T] lists of [P,4] boxes / [P] logits (the return value of _generate_and_postprocess_masks, GROVE.py:297-331)
+    for ONE video -> packed [T, P, 5]"""
+    fb, fl = boxes_nested[0], logits_nested[0]
+    return torch.stack([torch.cat([b.float(), l.float()[:, None]], 1) for b, l in zip(fb, fl)])
