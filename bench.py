@@ -24,6 +24,10 @@ import torch  # noqa: E402
 
 IMG, FRAMES, PHRASES, SEQ_L, VIT = 1024, 8, 4, 640, "vit_b"
 METRIC, UNIT = "grounding_path_frames_per_s", "frames/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch of the dominant kernel (qkv GEMM, M=32768 N=2304 K=768),
+# from the `ncu --set full` capture summarised in profiles/r1_ncu_full_summary.txt (algorithmic bytes of that launch: 205 MB)
+NCU_TRAFFIC_BYTES = 154364416
+NCU_TRAFFIC_NOTE = "qkv GEMM launch (M=32768,N=2304,K=768): 53.9 MB read + 100.4 MB written vs 205 MB algorithmic (profiles/r1_ncu_full_summary.txt)"
 
 
 def useful_flops_per_frame(D, depth, n_glob, G):
@@ -307,7 +311,8 @@ def main():
                 "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": FRAMES * PHRASES * 5 * 4},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                             "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                             "frac": achieved / pk["bf16_tflops_sustained"], "traffic": NCU_TRAFFIC_BYTES,
+                             "traffic_note": NCU_TRAFFIC_NOTE,
                              "kernel": "gemm_bf16_tcgen05_kernel (all GEMM + implicit-conv launches of one step: %d launches, %.3f ms, %.2f TFLOP)"
                                        % (len(rec), gemm_ms, gemm_flops / 1e12),
                              "peak_source": pk["src"] + " cuBLAS bf16 sustained (kernel timed inside a long step)",
