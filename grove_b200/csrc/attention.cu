@@ -278,24 +278,32 @@ attn_global_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 // =====================================================================================================
 constexpr int WS = 14, WQ = 196, WQP = 208;  // window side, tokens, tokens padded to 13 m-tiles / 26 n-tiles
 
-template <int NT>  // n-tiles (8 keys each) in this key block
-__device__ __forceinline__ void window_block(const uint32_t (&qf)[4][4], uint32_t sK, uint32_t sV, int key0, const float* relh_s,
-                                             const float* relw_s, int qrow_lo, float (&o)[8][4], float (&m_run)[2], float (&l_run)[2],
+// row addressing of a [rows][HD] bf16 tile: HD = 64 -> 128-byte rows with the XOR swizzle; HD = 80 (ViT-H) -> plain 160-byte
+// rows (8 consecutive rows land on banks 0,8,16,24,0,.. : a 2-way ldmatrix conflict, accepted)
+template <int HD>
+__device__ __forceinline__ uint32_t swh(uint32_t base, int row, int chunk) {
+  if (HD == 64) return base + row * 128 + ((chunk ^ (row & 7)) << 4);
+  return base + row * (HD * 2) + (chunk << 4);
+}
+
+template <int NT, int HD>  // n-tiles (8 keys each) in this key block; head dim
+__device__ __forceinline__ void window_block(const uint32_t (&qf)[HD / 16][4], uint32_t sK, uint32_t sV, int key0, const float* relh_s,
+                                             const float* relw_s, int qrow_lo, float (&o)[HD / 8][4], float (&m_run)[2], float (&l_run)[2],
                                              int lane) {
   const int g = lane >> 2, t = lane & 3;
   float s[NT][4];
 #pragma unroll
   for (int j = 0; j < NT; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
+  for (int ks = 0; ks < HD / 16; ++ks)
 #pragma unroll
     for (int jp = 0; jp < NT / 2; ++jp) {
       uint32_t bb[4];
-      ldsm_x4(sw(sK, key0 + jp * 16 + (lane & 7) + (lane >> 4) * 8, 2 * ks + ((lane >> 3) & 1)), bb);
+      ldsm_x4(swh<HD>(sK, key0 + jp * 16 + (lane & 7) + (lane >> 4) * 8, 2 * ks + ((lane >> 3) & 1)), bb);
       mma16816(s[2 * jp], qf[ks], bb[0], bb[1]);
       mma16816(s[2 * jp + 1], qf[ks], bb[2], bb[3]);
     }
-  const float scale_log2 = 0.125f * kLog2e;
+  const float scale_log2 = (HD == 64 ? 0.125f : 0.11180339887498949f) * kLog2e;   // hd^-0.5
   float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
   for (int j = 0; j < NT; ++j)
@@ -330,7 +338,7 @@ __device__ __forceinline__ void window_block(const uint32_t (&qf)[4][4], uint32_
   l_run[0] = l_run[0] * alpha[0] + rsum[0];
   l_run[1] = l_run[1] * alpha[1] + rsum[1];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < HD / 8; ++j) {
     o[j][0] *= alpha[0]; o[j][1] *= alpha[0];
     o[j][2] *= alpha[1]; o[j][3] *= alpha[1];
   }
@@ -342,47 +350,49 @@ __device__ __forceinline__ void window_block(const uint32_t (&qf)[4][4], uint32_
     pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
     pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-    for (int dp = 0; dp < 4; ++dp) {
+    for (int dp = 0; dp < HD / 16; ++dp) {
       uint32_t bb[4];
-      ldsm_x4_t(sw(sV, key0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * dp + (lane >> 4)), bb);
+      ldsm_x4_t(swh<HD>(sV, key0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * dp + (lane >> 4)), bb);
       mma16816(o[2 * dp], pa, bb[0], bb[1]);
       mma16816(o[2 * dp + 1], pa, bb[2], bb[3]);
     }
   }
 }
 
-__global__ void __launch_bounds__(128, 2)
+template <int HD>
+__global__ void __launch_bounds__(128, HD == 64 ? 2 : 1)
 attn_window_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ qkv_bias, const __nv_bfloat16* __restrict__ Rh,
                    const __nv_bfloat16* __restrict__ Rw, __nv_bfloat16* __restrict__ out, int G, int heads) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t s0 = (smem_u32(smem_raw) + 127u) & ~127u;
-  const uint32_t sQ = s0, sK = sQ + WQP * 128, sV = sK + WQP * 128, sRh = sV + WQP * 128, sRw = sRh + 32 * 128;
-  const uint32_t sBias = sRw + 32 * 128;  // relh [196][14] fp32 then relw [196][14] fp32
+  constexpr int RB = HD * 2, CH = HD / 8;   // bytes / 16-byte chunks per row
+  const uint32_t sQ = s0, sK = sQ + WQP * RB, sV = sK + WQP * RB, sRh = sV + WQP * RB, sRw = sRh + 32 * RB;
+  const uint32_t sBias = sRw + 32 * RB;  // relh [196][14] fp32 then relw [196][14] fp32
   float* relh_s = reinterpret_cast<float*>(smem_raw + (sBias - smem_u32(smem_raw)));
   float* relw_s = relh_s + WQ * WS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int nW = (G + WS - 1) / WS;
   const int wy = blockIdx.x / nW, wx = blockIdx.x % nW, h = blockIdx.y, f = blockIdx.z;
-  const int D = heads * 64;
+  const int D = heads * HD;
 
   // ---- stage Q, K, V of the window (pad tokens: k = b_k, v = b_v; rows >= 196: zeros) and the rel-pos tables
-  for (int i = tid; i < 3 * WQP * 8; i += 128) {
-    const int which = i / (WQP * 8), rem = i % (WQP * 8), row = rem >> 3, c = rem & 7;
-    const uint32_t dst = sw(sQ + which * (WQP * 128), row, c);
+  for (int i = tid; i < 3 * WQP * CH; i += 128) {
+    const int which = i / (WQP * CH), rem = i % (WQP * CH), row = rem / CH, c = rem % CH;
+    const uint32_t dst = swh<HD>(sQ + which * (WQP * RB), row, c);
     const int gy = wy * WS + row / WS, gx = wx * WS + row % WS;
     if (row < WQ && gy < G && gx < G) {
-      cp_async16(dst, qkv + (((size_t)(f * G + gy) * G + gx) * 3 + which) * D + h * 64 + c * 8);
+      cp_async16(dst, qkv + (((size_t)(f * G + gy) * G + gx) * 3 + which) * D + h * HD + c * 8);
     } else if (row < WQ && which > 0) {
-      st_smem16(dst, __ldg(reinterpret_cast<const uint4*>(qkv_bias + which * D + h * 64 + c * 8)));
+      st_smem16(dst, __ldg(reinterpret_cast<const uint4*>(qkv_bias + which * D + h * HD + c * 8)));
     } else {
       st_smem16(dst, make_uint4(0, 0, 0, 0));
     }
   }
-  for (int i = tid; i < 2 * 32 * 8; i += 128) {
-    const int which = i / 256, rem = i % 256, row = rem >> 3, c = rem & 7;
-    const uint32_t dst = sw(which ? sRw : sRh, row, c);
-    if (row < 2 * WS - 1) cp_async16(dst, (which ? Rw : Rh) + row * 64 + c * 8);
+  for (int i = tid; i < 2 * 32 * CH; i += 128) {
+    const int which = i / (32 * CH), rem = i % (32 * CH), row = rem / CH, c = rem % CH;
+    const uint32_t dst = swh<HD>(which ? sRw : sRh, row, c);
+    if (row < 2 * WS - 1) cp_async16(dst, (which ? Rw : Rh) + row * HD + c * 8);
     else st_smem16(dst, make_uint4(0, 0, 0, 0));
   }
   cp_async_commit();
@@ -391,9 +401,9 @@ attn_window_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 
   for (int mt = warp; mt < WQP / 16; mt += 4) {
     const int r0 = mt * 16;
-    uint32_t qf[4][4];
+    uint32_t qf[HD / 16][4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) ldsm_x4(sw(sQ, r0 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)), qf[ks]);
+    for (int ks = 0; ks < HD / 16; ++ks) ldsm_x4(swh<HD>(sQ, r0 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)), qf[ks]);
 
     // rel-pos products against the whole (27-row) tables, scattered to relh_s[q][kh], relw_s[q][kw] (pre-scaled by log2 e)
 #pragma unroll
@@ -402,11 +412,11 @@ attn_window_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
+      for (int ks = 0; ks < HD / 16; ++ks)
 #pragma unroll
         for (int jp = 0; jp < 2; ++jp) {
           uint32_t bb[4];
-          ldsm_x4(sw(which ? sRw : sRh, jp * 16 + (lane & 7) + (lane >> 4) * 8, 2 * ks + ((lane >> 3) & 1)), bb);
+          ldsm_x4(swh<HD>(which ? sRw : sRh, jp * 16 + (lane & 7) + (lane >> 4) * 8, 2 * ks + ((lane >> 3) & 1)), bb);
           mma16816(acc[2 * jp], qf[ks], bb[0], bb[1]);
           mma16816(acc[2 * jp + 1], qf[ks], bb[2], bb[3]);
         }
@@ -423,12 +433,12 @@ attn_window_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     }
     __syncwarp();
 
-    float o[8][4];
+    float o[HD / 8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    for (int j = 0; j < HD / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-    window_block<14>(qf, sK, sV, 0, relh_s, relw_s, r0 + g, o, m_run, l_run, lane);
-    window_block<12>(qf, sK, sV, 112, relh_s, relw_s, r0 + g, o, m_run, l_run, lane);
+    window_block<14, HD>(qf, sK, sV, 0, relh_s, relw_s, r0 + g, o, m_run, l_run, lane);
+    window_block<12, HD>(qf, sK, sV, 112, relh_s, relw_s, r0 + g, o, m_run, l_run, lane);
 
 #pragma unroll
     for (int rs = 0; rs < 2; ++rs) {
@@ -441,16 +451,17 @@ attn_window_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       const int gy = wy * WS + q / WS, gx = wx * WS + q % WS;
       if (q < WQ && gy < G && gx < G) {
         const float inv = 1.f / l_run[rs];
-        __nv_bfloat16* orow = out + ((size_t)(f * G + gy) * G + gx) * D + h * 64 + 2 * t;
+        __nv_bfloat16* orow = out + ((size_t)(f * G + gy) * G + gx) * D + h * HD + 2 * t;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t*>(orow + 8 * j) = pack_bf16(o[j][2 * rs] * inv, o[j][2 * rs + 1] * inv);
+        for (int j = 0; j < HD / 8; ++j) *reinterpret_cast<uint32_t*>(orow + 8 * j) = pack_bf16(o[j][2 * rs] * inv, o[j][2 * rs + 1] * inv);
       }
     }
   }
 }
 
 constexpr int kGlobalSmem = 5 * 16384 + 128;
-constexpr int kWindowSmem = 3 * WQP * 128 + 2 * 32 * 128 + 2 * WQ * WS * 4 + 128;
+template <int HD>
+constexpr int window_smem() { return 3 * WQP * HD * 2 + 2 * 32 * HD * 2 + 2 * WQ * WS * 4 + 128; }
 
 }  // namespace grove
 using namespace grove;
@@ -482,21 +493,29 @@ extern "C" int grove_attn_global_relpos_fwd_mma(const void* qkv, const void* rel
   return GROVE_OK;
 }
 
-extern "C" int grove_attn_window_relpos_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w,
-                                            void* out, int F, int G, int heads, int hd, int ws, cudaStream_t stream) {
-  GROVE_CHECK_ARG(qkv && qkv_bias_bf16 && rel_pos_h && rel_pos_w && out && F > 0 && G > 0 && heads > 0);
-  if (hd != 64 || ws != 14) {
-    grove_set_error("grove_attn_window_relpos_fwd: only hd=64, window 14 are built (got hd=%d ws=%d)", hd, ws);
-    return GROVE_ERR_UNSUPPORTED;
-  }
-  GROVE_CHECK_ARG(F <= 65535 && heads <= 65535);
+template <int HD>
+static int launch_window(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
+                         int heads, cudaStream_t stream) {
   const int nW = (G + WS - 1) / WS;
-  cudaError_t e = cudaFuncSetAttribute(attn_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWindowSmem);
+  constexpr int smem = window_smem<HD>();
+  cudaError_t e = cudaFuncSetAttribute(attn_window_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-  attn_window_kernel<<<dim3(nW * nW, heads, F), 128, kWindowSmem, stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_bias_bf16,
-                                                                            (const __nv_bfloat16*)rel_pos_h, (const __nv_bfloat16*)rel_pos_w,
-                                                                            (__nv_bfloat16*)out, G, heads);
+  attn_window_kernel<HD><<<dim3(nW * nW, heads, F), 128, smem, stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)qkv_bias_bf16,
+                                                                         (const __nv_bfloat16*)rel_pos_h, (const __nv_bfloat16*)rel_pos_w,
+                                                                         (__nv_bfloat16*)out, G, heads);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
+}
+
+extern "C" int grove_attn_window_relpos_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w,
+                                            void* out, int F, int G, int heads, int hd, int ws, cudaStream_t stream) {
+  GROVE_CHECK_ARG(qkv && qkv_bias_bf16 && rel_pos_h && rel_pos_w && out && F > 0 && G > 0 && heads > 0);
+  if ((hd != 64 && hd != 80) || ws != 14) {
+    grove_set_error("grove_attn_window_relpos_fwd: head dim 64 / 80 and window 14 are built (got hd=%d ws=%d)", hd, ws);
+    return GROVE_ERR_UNSUPPORTED;
+  }
+  GROVE_CHECK_ARG(F <= 65535 && heads <= 65535);
+  return hd == 64 ? launch_window<64>(qkv, qkv_bias_bf16, rel_pos_h, rel_pos_w, out, F, G, heads, stream)
+                  : launch_window<80>(qkv, qkv_bias_bf16, rel_pos_h, rel_pos_w, out, F, G, heads, stream);
 }

@@ -20,21 +20,29 @@
 namespace grove {
 
 constexpr int kAttThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two threads per query row)
-constexpr int kKStages = 4, kVStages = 2;
+constexpr int kVStages = 2;
+template <int HD> constexpr int k_stages() { return HD == 64 ? 4 : 3; }
 
-template <int G>
+// Head dim 80 (ViT-H) = a 64-wide part (128-byte rows, SWIZZLE_128B) + a 16-wide tail (32-byte rows, SWIZZLE_32B): every operand
+// tile is [128 x 64 | 128 x 16], Q.K^T takes a 5th k-step from the tails, P.V issues a second N=16 MMA into O columns 64-79.
+struct AttTmaps { CUtensorMap qkv, rh, rw, qkv_x, rh_x, rw_x; };
+
+template <int G, int HD>
 __global__ void __launch_bounds__(kAttThreads, 1)
-attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_rh,
-                      const __grid_constant__ CUtensorMap tmap_rw, __nv_bfloat16* __restrict__ out, int heads) {
+attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __restrict__ out, int heads) {
+  constexpr bool kX = HD > 64;                      // has the 16-wide tail
+  constexpr int TS = 16384 + (kX ? 4096 : 0);       // bytes of one [128 x HD] operand tile
+  constexpr int kKStages = k_stages<HD>();
+  const CUtensorMap& tmap_qkv = tm.qkv; const CUtensorMap& tmap_rh = tm.rh; const CUtensorMap& tmap_rw = tm.rw;
   constexpr int N = G * G;
   constexpr int NB = N / 128;          // key blocks
   constexpr int NKW = G;               // rel_w entries per row
   extern __shared__ uint8_t smem_raw[];
   const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = s0;                         // 16 KB   Q tile [128][64] bf16, SW128
-  const uint32_t sK = sQ + 16384;                 // kKStages x 16 KB K ring
-  const uint32_t sV = sK + kKStages * 16384;      // 2 x 16 KB V ring; during the prologue: Rh | Rw tables
-  const uint32_t sP = sV + kVStages * 16384;      // 2 x 32 KB P buffers (two 64-key slabs each); prologue: fp32 staging [128][128]
+  const uint32_t sQ = s0;                         // Q tile [128][HD] bf16
+  const uint32_t sK = sQ + TS;                    // kKStages K tiles
+  const uint32_t sV = sK + kKStages * TS;         // 2 V tiles; during the prologue: Rw | Rh tables
+  const uint32_t sP = sV + kVStages * TS;      // 2 x 32 KB P buffers (two 64-key slabs each); prologue: fp32 staging [128][128]
   const uint32_t sRelH = sP + 65536;              // [G][128] fp32
   const uint32_t sXch = sRelH + G * 128 * 4;      // 2 x [2][128] fp32: max and sum exchange between the two threads of a row
   const uint32_t bar0 = sXch + 2048;
@@ -49,7 +57,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, f = blockIdx.z;
-  const int D = heads * 64;
+  const int D = heads * HD;
   const int tok0 = f * N;                // first token row of this frame in the [F*N, 3D] qkv matrix
 
   if (warp == 0 && lane == 0) {
@@ -74,33 +82,38 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(bar(Q_FULL), 3 * 16384);
-      tma_load_2d(sQ, &tmap_qkv, bar(Q_FULL), h * 64, tok0 + q0);
-      tma_load_2d(sV, &tmap_rw, bar(Q_FULL), 0, 0);            // Rw table -> first V slot (rows >= 2G-1 zero-filled)
-      tma_load_2d(sV + 16384, &tmap_rh, bar(Q_FULL), 0, 0);    // Rh table -> second V slot
+      auto load_tile = [&](uint32_t dst, const CUtensorMap* main_map, const CUtensorMap* tail_map, uint32_t b, int col, int rowc) {
+        tma_load_2d(dst, main_map, b, col, rowc);
+        if (kX) tma_load_2d(dst + 16384, tail_map, b, col + 64, rowc);
+      };
+      mbar_expect_tx(bar(Q_FULL), 3 * TS);
+      load_tile(sQ, &tmap_qkv, &tm.qkv_x, bar(Q_FULL), h * HD, tok0 + q0);
+      load_tile(sV, &tmap_rw, &tm.rw_x, bar(Q_FULL), 0, 0);          // Rw table -> first V slot (rows >= 2G-1 zero-filled)
+      load_tile(sV + TS, &tmap_rh, &tm.rh_x, bar(Q_FULL), 0, 0);     // Rh table -> second V slot
       uint32_t kit = 0, vit = 0;
       for (int b = 0; b < NB; ++b, ++kit) {                    // phase 1: K only
         const int s = kit % kKStages;
         mbar_wait(bar(K_EMPTY + s), ((kit / kKStages) & 1u) ^ 1u);
-        mbar_expect_tx(bar(K_FULL + s), 16384);
-        tma_load_2d(sK + s * 16384, &tmap_qkv, bar(K_FULL + s), D + h * 64, tok0 + b * 128);
+        mbar_expect_tx(bar(K_FULL + s), TS);
+        load_tile(sK + s * TS, &tmap_qkv, &tm.qkv_x, bar(K_FULL + s), D + h * HD, tok0 + b * 128);
       }
       mbar_wait(bar(TAB_FREE), 0);                             // prologue MMAs have finished reading the tables
       for (int b = 0; b < NB; ++b, ++kit, ++vit) {             // phase 2: K and V
         const int s = kit % kKStages;
         mbar_wait(bar(K_EMPTY + s), ((kit / kKStages) & 1u) ^ 1u);
-        mbar_expect_tx(bar(K_FULL + s), 16384);
-        tma_load_2d(sK + s * 16384, &tmap_qkv, bar(K_FULL + s), D + h * 64, tok0 + b * 128);
+        mbar_expect_tx(bar(K_FULL + s), TS);
+        load_tile(sK + s * TS, &tmap_qkv, &tm.qkv_x, bar(K_FULL + s), D + h * HD, tok0 + b * 128);
         const int v = vit % kVStages;
         mbar_wait(bar(V_EMPTY + v), ((vit / kVStages) & 1u) ^ 1u);
-        mbar_expect_tx(bar(V_FULL + v), 16384);
-        tma_load_2d(sV + v * 16384, &tmap_qkv, bar(V_FULL + v), 2 * D + h * 64, tok0 + b * 128);
+        mbar_expect_tx(bar(V_FULL + v), TS);
+        load_tile(sV + v * TS, &tmap_qkv, &tm.qkv_x, bar(V_FULL + v), 2 * D + h * HD, tok0 + b * 128);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
+    constexpr uint32_t idesc_ox = umma_idesc_bf16(128, 16) | (1u << 16);  // the 16-wide tail of V -> O columns 64..79
     uint32_t sit = 0, kit = 0, vit = 0;
     auto issue_s = [&](uint32_t b_smem) {   // S[sit&1] = Q . B^T  (B: [128 rows][64] K-major)
       const uint32_t sb = sit & 1u;
@@ -110,6 +123,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           tc_mma_f16(tS0 + sb * 128, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(b_smem + k * 32), idesc_s, k != 0);
+        if (kX) tc_mma_f16(tS0 + sb * 128, umma_desc_sw32(sQ + 16384), umma_desc_sw32(b_smem + 16384), idesc_s, 1);
       }
       __syncwarp();
     };
@@ -119,7 +133,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     if (lane == 0) tc_commit(bar(S_FULL + 0));
     __syncwarp();
     ++sit;
-    issue_s(sV + 16384);                               // T_h
+    issue_s(sV + TS);                                  // T_h
     if (lane == 0) { tc_commit(bar(S_FULL + 1)); tc_commit(bar(TAB_FREE)); }
     __syncwarp();
     ++sit;
@@ -127,7 +141,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       const int s = kit % kKStages;
       mbar_wait(bar(K_FULL + s), (kit / kKStages) & 1u);
       tc_fence_after();
-      issue_s(sK + s * 16384);
+      issue_s(sK + s * TS);
       if (lane == 0) { tc_commit(bar(K_EMPTY + s)); tc_commit(bar(S_FULL + (sit & 1u))); }
       __syncwarp();
     }
@@ -136,7 +150,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       const int s = kit % kKStages;
       mbar_wait(bar(K_FULL + s), (kit / kKStages) & 1u);
       tc_fence_after();
-      issue_s(sK + s * 16384);
+      issue_s(sK + s * TS);
       if (lane == 0) { tc_commit(bar(K_EMPTY + s)); tc_commit(bar(S_FULL + (sit & 1u))); }
       __syncwarp();
       ++kit; ++sit;
@@ -153,8 +167,9 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t da = umma_desc_sw128(sP + pb * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32);
-          const uint64_t db = umma_desc_sw128(sV + v * 16384 + kk * 2048);
+          const uint64_t db = umma_desc_sw128(sV + v * TS + kk * 2048);
           tc_mma_f16(tO, da, db, idesc_o, (b | kk) != 0);
+          if (kX) tc_mma_f16(tO + 64, da, umma_desc_sw32(sV + v * TS + 16384 + kk * 512), idesc_ox, (b | kk) != 0);
         }
         tc_commit(bar(V_EMPTY + v));
         tc_commit(bar(P_EMPTY + pb));
@@ -205,7 +220,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
       }
       softmax_sync();                                    // staging is rewritten by the next table / rel_h complete
     }
-    const float c_scale = 0.125f * kL2e;                 // hd^-0.5 * log2(e), hd = 64
+    const float c_scale = (HD == 64 ? 0.125f : 0.11180339887498949f) * kL2e;   // hd^-0.5 * log2(e)
     // ---- phase 1: exact row max
     float m = -INFINITY;
     for (int b = 0; b < NB; ++b, ++sit) {
@@ -281,7 +296,7 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     const float inv = 1.f / (lsum + xch_f[256 + (hs ^ 1) * 128 + row]);
     mbar_wait(bar(O_FULL), 0);
     tc_fence_after();
-    __nv_bfloat16* orow = out + ((size_t)tok0 + q) * D + h * 64 + hs * 32;
+    __nv_bfloat16* orow = out + ((size_t)tok0 + q) * D + h * HD + hs * 32;
     {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tO + hs * 32 + tlane, r);
@@ -292,32 +307,49 @@ attn_global_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
             make_uint4(pack_bf16(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv), pack_bf16(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv),
                        pack_bf16(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv), pack_bf16(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv));
     }
+    if (kX) {   // head dims 64..79: 8 per thread of the pair
+      uint32_t r[8];
+      tmem_ld_32x32b_x8(tO + 64 + hs * 8 + tlane, r);
+      tmem_ld_wait();
+      *reinterpret_cast<uint4*>(out + ((size_t)tok0 + q) * D + h * HD + 64 + hs * 8) =
+          make_uint4(pack_bf16(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv), pack_bf16(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv),
+                     pack_bf16(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv), pack_bf16(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv));
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int G>
-constexpr int att_tc_smem() { return 16384 + kKStages * 16384 + kVStages * 16384 + 65536 + G * 128 * 4 + 2048 /*xch*/ + 1024 /*align*/ + 512 /*barriers*/; }
+template <int G, int HD>
+constexpr int att_tc_smem() {
+  return (1 + k_stages<HD>() + kVStages) * (16384 + (HD > 64 ? 4096 : 0)) + 65536 + G * 128 * 4 + 2048 /*xch*/ + 1024 /*align*/ + 512 /*barriers*/;
+}
 
 int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows);
 
 }  // namespace grove
 using namespace grove;
 
-template <int G>
+template <int G, int HD>
 static int launch_att_tc(const void* qkv, const void* rh, const void* rw, void* out, int F, int heads, cudaStream_t stream) {
-  const int N = G * G, D = heads * 64;
-  CUtensorMap tq, th, tw;
+  const int N = G * G, D = heads * HD;
+  AttTmaps tm;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)3 * D, (uint64_t)F * N, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&th, rh, 64, 2 * G - 1, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tw, rw, 64, 2 * G - 1, 64, 128))) return rc;
-  constexpr int smem = att_tc_smem<G>();
-  cudaError_t e = cudaFuncSetAttribute(attn_global_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if ((rc = make_tmap_bf16_2d(&tm.qkv, qkv, (uint64_t)3 * D, (uint64_t)F * N, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm.rh, rh, HD, 2 * G - 1, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm.rw, rw, HD, 2 * G - 1, 64, 128))) return rc;
+  if (HD > 64) {
+    if ((rc = make_tmap_bf16_2d(&tm.qkv_x, qkv, (uint64_t)3 * D, (uint64_t)F * N, 16, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm.rh_x, rh, HD, 2 * G - 1, 16, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm.rw_x, rw, HD, 2 * G - 1, 16, 128))) return rc;
+  } else {
+    tm.qkv_x = tm.qkv; tm.rh_x = tm.rh; tm.rw_x = tm.rw;
+  }
+  constexpr int smem = att_tc_smem<G, HD>();
+  cudaError_t e = cudaFuncSetAttribute(attn_global_tc_kernel<G, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-  attn_global_tc_kernel<G><<<dim3(N / 128, heads, F), kAttThreads, smem, stream>>>(tq, th, tw, (__nv_bfloat16*)out, heads);
+  attn_global_tc_kernel<G, HD><<<dim3(N / 128, heads, F), kAttThreads, smem, stream>>>(tm, (__nv_bfloat16*)out, heads);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
@@ -326,12 +358,14 @@ static int launch_att_tc(const void* qkv, const void* rh, const void* rw, void* 
 extern "C" int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G, int heads,
                                             int hd, cudaStream_t stream) {
   GROVE_CHECK_ARG(qkv && rel_pos_h && rel_pos_w && out && F > 0 && heads > 0);
-  if (hd != 64 || (G != 64 && G != 32)) {
-    grove_set_error("grove_attn_global_relpos_fwd: only hd=64 and G in {32,64} are built (got hd=%d G=%d)", hd, G);
+  if ((hd != 64 && hd != 80) || (G != 64 && G != 32)) {
+    grove_set_error("grove_attn_global_relpos_fwd: head dim 64 / 80 and G in {32,64} are built (got hd=%d G=%d)", hd, G);
     return GROVE_ERR_UNSUPPORTED;
   }
   GROVE_CHECK_ARG(F <= 65535 && heads <= 65535);
   GROVE_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)rel_pos_h & 15) == 0 && ((uintptr_t)rel_pos_w & 15) == 0);
-  return G == 64 ? launch_att_tc<64>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream)
-                 : launch_att_tc<32>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream);
+  if (hd == 64) return G == 64 ? launch_att_tc<64, 64>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream)
+                               : launch_att_tc<32, 64>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream);
+  return G == 64 ? launch_att_tc<64, 80>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream)
+                 : launch_att_tc<32, 80>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream);
 }

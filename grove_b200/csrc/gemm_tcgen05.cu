@@ -351,7 +351,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 tensor, innermost dimension contiguous; dims/box listed innermost first.  128-byte swizzle, zero OOB fill.
-static int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+static int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint32_t* box,
+                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { grove_set_error("cuTensorMapEncodeTiled entry point not available"); return GROVE_ERR_CUDA; }
   cuuint64_t gdim[5], gstr[4];
@@ -365,15 +366,16 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint
     if (i < rank - 1) gstr[i] = stride;
   }
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { grove_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return GROVE_ERR_CUDA; }
   return GROVE_OK;
 }
 
+// box_inner * 2 bytes must equal the swizzle span (64 elements -> 128B swizzle, 16 elements -> 32B swizzle)
 int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows) {
   uint64_t d[2] = {inner, rows};
   uint32_t b[2] = {box_inner, box_rows};
-  return make_tmap_bf16(m, base, 2, d, b);
+  return make_tmap_bf16(m, base, 2, d, b, box_inner == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 static int g_num_sms = 0;

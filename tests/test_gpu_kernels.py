@@ -122,11 +122,10 @@ def _ref_attention(qkv, rel_h, rel_w, B, S, heads, hd):
     return o.view(B, heads, S, S, hd).permute(0, 2, 3, 1, 4).reshape(B, S, S, heads * hd)
 
 
-@pytest.mark.parametrize("legacy", [False, True])
+@pytest.mark.parametrize("legacy,hd", [(False, 64), (True, 64), (False, 80)])
 @pytest.mark.parametrize("G,Fr,heads", [(64, 2, 3), (32, 3, 2)])
-def test_global_attention(ops, G, Fr, heads, legacy):
-    """legacy=False: the tcgen05/TMEM kernel the modules use; legacy=True: the mma.sync cross-check kernel"""
-    hd = 64
+def test_global_attention(ops, G, Fr, heads, legacy, hd):
+    """legacy=False: the tcgen05/TMEM kernel the modules use (head dim 64 = ViT-B/L, 80 = ViT-H); legacy=True: the mma.sync cross-check"""
     qkv = _rand((Fr, G, G, 3, heads, hd), 20, dtype=torch.bfloat16)
     rh, rw = _rand((2 * G - 1, hd), 21, 0.1, dtype=torch.bfloat16), _rand((2 * G - 1, hd), 22, 0.1, dtype=torch.bfloat16)
     out = torch.full((Fr, G, G, heads * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
@@ -138,9 +137,10 @@ def test_global_attention(ops, G, Fr, heads, legacy):
     assert float((out.float() - ref).abs().mean()) < 2e-3
 
 
+@pytest.mark.parametrize("hd", [64, 80])
 @pytest.mark.parametrize("G,Fr,heads", [(64, 2, 2), (32, 1, 3), (28, 1, 1)])
-def test_window_attention_with_padding(ops, G, Fr, heads):
-    hd, ws = 64, 14
+def test_window_attention_with_padding(ops, G, Fr, heads, hd):
+    ws = 14
     D = heads * hd
     qkv_bias = _rand((3 * D,), 23, 0.5)
     qkv = _rand((Fr, G, G, 3, heads, hd), 24, dtype=torch.bfloat16)

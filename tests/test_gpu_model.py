@@ -129,7 +129,7 @@ def _run_encoder_case(vit, img, frames, seed):
     return sam, sd, out, ref
 
 
-@pytest.mark.parametrize("vit,img,frames", [("vit_b", 512, 8), ("vit_b", 1024, 8)])
+@pytest.mark.parametrize("vit,img,frames", [("vit_b", 512, 8), ("vit_b", 1024, 8), ("vit_l", 512, 8), ("vit_h", 512, 8), ("vit_h", 1024, 8)])
 def test_image_encoder_vs_oracle(vit, img, frames):
     sam, sd, out, ref = _run_encoder_case(vit, img, frames, 11)
     assert out.shape == ref.shape
