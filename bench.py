@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 IMG, FRAMES, PHRASES, SEQ_L, VIT = 1024, 8, 4, 640, "vit_b"
+VIDEOS = 1   # videos per GPU per step (config 3: 2)
 METRIC, UNIT = "grounding_path_frames_per_s", "frames/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch of the dominant kernel (qkv GEMM, M=32768 N=2304 K=768),
 # from the `ncu --set full` capture summarised in profiles/r1_ncu_full_summary.txt (algorithmic bytes of that launch: 205 MB)
@@ -109,11 +110,12 @@ def synth_inputs(n_sets, seed0=100):
     from oracle import synth
     sets = []
     for i in range(n_sets):
-        images = synth.synth_tensor(f"bench.images.{i}", (1, 3, FRAMES, IMG, IMG), seed0 + i).to(torch.bfloat16)
-        hidden = synth.synth_tensor(f"bench.hidden.{i}", (1, SEQ_L, 4096), seed0 + i).to(torch.bfloat16)
-        ids = torch.full((1, SEQ_L - 575), 7, dtype=torch.long)
-        for p in synth.det_positions(SEQ_L, PHRASES, seed0 + i):
-            ids[0, p - 575 + 1] = 32005
+        images = synth.synth_tensor(f"bench.images.{i}", (VIDEOS, 3, FRAMES, IMG, IMG), seed0 + i).to(torch.bfloat16)
+        hidden = synth.synth_tensor(f"bench.hidden.{i}", (VIDEOS, SEQ_L, 4096), seed0 + i).to(torch.bfloat16)
+        ids = torch.full((VIDEOS, SEQ_L - 575), 7, dtype=torch.long)
+        for v in range(VIDEOS):
+            for p in synth.det_positions(SEQ_L, PHRASES, seed0 + i + 1000 * v):
+                ids[v, p - 575 + 1] = 32005
         sets.append((images, hidden, ids))
     return sets
 
@@ -197,8 +199,10 @@ def run_reference(args, rank):
 
 
 def workload_config(n):
-    return {"workload": f"SAM ViT-B encoder (+4 Conv3d adapters) + text projection + box decoder + heads; 1 video x {FRAMES} frames at {IMG}^2, "
-                        f"{PHRASES} phrases per GPU (BASELINE configs[1])", "frames_per_step_per_gpu": FRAMES, "phrases": PHRASES,
+    name = {"vit_b": "ViT-B", "vit_l": "ViT-L", "vit_h": "ViT-H"}[VIT]
+    cfgname = "BASELINE configs[1]" if (VIT, VIDEOS) == ("vit_b", 1) else ("BASELINE configs[2], one GPU's share" if (VIT, VIDEOS) == ("vit_h", 2) else "non-default")
+    return {"workload": f"SAM {name} encoder (+4 Conv3d adapters) + text projection + box decoder + heads; {VIDEOS} video(s) x {FRAMES} frames at {IMG}^2, "
+                        f"{PHRASES} phrases per GPU ({cfgname})", "frames_per_step_per_gpu": FRAMES * VIDEOS, "phrases": PHRASES,
             "image_size": IMG, "sharding": f"by video, {n} GPU(s), no data-path collective",
             "l2": "4 rotating input sets (220 MB) and a ~3 GB per-step activation working set, both larger than the 126 MB L2"}
 
@@ -211,7 +215,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="grove_b200", choices=["grove_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vit", default="vit_b", choices=["vit_b", "vit_l", "vit_h"], help="non-default workloads are for profiling only")
+    ap.add_argument("--videos", type=int, default=1, help="videos per GPU per step (BASELINE configs[2] = vit_h with 2)")
     args = ap.parse_args()
+    global VIT, VIDEOS
+    VIT, VIDEOS = args.vit, args.videos
+    if (VIT, VIDEOS) != ("vit_b", 1):
+        args.no_cpu_baseline = True
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -297,18 +307,19 @@ def main():
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     step_ms = ms / args.steps
     G = IMG // 16
-    flops_step = FRAMES * useful_flops_per_frame(cfg["embed_dim"], cfg["depth"], len(cfg["global_idx"]), G) + \
-        FRAMES * PHRASES * decoder_flops_per_instance(G * G) + PHRASES * 35.7e6
+    TOT = FRAMES * VIDEOS
+    flops_step = TOT * useful_flops_per_frame(cfg["embed_dim"], cfg["depth"], len(cfg["global_idx"]), G) + \
+        TOT * PHRASES * decoder_flops_per_instance(G * G) + VIDEOS * PHRASES * 35.7e6
     step_tflops = flops_step / (step_ms * 1e-3) / 1e12
 
     if rank == 0:
-        value = world * FRAMES * args.steps / (ms * 1e-3)
-        e2e_v = world * FRAMES * args.steps / (ms_e2e * 1e-3)
+        value = world * TOT * args.steps / (ms * 1e-3)
+        e2e_v = world * TOT * args.steps / (ms_e2e * 1e-3)
         h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
-                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": FRAMES * PHRASES * 5 * 4},
+                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOT * PHRASES * 5 * 4},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                              "frac": achieved / pk["bf16_tflops_sustained"], "traffic": NCU_TRAFFIC_BYTES,

@@ -7,6 +7,10 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 
+if len(sys.argv) > 1:
+    bench.VIT = sys.argv[1]
+if len(sys.argv) > 2:
+    bench.VIDEOS = int(sys.argv[2])
 dev = torch.device("cuda:0")
 torch.cuda.set_device(dev)
 gb, sd, cfg = bench.build_model(dev)

@@ -138,13 +138,12 @@ def test_image_encoder_vs_oracle(vit, img, frames):
     assert float(d.mean()) < 1e-2 and float(d.max()) < 0.15   # LayerNorm-ed outputs are O(1); output itself is bf16 (ulp 8e-3)
 
 
-def test_end_to_end_config2():
-    """BASELINE config 2: ViT-B encoder + box decoder, 1 video x 8 frames at 1024^2, 4 phrases, bf16, vs the fp32 oracle."""
+def _end_to_end(vit, img, V, P, seed):
     from grove_b200.modeling.grounding import GroundingBranch
     from oracle.grounding import VIT_CFG
-    cfg = VIT_CFG["vit_b"]
-    seed, img, L, P = 21, 1024, 640, 4
-    gb = GroundingBranch(vit="vit_b", num_frames=8, image_size=img)
+    cfg = VIT_CFG[vit]
+    L = 640
+    gb = GroundingBranch(vit=vit, num_frames=8, image_size=img)
     shapes = {**synth.encoder_param_shapes(cfg["embed_dim"], cfg["depth"], cfg["heads"], cfg["global_idx"], img // 16),
               **synth.decoder_param_shapes()}
     sd = synth.synth_state_dict(shapes, seed)
@@ -152,11 +151,12 @@ def test_end_to_end_config2():
     gb.grounding_encoder.load_state_dict(sd, strict=False)
     gb.text_hidden_fcs.load_state_dict({k[len("text_hidden_fcs."):]: v for k, v in fsd.items()})
     gb = gb.cuda()   # parameters stay fp32 masters; the pipeline picks bf16 operands / fp32 accumulation itself
-    images = synth.synth_tensor("cfg2.images", (1, 3, 8, img, img), seed).cuda().to(torch.bfloat16)
-    hid = synth.synth_tensor("cfg2.hidden", (1, L, 4096), seed).cuda().to(torch.bfloat16)
-    ids = torch.full((1, L - 575), 7, dtype=torch.long)
-    for p in synth.det_positions(L, P, seed):
-        ids[0, p - 575 + 1] = gb.det_token_idx
+    images = synth.synth_tensor(f"e2e.{vit}.images", (V, 3, 8, img, img), seed).cuda().to(torch.bfloat16)
+    hid = synth.synth_tensor(f"e2e.{vit}.hidden", (V, L, 4096), seed).cuda().to(torch.bfloat16)
+    ids = torch.full((V, L - 575), 7, dtype=torch.long)
+    for v in range(V):
+        for p in synth.det_positions(L, P, seed + v):
+            ids[v, p - 575 + 1] = gb.det_token_idx
     mask = gb._create_det_token_mask(ids.cuda())
     emb, (boxes, logits) = gb.ground(images, hid, mask, infer=False)
     b = torch.cat([x for v in boxes for x in v]).float()
@@ -166,8 +166,43 @@ def test_end_to_end_config2():
         _, rb, rl, reps = og.grounding_forward(images.float(), hid.float(), mask, full, depth=cfg["depth"], heads=cfg["heads"],
                                                global_idx=cfg["global_idx"])
     eb, el = float((b - rb).abs().max()), float((l - rl).abs().max())
-    print(f"config2: max|dbox|={eb:.2e} max|dlogit|={el:.2e} min|ref logit|={float(rl.abs().min()):.3f}")
-    assert reps == [P] * 8
+    print(f"{vit}@{img} V={V}: max|dbox|={eb:.2e} max|dlogit|={el:.2e} min|ref logit|={float(rl.abs().min()):.3f}")
+    assert reps == [P] * (8 * V)
     assert eb < BOX_TOL and el < LOGIT_TOL
     safe = rl.abs() > LOGIT_TOL          # decisions are well-defined only outside the float tolerance band of the threshold
     assert torch.equal((torch.sigmoid(l) > 0.5)[safe], (torch.sigmoid(rl) > 0.5)[safe])
+
+
+def test_end_to_end_config2():
+    """BASELINE config 2: ViT-B encoder + box decoder, 1 video x 8 frames at 1024^2, 4 phrases, bf16 operands, vs the fp32 oracle."""
+    _end_to_end("vit_b", 1024, 1, 4, 21)
+
+
+def test_end_to_end_config3_one_gpu_share():
+    """BASELINE config 3 as seen by ONE of the 8 GPUs: ViT-H (head dim 80), 2 videos x 8 frames at 1024^2, 4 phrases each."""
+    _end_to_end("vit_h", 1024, 2, 4, 22)
+
+
+def test_sharded_long_clip_single_rank():
+    """BASELINE config 5 on one rank: a 32-frame clip cut into the reference's strided 8-frame windows (infer_iground.py:110-148),
+    each grounded by the real pipeline, records re-assembled in temporal order; equals grounding the windows directly."""
+    from grove_b200 import parallel
+    from grove_b200.modeling.grounding import GroundingBranch
+    seed, img, L, P, Ftot = 23, 512, 640, 3, 32
+    gb = GroundingBranch(vit="vit_b", num_frames=8, image_size=img).cuda()
+    clip = synth.synth_tensor("clip.images", (1, 3, Ftot, img, img), seed).cuda().to(torch.bfloat16)
+    hid = synth.synth_tensor("clip.hidden", (1, L, 4096), seed).cuda().to(torch.bfloat16)
+    ids = torch.full((1, L - 575), 7, dtype=torch.long)
+    for p in synth.det_positions(L, P, seed):
+        ids[0, p - 575 + 1] = gb.det_token_idx
+    mask = gb._create_det_token_mask(ids.cuda())
+
+    def window_fn(frame_ids):
+        _, (b, l) = gb.ground(clip[:, :, frame_ids].contiguous(), hid, mask, infer=False)
+        return parallel.pack_records(b, l)
+    out = parallel.ground_sharded_clip(window_fn, Ftot, P)
+    assert out.shape == (Ftot, P, 5)
+    windows, _ = parallel.sliding_segment_with_mask(Ftot, 8)
+    rec = window_fn(windows[1])
+    assert torch.equal(out[windows[1]], rec.float())
+    assert torch.isfinite(out).all() and float(out[..., :4].min()) > 0 and float(out[..., :4].max()) < 1
