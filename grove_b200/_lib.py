@@ -30,6 +30,7 @@ SIGNATURES = {
     "grove_im2col_patch16": [_P, _P, _I, _I, _I, _I, _P],
     "grove_layernorm": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "grove_attn_window_relpos_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_attn_window_relpos_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd_mma": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_cast_f32_bf16": [_P, _P, _LL, _P],

@@ -77,7 +77,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS0 = tmem_base, tO = tmem_base + 256;
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 256, tP0 = tmem_base + 384;   // S0|S1 (2x128), O (<=80), P0|P1 (2x64: bf16 pairs)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -166,10 +166,10 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       if (lane == 0) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t da = umma_desc_sw128(sP + pb * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32);
+          const uint32_t ta = tP0 + pb * 64 + kk * 8;        // P[:, 16 keys] = 8 packed columns of tensor memory
           const uint64_t db = umma_desc_sw128(sV + v * TS + kk * 2048);
-          tc_mma_f16(tO, da, db, idesc_o, (b | kk) != 0);
-          if (kX) tc_mma_f16(tO + 64, da, umma_desc_sw32(sV + v * TS + 16384 + kk * 512), idesc_ox, (b | kk) != 0);
+          tc_mma_f16_ts(tO, ta, db, idesc_o, (b | kk) != 0);
+          if (kX) tc_mma_f16_ts(tO + 64, ta, umma_desc_sw32(sV + v * TS + 16384 + kk * 512), idesc_ox, (b | kk) != 0);
         }
         tc_commit(bar(V_EMPTY + v));
         tc_commit(bar(P_EMPTY + pb));
@@ -276,17 +276,11 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
           lsum += p0 + p1;
           pk[j >> 1] = pack_bf16(p0, p1);
         }
-        // keys [c*32, c*32+32) of the block -> slab c/2, 16-byte chunks (c%2)*4 .. +3 of this row, XOR-swizzled by the row
-        const uint32_t prow = sP + pb * 32768 + (c >> 1) * 16384 + row * 128;
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint32_t ch = (uint32_t)((c & 1) * 4 + k4) ^ (uint32_t)(row & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (ch << 4)), "r"(pk[4 * k4]), "r"(pk[4 * k4 + 1]), "r"(pk[4 * k4 + 2]),
-                       "r"(pk[4 * k4 + 3])
-                       : "memory");
-        }
+        // keys [c*32, c*32+32) of the block -> 16 packed bf16x2 columns of the P buffer in tensor memory (the A operand of P.V)
+        tmem_st_32x32b_x16(tP0 + pb * 64 + c * 16 + tlane, pk);
       }
-      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(P_FULL + pb));
     }

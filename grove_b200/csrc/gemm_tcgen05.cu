@@ -378,6 +378,10 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t
   return make_tmap_bf16(m, base, 2, d, b, box_inner == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+int make_tmap_bf16_nd(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+  return make_tmap_bf16(m, base, rank, dims, box, box[0] == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {

@@ -178,12 +178,14 @@ class ImageEncoderViT(nn.Module):
             wq, bq = self._linear(k + ".qkv", blk.attn.qkv)
             ops.gemm(h, wq, qkv, bias=bq)
             S = blk.window_size if blk.window_size > 0 else G
-            rh = self._pack.get(k + ".rh", [blk.attn.rel_pos_h], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
-            rw = self._pack.get(k + ".rw", [blk.attn.rel_pos_w], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
             if blk.window_size > 0:
                 bqb = self._pack.get(k + ".qkvb16", [blk.attn.qkv.bias], bf16)
-                ops.attn_window(qkv, bqb, rh, rw, att, F=Fr, G=G, heads=heads, hd=hd, ws=blk.window_size)
+                tab = self._pack.get(k + ".reltab", [blk.attn.rel_pos_h, blk.attn.rel_pos_w],
+                                     lambda a, b, S=S: ops.window_rel_table(_resize_rel_pos(a, S), _resize_rel_pos(b, S)))
+                ops.attn_window_tc(qkv, bqb, tab, att, F=Fr, G=G, heads=heads, hd=hd, ws=blk.window_size)
             else:
+                rh = self._pack.get(k + ".rh", [blk.attn.rel_pos_h], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
+                rw = self._pack.get(k + ".rw", [blk.attn.rel_pos_w], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
                 ops.attn_global(qkv, rh, rw, att, F=Fr, G=G, heads=heads, hd=hd)
             wp, bp = self._linear(k + ".proj", blk.attn.proj)
             ops.gemm(att, wp, xs, bias=bp, resid=xs)

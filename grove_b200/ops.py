@@ -91,6 +91,24 @@ def attn_window(qkv, qkv_bias_bf16, rel_h, rel_w, out, *, F, G, heads, hd, ws=14
     return out
 
 
+def window_rel_table(rel_h, rel_w):
+    """[64, hd] bf16 table for the tcgen05 window kernel: rows 0..26 rel_pos_h, rows 32..58 rel_pos_w"""
+    assert rel_h.shape[0] == 27 and rel_w.shape[0] == 27
+    t = torch.zeros(64, rel_h.shape[1], device=rel_h.device, dtype=BF16)
+    t[0:27] = rel_h.to(BF16)
+    t[32:59] = rel_w.to(BF16)
+    return t
+
+
+def attn_window_tc(qkv, qkv_bias_bf16, rel_table, out, *, F, G, heads, hd, ws=14):
+    for t, n in ((qkv, "qkv"), (qkv_bias_bf16, "qkv_bias"), (rel_table, "rel_table"), (out, "out")):
+        _req(t, BF16, n)
+    assert qkv.numel() == F * G * G * 3 * heads * hd and rel_table.shape == (64, hd)
+    check(lib().grove_attn_window_relpos_tc_fwd(_p(qkv), _p(qkv_bias_bf16), _p(rel_table), _p(out), F, G, heads, hd, ws, _stream(qkv)),
+          "grove_attn_window_relpos_tc_fwd")
+    return out
+
+
 def attn_global(qkv, rel_h, rel_w, out, *, F, G, heads, hd, legacy_mma=False):
     for t, n in ((qkv, "qkv"), (rel_h, "rel_pos_h"), (rel_w, "rel_pos_w"), (out, "out")):
         _req(t, BF16, n)

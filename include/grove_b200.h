@@ -73,9 +73,15 @@ int grove_layernorm(const float* x, const float* gamma, const float* beta, void*
  * (bf16): window_partition's zero padding after norm1 (image_encoder.py:245-249,344-348) is reproduced by
  * giving pad tokens k = b_k, v = b_v (qkv_bias, bf16) — they receive softmax mass like in the reference —
  * and window_unpartition's crop (:382-383) by not computing pad queries.  rel_pos_h/w: [2*ws-1, hd] bf16.
- * out[F,G,G,heads*hd] bf16.  Replaces Attention.forward :301-326 + add_decomposed_rel_pos :420-458. */
+ * out[F,G,G,heads*hd] bf16.  Replaces Attention.forward :301-326 + add_decomposed_rel_pos :420-458.
+ * (legacy warp-level mma.sync implementation, kept as an independent cross-check for the tests) */
 int grove_attn_window_relpos_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w,
                                  void* out, int F, int G, int heads, int hd, int ws, grove_stream_t stream);
+/* The same contract on tcgen05/TMEM/TMA (attention_win_tc.cu): persistent CTAs over (frame, window, head) units, one 4-D TMA
+ * box per operand, pad tokens patched in shared memory, P kept in tensor memory.  rel_table: bf16 [64, hd] with rows 0..26 =
+ * rel_pos_h, rows 32..58 = rel_pos_w, other rows zero.  This is the kernel the modules call. */
+int grove_attn_window_relpos_tc_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_table, void* out, int F, int G, int heads,
+                                    int hd, int ws, grove_stream_t stream);
 /* Global attention over one frame's G*G tokens with decomposed rel-pos bias (tables [2G-1, hd] bf16): tcgen05/TMEM/TMA
  * kernel (attention_tc.cu), exact two-phase softmax, scores never leave the SM.  qkv [F,G,G,3,heads,hd], out [F,G,G,heads*hd]. */
 int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,

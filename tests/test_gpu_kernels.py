@@ -137,16 +137,22 @@ def test_global_attention(ops, G, Fr, heads, legacy, hd):
     assert float((out.float() - ref).abs().mean()) < 2e-3
 
 
+@pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("hd", [64, 80])
-@pytest.mark.parametrize("G,Fr,heads", [(64, 2, 2), (32, 1, 3), (28, 1, 1)])
-def test_window_attention_with_padding(ops, G, Fr, heads, hd):
+@pytest.mark.parametrize("G,Fr,heads", [(64, 2, 2), (32, 1, 3), (28, 1, 1), (64, 3, 16)])
+def test_window_attention_with_padding(ops, G, Fr, heads, hd, tc):
+    """tc=True: the tcgen05/TMEM kernel the modules use; tc=False: the mma.sync cross-check kernel"""
     ws = 14
     D = heads * hd
     qkv_bias = _rand((3 * D,), 23, 0.5)
     qkv = _rand((Fr, G, G, 3, heads, hd), 24, dtype=torch.bfloat16)
     rh, rw = _rand((2 * ws - 1, hd), 25, 0.1, dtype=torch.bfloat16), _rand((2 * ws - 1, hd), 26, 0.1, dtype=torch.bfloat16)
     out = torch.full((Fr, G, G, D), float("nan"), device="cuda", dtype=torch.bfloat16)
-    ops.attn_window(qkv, qkv_bias.to(torch.bfloat16), rh, rw, out, F=Fr, G=G, heads=heads, hd=hd, ws=ws)
+    if tc:
+        ops.attn_window_tc(qkv, qkv_bias.to(torch.bfloat16), ops.window_rel_table(rh, rw), out, F=Fr, G=G, heads=heads, hd=hd, ws=ws)
+    else:
+        ops.attn_window(qkv, qkv_bias.to(torch.bfloat16), rh, rw, out, F=Fr, G=G, heads=heads, hd=hd, ws=ws)
+    torch.cuda.synchronize()
     # reference: pad tokens carry qkv = bias (x = 0 after norm1, image_encoder.py:245-249); partition, attend, unpartition
     Gp = ((G + ws - 1) // ws) * ws
     full = qkv_bias.to(torch.bfloat16).float().view(1, 1, 1, 3 * D).expand(Fr, Gp, Gp, 3 * D).clone()
