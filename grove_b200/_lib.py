@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libgrove_b200.so")
 class GemmEpilogue(C.Structure):
     """mirror of `struct grove_gemm_epilogue`"""
     _fields_ = [("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_row_mod", C.c_int), ("gate_alpha", C.c_void_p),
-                ("act", C.c_int), ("out_f32", C.c_int), ("out2_bf16", C.c_void_p), ("max_ctas", C.c_int), ("force_ctas", C.c_int)]
+                ("act", C.c_int), ("out_f32", C.c_int), ("out2_bf16", C.c_void_p), ("max_ctas", C.c_int), ("force_ctas", C.c_int),
+                ("out2_pre_act", C.c_int), ("dact_pre", C.c_void_p), ("dact", C.c_int), ("splits", C.c_int)]
 
 
 _P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
@@ -39,7 +40,7 @@ SIGNATURES = {
     "grove_gather_rows_bf16": [_P, _I, _P, _P, _I, _I, _P],
     "grove_dense_pe": [_P, _P, _I, _I, _P],
     "grove_add_rowvec_bf16": [_P, _P, _P, _LL, _I, _P],
-    "grove_decoder_t2i_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_decoder_t2i_attention": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_decoder_i2t_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_decoder_keys_add_ln": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "grove_small_linear_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -49,8 +50,27 @@ SIGNATURES = {
     "grove_box_losses_fwd": [_P, _P, _P, _P, _P, _P, _I, _P],
     "grove_box_iou": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "grove_greedy_match": [_P, _P, _D, _D, _P, _P, _I, _I, _P],
+    # training step (backward pass)
+    "grove_conv_wgrad_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "grove_transpose_to_bf16": [_P, _I, _P, _I, _I, _P],
+    "grove_transpose_shift3_to_bf16": [_P, _I, _P, _I, _I, _I, _P],
+    "grove_reduce_partials_f32": [_P, _I, _LL, _P, _I, _F, _P],
+    "grove_layernorm_bwd": [_P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _LL, _I, _F, _P],
+    "grove_adapter_gate_bwd": [_P, _P, _P, _P, _P, _P, _LL, _I, _P],
+    "grove_colsum": [_P, _I, _P, _LL, _I, _P],
+    "grove_segment_sum_f32": [_P, _P, _P, _I, _LL, _I, _P],
+    "grove_small_wgrad_f32": [_P, _P, _P, _I, _I, _I, _P],
+    "grove_act_bwd_f32": [_P, _P, _P, _LL, _I, _P],
+    "grove_token_self_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "grove_decoder_t2i_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_decoder_i2t_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_batch_sum_bf16": [_P, _P, _I, _LL, _P],
+    "grove_attn_relpos_bwd_workspace_bytes": [_I, _I, _I, _I, _I],
+    "grove_attn_relpos_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_box_losses_bwd": [_P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _P],
 }
-_RESTYPES = {"grove_last_error": C.c_char_p, "grove_launch_count": C.c_longlong, "grove_reset_launch_count": None}
+_RESTYPES = {"grove_last_error": C.c_char_p, "grove_launch_count": C.c_longlong, "grove_reset_launch_count": None,
+             "grove_attn_relpos_bwd_workspace_bytes": C.c_longlong}
 
 _lib = None
 
@@ -66,7 +86,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if l.grove_abi_version() != 1:
+        if l.grove_abi_version() != 2:
             raise RuntimeError("libgrove_b200.so ABI version mismatch; rebuild")
         _lib = l
     return _lib

@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgrove_b200.so")
-SOURCES = ["lib.cu", "gemm_tcgen05.cu", "encoder_ops.cu", "attention.cu", "attention_tc.cu", "attention_win_tc.cu", "decoder_ops.cu", "box_ops.cu"]
+SOURCES = ["lib.cu", "gemm_tcgen05.cu", "encoder_ops.cu", "attention.cu", "attention_tc.cu", "attention_win_tc.cu", "decoder_ops.cu", "box_ops.cu",
+           "backward_ops.cu", "attention_bwd.cu", "decoder_bwd.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-I", os.path.join(ROOT, "include"), "-I", CSRC, "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -21,7 +22,7 @@ def _stale(out, deps):
 
 def build(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
-    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tmem_ldst.cuh"), os.path.join(ROOT, "include", "grove_b200.h")]
+    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tmem_ldst.cuh"), os.path.join(CSRC, "mma_sync.cuh"), os.path.join(ROOT, "include", "grove_b200.h")]
     objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

@@ -64,7 +64,7 @@ __global__ void add_rowvec_bf16_kernel(const __nv_bfloat16* __restrict__ x, cons
 template <int T, int DH>
 __global__ void __launch_bounds__(128) t2i_attention_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                             const __nv_bfloat16* __restrict__ v, const int* __restrict__ src_of,
-                                                            float* __restrict__ out, int N, int heads) {
+                                                            float* __restrict__ out, float* __restrict__ lse_out, int N, int heads) {
   static_assert(DH == 16, "one key/value head row = two 16-byte loads");
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int HD = heads * DH;
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(128) t2i_attention_kernel(const float* __restr
     for (int i = 0; i < 128; ++i) lsum += red_l[t][i];
     const float a = red_acc[t][d][0] + red_acc[t][d][1] + red_acc[t][d][2] + red_acc[t][d][3];
     out[((size_t)b * T + t) * HD + h * DH + d] = a / lsum;
+    if (lse_out && d == 0) lse_out[((size_t)b * T + t) * heads + h] = gm[t] + log2f(lsum);   // log2 domain, scale folded in (backward pass)
   }
-  (void)gm;
 }
 
 // ---------------------------------------------------------------- image -> token attention (per key row, T tokens)
@@ -358,11 +358,11 @@ extern "C" int grove_add_rowvec_bf16(const void* x, const float* vec, void* y, l
   return GROVE_OK;
 }
 
-extern "C" int grove_decoder_t2i_attention(const float* q, const void* k, const void* v, const int* src_of, float* out, int B, int T, int N,
-                                           int heads, int dh, cudaStream_t stream) {
+extern "C" int grove_decoder_t2i_attention(const float* q, const void* k, const void* v, const int* src_of, float* out, float* lse_out, int B, int T,
+                                           int N, int heads, int dh, cudaStream_t stream) {
   GROVE_CHECK_ARG(q && k && v && out && B > 0 && N > 0 && heads > 0);
   if (T != 6 || dh != 16) { grove_set_error("t2i attention is built for T=6 tokens, 16-dim heads (got T=%d dh=%d)", T, dh); return GROVE_ERR_UNSUPPORTED; }
-  t2i_attention_kernel<6, 16><<<dim3(B, heads), 128, 0, stream>>>(q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, src_of, out, N, heads);
+  t2i_attention_kernel<6, 16><<<dim3(B, heads), 128, 0, stream>>>(q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, src_of, out, lse_out, N, heads);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;

@@ -25,8 +25,13 @@ constexpr int kEpiWarps = 8;
 struct GemmParams {
   int M, N;
   int num_m_blocks, num_n_blocks, num_k_blocks;
-  int conv;            // 0: A is a plain [M,K] matrix; 1: implicit-GEMM taps over [V,T,G,G,C]
+  int conv;            // 0: A is a plain [M,K] matrix; 1: implicit-GEMM taps over [V,T,G,G,C] (A shifted);
+                       // 2: conv weight gradient — K runs over tokens, B is X^T [C,V,T,G,G] fetched at shifted (w,h,t)
   int G, rows_per_tile, tiles_per_frame, T, kt, kc_blocks;
+  int cblocks_per_tap, kblocks_per_frame, rows_per_kblock, wg_C;   // conv == 2
+  int splits, kb_per_split;                                   // split-K: partial sums to out + split*M*N (fp32)
+  const __nv_bfloat16* dact_pre;  // bf16 [M,N] or null: multiply by act'(dact_pre) (backward of GELU / ReLU)
+  int dact;            // 1 exact-GELU derivative, 2 ReLU mask
   const float* bias;   // [N] or null
   const float* resid;  // fp32 [*,N] or null
   int resid_mod;       // >0: residual row = m % resid_mod (abs-pos embedding broadcast over frames)
@@ -35,6 +40,7 @@ struct GemmParams {
   void* out;           // [M,N] fp32 or bf16
   int out_f32;
   __nv_bfloat16* out2; // optional extra bf16 copy of the output (feeds the next tensor-core op)
+  int out2_pre;        // 1: out2 receives the value BEFORE the activation (saved for the backward pass)
 };
 
 // CTAS = 1: one CTA owns a 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns a 256 x BN tile —
@@ -73,7 +79,8 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;   // m-blocks of 128*CTAS rows
+  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;    // m-blocks of 128*CTAS rows
+  const int num_tiles = tiles_mn * p.splits;
   const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
@@ -105,14 +112,21 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = (tile / p.num_n_blocks) * CTAS + (int)cta_rank;   // this CTA's 128-row block
-        const int n_blk = tile % p.num_n_blocks;
+        const int sp = tile / tiles_mn, tmn = tile % tiles_mn;
+        const int m_blk = (tmn / p.num_n_blocks) * CTAS + (int)cta_rank;   // this CTA's 128-row block
+        const int n_blk = tmn % p.num_n_blocks;
+        const int kb_begin = sp * p.kb_per_split, kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
         int f = 0, h0 = 0;
-        if (p.conv) {
+        if (p.conv == 1) {
           f = m_blk / p.tiles_per_frame;
           h0 = (m_blk % p.tiles_per_frame) * p.rows_per_tile;
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+        int wtap = 0, wc0 = 0;
+        if (p.conv == 2) {
+          wtap = n_blk / p.cblocks_per_tap;
+          wc0 = (n_blk % p.cblocks_per_tap) * BN + (int)cta_rank * Cfg::kBRows;
+        }
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -121,7 +135,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
           const int brow = n_blk * BN + (int)cta_rank * Cfg::kBRows;
           if (CTAS == 1) {
             mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-            if (!p.conv) {
+            if (p.conv != 1) {
               tma_load_2d(sa, &tmap_a, full_bar(s), kb * BK, m_blk * BM);
             } else {
               const int tap = kb / p.kc_blocks, c0 = (kb % p.kc_blocks) * BK;
@@ -130,11 +144,21 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
               else           { dh = tap / 3 - 1; dw = tap % 3 - 1; }
               tma_load_5d(sa, &tmap_a, full_bar(s), c0, dw, h0 + dh, (f % p.T) + dt, f / p.T);
             }
-            tma_load_2d(sb, &tmap_b, full_bar(s), kb * BK, brow);
+            if (p.conv != 2) {
+              tma_load_2d(sb, &tmap_b, full_bar(s), kb * BK, brow);
+            } else {
+              int dt = 0, dh, dw;
+              if (p.kt == 3) { dt = wtap / 9 - 1; dh = (wtap / 3) % 3 - 1; dw = wtap % 3 - 1; }
+              else           { dh = wtap / 3 - 1; dw = wtap % 3 - 1; }
+              const int fr = kb / p.kblocks_per_frame, s0 = (kb % p.kblocks_per_frame) * BK;
+              // the w shift selects one of the three pre-shifted planes (outermost coordinate); the h shift moves the origin of the
+              // flattened (h,w) axis by whole grid rows (16-byte aligned, zero fill above / below the frame); t shifts its own axis
+              tma_load_4d_cta(sb, &tmap_b, full_bar(s), s0 + dh * p.G, (fr % p.T) + dt, fr / p.T, (dw + 1) * p.wg_C + wc0);
+            }
           } else {
             // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
             if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
-            if (!p.conv) {
+            if (p.conv != 1) {
               tma_load_2d_cg2(sa, &tmap_a, full_bar(s), kb * BK, m_blk * BM);
             } else {
               const int tap = kb / p.kc_blocks, c0 = (kb % p.kc_blocks) * BK;
@@ -143,7 +167,17 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
               else           { dh = tap / 3 - 1; dw = tap % 3 - 1; }
               tma_load_5d_cg2(sa, &tmap_a, full_bar(s), c0, dw, h0 + dh, (f % p.T) + dt, f / p.T);
             }
-            tma_load_2d_cg2(sb, &tmap_b, full_bar(s), kb * BK, brow);
+            if (p.conv != 2) {
+              tma_load_2d_cg2(sb, &tmap_b, full_bar(s), kb * BK, brow);
+            } else {
+              int dt = 0, dh, dw;
+              if (p.kt == 3) { dt = wtap / 9 - 1; dh = (wtap / 3) % 3 - 1; dw = wtap % 3 - 1; }
+              else           { dh = wtap / 3 - 1; dw = wtap % 3 - 1; }
+              const int fr = kb / p.kblocks_per_frame, s0 = (kb % p.kblocks_per_frame) * BK;
+              // the w shift selects one of the three pre-shifted planes (outermost coordinate); the h shift moves the origin of the
+              // flattened (h,w) axis by whole grid rows (16-byte aligned, zero fill above / below the frame); t shifts its own axis
+              tma_load_4d_cg2(sb, &tmap_b, full_bar(s), s0 + dh * p.G, (fr % p.T) + dt, fr / p.T, (dw + 1) * p.wg_C + wc0);
+            }
           }
         }
       }
@@ -158,7 +192,9 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);  // epilogues (of both CTAs) have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
+        const int sp = tile / tiles_mn;
+        const int kb_begin = sp * p.kb_per_split, kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1u;
           mbar_wait(full_bar(s), ph);
@@ -170,15 +206,15 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t da = umma_desc_sw128(sa + k * 32);
               const uint64_t db = umma_desc_sw128(sb + k * 32);
-              if (CTAS == 2) tc_mma_f16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
-              else           tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0);
+              if (CTAS == 2) tc_mma_f16_cg2(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0);
+              else           tc_mma_f16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0);
             }
             if (CTAS == 2) {
               tc_commit_cg2(empty_bar(s), 3);                                   // frees the slot in both CTAs
-              if (kb == p.num_k_blocks - 1) tc_commit_cg2(tfull_bar(acc), 3);   // accumulators complete in both CTAs
+              if (kb == kb_end - 1) tc_commit_cg2(tfull_bar(acc), 3);   // accumulators complete in both CTAs
             } else {
               tc_commit(empty_bar(s));
-              if (kb == p.num_k_blocks - 1) tc_commit(tfull_bar(acc));
+              if (kb == kb_end - 1) tc_commit(tfull_bar(acc));
             }
           }
           __syncwarp();
@@ -198,9 +234,11 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     constexpr int kPasses = BN / 2 / 32;
     uint32_t tile_it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
-      const int m_blk = (tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
+      const int sp = tile / tiles_mn, tmn = tile % tiles_mn;
+      const int m_blk = (tmn / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tmn % p.num_n_blocks;
       const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
       const int row_base = m_blk * BM + quad * 32;
+      float* const out_f = reinterpret_cast<float*>(p.out) + (size_t)sp * p.M * p.N;   // split-K partial plane
       bool waited = false;
 #pragma unroll 1
       for (int ps = 0; ps < kPasses; ++ps) {
@@ -240,12 +278,14 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
             v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
             if (p.act == 1) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
             else if (p.act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (p.out2_pre && p.out2 && row < p.M)   // value after the activation, before gate / residual (saved for the backward pass)
+              *reinterpret_cast<uint2*>(p.out2 + (size_t)row * p.N + col0 + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
             if (p.gate_alpha) { v.x *= gate; v.y *= gate; v.z *= gate; v.w *= gate; }
             if (p.resid) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
             if (row < p.M) {
               const size_t o = (size_t)row * p.N + col0 + c;
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = v;
-              if (p.out2) *reinterpret_cast<uint2*>(p.out2 + o) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+              *reinterpret_cast<float4*>(out_f + o) = v;
+              if (p.out2 && !p.out2_pre) *reinterpret_cast<uint2*>(p.out2 + o) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
             }
           }
         } else {
@@ -262,6 +302,15 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
                 res[2 * i] = *reinterpret_cast<const float4*>(rp);
                 res[2 * i + 1] = *reinterpret_cast<const float4*>(rp + 4);
               }
+            }
+          }
+          uint4 pre[4];
+          if (p.dact_pre) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = row_base + 8 * i + (lane >> 2);
+              pre[i] = make_uint4(0, 0, 0, 0);
+              if (row < p.M) pre[i] = *reinterpret_cast<const uint4*>(p.dact_pre + (size_t)row * p.N + col0 + c);
             }
           }
           float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
@@ -289,6 +338,9 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(u.x), "=f"(u.y), "=f"(u.z), "=f"(u.w) : "r"(a));
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(a + 16));
             float v[8] = {u.x + ba.x, u.y + ba.y, u.z + ba.z, u.w + ba.w, w.x + bb.x, w.y + bb.y, w.z + bb.z, w.w + bb.w};
+            if (p.out2_pre && p.out2 && row < p.M)
+              *reinterpret_cast<uint4*>(p.out2 + (size_t)row * p.N + col0 + c) =
+                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             if (p.act == 1) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]);
@@ -300,6 +352,15 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] *= gate;
             }
+            if (p.dact_pre) {
+              const uint32_t pu[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 z = unpack_bf16(pu[j]);
+                if (p.dact == 1) { v[2 * j] *= gelu_grad(z.x); v[2 * j + 1] *= gelu_grad(z.y); }
+                else             { v[2 * j] = z.x > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = z.y > 0.f ? v[2 * j + 1] : 0.f; }
+              }
+            }
             if (p.resid) {
               v[0] += res[2 * i].x; v[1] += res[2 * i].y; v[2] += res[2 * i].z; v[3] += res[2 * i].w;
               v[4] += res[2 * i + 1].x; v[5] += res[2 * i + 1].y; v[6] += res[2 * i + 1].z; v[7] += res[2 * i + 1].w;
@@ -308,7 +369,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
               const size_t o = (size_t)row * p.N + col0 + c;
               const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
               *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pk;
-              if (p.out2) *reinterpret_cast<uint4*>(p.out2 + o) = pk;
+              if (p.out2 && !p.out2_pre) *reinterpret_cast<uint4*>(p.out2 + o) = pk;
             }
           }
         }
@@ -402,7 +463,7 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& ta, const CUtenso
     if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
     attr_set = true;
   }
-  int grid = p.num_m_blocks * p.num_n_blocks * CTAS;
+  int grid = p.num_m_blocks * p.num_n_blocks * p.splits * CTAS;
   int cap = max_ctas > 0 ? max_ctas : num_sms();
   cap -= cap % CTAS;
   if (cap < CTAS) cap = CTAS;
@@ -426,18 +487,28 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& ta, const CUtenso
 
 // tile configuration: CTA pairs (256 x 256 tiles) whenever the problem has them, else single-CTA 128 x {256,128} tiles
 static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K_total, int N, int M, bool conv, const uint64_t* adims,
-                         const uint32_t* abox, int arank, int max_ctas, int force_ctas, cudaStream_t st) {
+                         const uint32_t* abox, int arank, int max_ctas, int force_ctas, cudaStream_t st, const uint64_t* bdims5 = nullptr) {
   const int BN = (N % 256 == 0) ? 256 : 128;
   int ctas = (BN == 256 && M >= 256) ? 2 : 1;
   if (force_ctas == 1 || force_ctas == 2) ctas = (force_ctas == 2 && BN == 256) ? 2 : 1;
   p.num_m_blocks = (M + BM * ctas - 1) / (BM * ctas);
   p.num_n_blocks = N / BN;
+  if (p.splits < 1) p.splits = 1;
+  p.kb_per_split = (p.num_k_blocks + p.splits - 1) / p.splits;
+  p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_tmap_bf16(&ta, A_or_X, arank, adims, abox))) return rc;
-  uint64_t db[2] = {(uint64_t)K_total, (uint64_t)N};
-  uint32_t bb[2] = {BK, (uint32_t)(BN / ctas)};
-  if ((rc = make_tmap_bf16(&tb, W, 2, db, bb))) return rc;
+  if (p.conv == 2) {
+    // B = X^T in three w-shifted planes [3*C, V, T, G*G] (channel-major); a 64-token k-block is 64 consecutive (h,w) positions of a frame
+    p.cblocks_per_tap = p.wg_C / BN;
+    uint32_t bb4[4] = {(uint32_t)BK, 1, 1, (uint32_t)(BN / ctas)};
+    if ((rc = make_tmap_bf16(&tb, W, 4, bdims5, bb4))) return rc;
+  } else {
+    uint64_t db[2] = {(uint64_t)K_total, (uint64_t)N};
+    uint32_t bb[2] = {BK, (uint32_t)(BN / ctas)};
+    if ((rc = make_tmap_bf16(&tb, W, 2, db, bb))) return rc;
+  }
   (void)conv;
   if (ctas == 2) return launch_gemm<256, 2>(p, ta, tb, max_ctas, st);
   return BN == 256 ? launch_gemm<256, 1>(p, ta, tb, max_ctas, st) : launch_gemm<128, 1>(p, ta, tb, max_ctas, st);
@@ -455,7 +526,15 @@ static int fill_epilogue(GemmParams& p, const grove_gemm_epilogue* e, int M, int
   p.act = e ? e->act : 0;
   p.out_f32 = e ? e->out_f32 : 0;
   p.out2 = e ? reinterpret_cast<__nv_bfloat16*>(e->out2_bf16) : nullptr;
+  p.out2_pre = e ? e->out2_pre_act : 0;
+  p.dact_pre = e ? reinterpret_cast<const __nv_bfloat16*>(e->dact_pre) : nullptr;
+  p.dact = e ? e->dact : 0;
+  p.splits = (e && e->splits > 1) ? e->splits : 1;
   GROVE_CHECK_ARG(p.act >= 0 && p.act <= 2);
+  GROVE_CHECK_ARG(!p.dact_pre || ((p.dact == 1 || p.dact == 2) && !p.out_f32 && ((uintptr_t)p.dact_pre & 15) == 0));
+  GROVE_CHECK_ARG(p.out2_pre == 0 || (p.out2_pre == 1 && !p.out_f32) || (p.out2_pre == 2 && p.out_f32));
+  // split-K writes raw fp32 partial planes [splits, M, N]; reduce them with grove_reduce_partials_f32
+  GROVE_CHECK_ARG(p.splits == 1 || (p.out_f32 && !p.bias && !p.resid && !p.gate_alpha && !p.act && !p.out2));
   GROVE_CHECK_ARG(((uintptr_t)p.bias & 15) == 0 && ((uintptr_t)p.resid & 15) == 0 && ((uintptr_t)p.out2 & 15) == 0);
   (void)M; (void)N;
   return GROVE_OK;
@@ -497,4 +576,31 @@ extern "C" int grove_conv_gemm_bf16(const void* X, const void* Wp, void* out, in
   uint64_t da[5] = {(uint64_t)C, (uint64_t)G, (uint64_t)G, (uint64_t)T, (uint64_t)V};
   uint32_t ba[5] = {BK, (uint32_t)G, (uint32_t)(BM / G), 1, 1};
   return dispatch_gemm(p, X, Wp, ntaps * C, N, p.M, true, da, ba, 5, epi ? epi->max_ctas : 0, epi ? epi->force_ctas : 0, stream);
+}
+
+/* Weight gradient of the implicit-GEMM convolutions: dWp[N, taps*C] (tap-major, fp32) = sum over tokens of
+ * dY[token, n] * X[token + shift(tap), c].  dYt is dY transposed ([N, tokens] bf16); Xt3 holds X channel-major in three
+ * w-shifted planes ([3, C, V,T,G,G] bf16, grove_transpose_shift3_to_bf16): K runs over tokens, the B operand is fetched with a
+ * 5-D TMA box whose origin carries the tap's (h,t) shift (zero fill = 'same' padding) and whose plane carries the w shift. */
+extern "C" int grove_conv_wgrad_bf16(const void* dYt, const void* Xt, float* dWp, int V, int T, int G, int C, int N, int kt, int splits,
+                                     cudaStream_t stream) {
+  GROVE_CHECK_ARG(dYt && Xt && dWp && V > 0 && T > 0 && G > 0 && C > 0 && N > 0);
+  GROVE_CHECK_ARG(kt == 1 || kt == 3);
+  GROVE_CHECK_ARG(64 % G == 0 && (G * G) % 64 == 0 && G >= 8);   // the h shift moves the box origin by G elements: 16-byte aligned
+  GROVE_CHECK_ARG(C % 256 == 0);   // an n-block of 256 output columns is (tap, channel block)
+  GROVE_CHECK_ARG(((uintptr_t)dYt & 15) == 0 && ((uintptr_t)Xt & 15) == 0 && ((uintptr_t)dWp & 15) == 0);
+  const int ntaps = kt * 9;
+  const long long tokens = (long long)V * T * G * G;
+  GemmParams p{};
+  p.M = N; p.N = ntaps * C;
+  p.num_k_blocks = (int)(tokens / BK);
+  p.conv = 2; p.G = G; p.T = T; p.kt = kt;
+  p.kblocks_per_frame = G * G / BK; p.rows_per_kblock = BK / G;
+  p.out = dWp; p.out_f32 = 1;
+  p.splits = splits > 1 ? splits : 1;
+  uint64_t da[2] = {(uint64_t)tokens, (uint64_t)N};
+  uint32_t ba[2] = {BK, BM};
+  p.wg_C = C;
+  uint64_t db5[4] = {(uint64_t)G * G, (uint64_t)T, (uint64_t)V, (uint64_t)3 * C};
+  return dispatch_gemm(p, dYt, Xt, (int)tokens, p.N, p.M, true, da, ba, 2, 0, 0, stream, db5);
 }

@@ -28,8 +28,12 @@ def _req(t: torch.Tensor, dtype, name: str):
     return t
 
 
-def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas=0):
+def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas=0, out2_pre_act=0, dact_pre=None, dact=None, splits=1):
     e = GemmEpilogue()
+    e.out2_pre_act = int(out2_pre_act)
+    e.dact_pre = None if dact_pre is None else _req(dact_pre, BF16, "dact_pre").data_ptr()
+    e.dact = ACT[dact] if dact_pre is not None else 0
+    e.splits = int(splits)
     e.bias = None if bias is None else _req(bias, F32, "bias").data_ptr()
     e.resid = None if resid is None else _req(resid, F32, "resid").data_ptr()
     e.resid_row_mod = int(resid_row_mod)
@@ -42,25 +46,29 @@ def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, 
     return e
 
 
-def gemm(a, w, out, *, bias=None, resid=None, resid_row_mod=0, gate_alpha=None, act=None, out2=None, max_ctas=0, force_ctas=0):
-    """out[M,N] = resid + tanh(gate_alpha) * act(a[M,K] @ w[N,K]^T + bias)   (tcgen05 GEMM)"""
+def gemm(a, w, out, *, bias=None, resid=None, resid_row_mod=0, gate_alpha=None, act=None, out2=None, max_ctas=0, force_ctas=0,
+         out2_pre_act=0, dact_pre=None, dact=None, splits=1):
+    """out[M,N] = resid + tanh(gate_alpha) * act(a[M,K] @ w[N,K]^T + bias) * dact'(dact_pre)   (tcgen05 GEMM).
+    splits > 1: out is fp32 [splits, M, N] raw partial sums (finish with reduce_partials)."""
     _req(a, BF16, "a"); _req(w, BF16, "w")
     M, K = a.shape
     N = w.shape[0]
-    assert w.shape[1] == K and out.shape == (M, N) and out.is_contiguous() and out.dtype in (BF16, F32)
-    e = _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas)
+    assert w.shape[1] == K and out.is_contiguous() and out.dtype in (BF16, F32)
+    assert out.shape == ((M, N) if splits == 1 else (splits, M, N))
+    e = _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas, out2_pre_act, dact_pre, dact, splits)
     check(lib().grove_gemm_bf16(_p(a), _p(w), _p(out), M, N, K, C.byref(e), _stream(a)), "grove_gemm_bf16")
     return out
 
 
-def conv_gemm(x, wp, out, *, V, T, G, kt, bias=None, resid=None, gate_alpha=None, act=None, out2=None, max_ctas=0, force_ctas=0):
+def conv_gemm(x, wp, out, *, V, T, G, kt, bias=None, resid=None, gate_alpha=None, act=None, out2=None, max_ctas=0, force_ctas=0,
+              out2_pre_act=0):
     """implicit-GEMM 'same' conv over token-major x[V,T,G,G,C]; wp[N, taps*C] tap-major"""
     _req(x, BF16, "x"); _req(wp, BF16, "wp")
     Cc = x.shape[-1]
     N = wp.shape[0]
     assert x.numel() == V * T * G * G * Cc and wp.shape[1] == 9 * kt * Cc
     assert out.shape == (V * T * G * G, N) and out.is_contiguous()
-    e = _epilogue(bias, resid, 0, gate_alpha, act, out, out2, max_ctas, force_ctas)
+    e = _epilogue(bias, resid, 0, gate_alpha, act, out, out2, max_ctas, force_ctas, out2_pre_act)
     check(lib().grove_conv_gemm_bf16(_p(x), _p(wp), _p(out), V, T, G, Cc, N, kt, C.byref(e), _stream(x)), "grove_conv_gemm_bf16")
     return out
 
@@ -157,10 +165,10 @@ def add_rowvec_bf16(x, vec, out):
     return out
 
 
-def t2i_attention(q, k, v, src_of, B, T, N, heads, dh):
+def t2i_attention(q, k, v, src_of, B, T, N, heads, dh, lse=None):
     out = torch.empty(B, T, heads * dh, device=q.device, dtype=F32)
     check(lib().grove_decoder_t2i_attention(_p(_req(q, F32, "q")), _p(_req(k, BF16, "k")), _p(_req(v, BF16, "v")), _p(src_of), _p(out),
-                                            B, T, N, heads, dh, _stream(q)), "grove_decoder_t2i_attention")
+                                            _p(lse), B, T, N, heads, dh, _stream(q)), "grove_decoder_t2i_attention")
     return out
 
 
@@ -243,6 +251,163 @@ def greedy_match(iou, sim, iou_thr, sim_thr):
                                    _p(pairs), _p(count), n, m, _stream(iou)), "grove_greedy_match")
     c = int(count.item())
     return [tuple(int(v) for v in p) for p in pairs[:c].tolist()]
+
+
+# ------------------------------------------------------------------ training step (backward pass)
+def transpose_to_bf16(x, out=None):
+    """[R,C] fp32|bf16 -> [C,R] bf16"""
+    assert x.is_cuda and x.is_contiguous() and x.dim() == 2 and x.dtype in (BF16, F32)
+    R, Cc = x.shape
+    if out is None:
+        out = torch.empty(Cc, R, device=x.device, dtype=BF16)
+    check(lib().grove_transpose_to_bf16(_p(x), 1 if x.dtype == F32 else 0, _p(_req(out, BF16, "out")), R, Cc, _stream(x)), "grove_transpose_to_bf16")
+    return out
+
+
+def reduce_partials(partials, out, accumulate=False, scale=1.0):
+    S = partials.shape[0]
+    n = partials[0].numel()
+    assert out.numel() == n and out.is_contiguous()
+    check(lib().grove_reduce_partials_f32(_p(_req(partials, F32, "partials")), S, n, _p(_req(out, F32, "out")), 1 if accumulate else 0, float(scale),
+                                          _stream(out)), "grove_reduce_partials_f32")
+    return out
+
+
+def wgrad(dy, x, out, accumulate=True):
+    """out[N,K] (fp32) (+)= dy[M,N]^T @ x[M,K] on the tcgen05 GEMM (K runs over the M rows; split-K when the output has few tiles).
+    dy, x: bf16 (or fp32, cast while transposing).  Requires K % 128 == 0, M % 8 == 0."""
+    M, N = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == M and out.shape == (N, K) and out.dtype == F32
+    dyt = transpose_to_bf16(dy)
+    xt = transpose_to_bf16(x)
+    tiles = ((N + 255) // 256) * max(K // 256, 1)
+    kblocks = (M + 63) // 64
+    splits = max(1, min(64, (74 + tiles - 1) // tiles, kblocks // 4))
+    part = torch.empty(splits, N, K, device=dy.device, dtype=F32)
+    gemm(dyt, xt, part if splits > 1 else part[0], splits=splits)
+    return reduce_partials(part, out, accumulate=accumulate)
+
+
+def conv_wgrad(dy, x, out, *, V, T, G, kt, accumulate=True):
+    """out[N, taps*C] fp32 (+)= weight gradient of conv_gemm; dy [tokens, N], x [tokens, C] token-major bf16/fp32"""
+    tokens, N = dy.shape
+    Cc = x.shape[1]
+    taps = 9 * kt
+    assert x.shape[0] == tokens == V * T * G * G and out.shape == (N, taps * Cc) and out.dtype == F32
+    dyt = transpose_to_bf16(dy)
+    assert x.is_contiguous() and x.dtype in (BF16, F32)
+    xt = torch.empty(3, Cc, tokens, device=x.device, dtype=BF16)
+    check(lib().grove_transpose_shift3_to_bf16(_p(x), 1 if x.dtype == F32 else 0, _p(xt), tokens, Cc, G, _stream(x)), "grove_transpose_shift3_to_bf16")
+    tiles = ((N + 255) // 256) * (taps * Cc // 256)
+    splits = max(1, min(16, 74 // max(tiles, 1), tokens // 64 // 8))
+    part = torch.empty(splits, N, taps * Cc, device=dy.device, dtype=F32)
+    check(lib().grove_conv_wgrad_bf16(_p(dyt), _p(xt), _p(part), V, T, G, Cc, N, kt, splits, _stream(dy)), "grove_conv_wgrad_bf16")
+    return reduce_partials(part, out, accumulate=accumulate)
+
+
+def layernorm_bwd(x, gamma, dy, *, eps, r=None, dx_in=None, dx_out=None, dx_bf16=None, dgamma=None, dbeta=None, keys_src_of=None, keys_N=0):
+    """dx_out = (dx_in or 0) + dLN(dy) for y = LN(x (+ r)); x fp32 [rows,D], or bf16 keys gathered through keys_src_of (then r = fp32 delta)."""
+    keys = x.dtype == BF16
+    rows, D = dy.shape
+    assert dy.is_contiguous() and dy.dtype in (BF16, F32)
+    check(lib().grove_layernorm_bwd(_p(x), _p(r), _p(keys_src_of), int(keys_N), 1 if keys else 0, _p(_req(gamma, F32, "gamma")), _p(dy),
+                                    1 if dy.dtype == F32 else 0, _p(dx_in), _p(dx_out), _p(dx_bf16), _p(dgamma), _p(dbeta), rows, D, float(eps),
+                                    _stream(dy)), "grove_layernorm_bwd")
+
+
+def adapter_gate_bwd(dy, relu_out, alpha, dyc, dbias, dalpha):
+    rows, D = dy.shape
+    check(lib().grove_adapter_gate_bwd(_p(_req(dy, F32, "dy")), _p(_req(relu_out, BF16, "relu_out")), _p(_req(alpha, F32, "alpha")),
+                                       _p(_req(dyc, BF16, "dyc")), _p(_req(dbias, F32, "dbias")), _p(_req(dalpha, F32, "dalpha")), rows, D,
+                                       _stream(dy)), "grove_adapter_gate_bwd")
+
+
+def colsum(x, out):
+    R, Cc = x.shape
+    assert x.is_contiguous() and x.dtype in (BF16, F32) and out.numel() == Cc
+    check(lib().grove_colsum(_p(x), 1 if x.dtype == F32 else 0, _p(_req(out, F32, "out")), R, Cc, _stream(x)), "grove_colsum")
+    return out
+
+
+def segment_sum(x, offsets, out, accumulate=False):
+    segs = offsets.numel() - 1
+    n = x[0].numel()
+    check(lib().grove_segment_sum_f32(_p(_req(x, F32, "x")), _p(offsets), _p(_req(out, F32, "out")), segs, n, 1 if accumulate else 0, _stream(x)),
+          "grove_segment_sum_f32")
+    return out
+
+
+def small_wgrad(dy, x, dw):
+    R, N = dy.shape
+    K = x.shape[1]
+    assert dw.shape == (N, K)
+    check(lib().grove_small_wgrad_f32(_p(_req(dy, F32, "dy")), _p(_req(x, F32, "x")), _p(_req(dw, F32, "dw")), R, N, K, _stream(dy)),
+          "grove_small_wgrad_f32")
+    return dw
+
+
+def act_bwd(dy, y, kind):
+    dx = torch.empty_like(dy)
+    check(lib().grove_act_bwd_f32(_p(_req(dy, F32, "dy")), _p(_req(y, F32, "y")), _p(dx), dy.numel(), ACT[kind], _stream(dy)), "grove_act_bwd_f32")
+    return dx
+
+
+def token_self_attention_bwd(q, k, v, dout, B, T, heads, dh):
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    check(lib().grove_token_self_attention_bwd(_p(_req(q, F32, "q")), _p(_req(k, F32, "k")), _p(_req(v, F32, "v")), _p(_req(dout, F32, "dout")),
+                                               _p(dq), _p(dk), _p(dv), B, T, heads, dh, _stream(q)), "grove_token_self_attention_bwd")
+    return dq, dk, dv
+
+
+def t2i_attention_bwd(q, k, v, src_of, att, datt, lse, B, T, N, heads, dh):
+    dq = torch.empty(B, T, heads * dh, device=q.device, dtype=F32)
+    dk = torch.empty(B * N, heads * dh, device=q.device, dtype=BF16)
+    dv = torch.empty(B * N, heads * dh, device=q.device, dtype=BF16)
+    check(lib().grove_decoder_t2i_attention_bwd(_p(_req(q, F32, "q")), _p(_req(k, BF16, "k")), _p(_req(v, BF16, "v")), _p(src_of),
+                                                _p(_req(att, F32, "att")), _p(_req(datt, F32, "datt")), _p(_req(lse, F32, "lse")), _p(dq), _p(dk),
+                                                _p(dv), B, T, N, heads, dh, _stream(q)), "grove_decoder_t2i_attention_bwd")
+    return dq, dk, dv
+
+
+def i2t_attention_bwd(qi, kt, vt, src_of, dout, B, T, N, heads, dh):
+    dqi = torch.empty(B * N, heads * dh, device=qi.device, dtype=BF16)
+    dkt = torch.zeros(B, T, heads * dh, device=qi.device, dtype=F32)
+    dvt = torch.zeros(B, T, heads * dh, device=qi.device, dtype=F32)
+    check(lib().grove_decoder_i2t_attention_bwd(_p(_req(qi, BF16, "qi")), _p(_req(kt, F32, "kt")), _p(_req(vt, F32, "vt")), _p(src_of),
+                                                _p(_req(dout, BF16, "dout")), _p(dqi), _p(dkt), _p(dvt), B, T, N, heads, dh, _stream(qi)),
+          "grove_decoder_i2t_attention_bwd")
+    return dqi, dkt, dvt
+
+
+def batch_sum_bf16(x, B):
+    n = x.numel() // B
+    out = torch.empty(n, device=x.device, dtype=F32)
+    check(lib().grove_batch_sum_bf16(_p(_req(x, BF16, "x")), _p(out), B, n, _stream(x)), "grove_batch_sum_bf16")
+    return out
+
+
+def attn_relpos_bwd(qkv, qkv_bias_bf16, rel_h, rel_w, att, datt, dqkv, *, F, G, heads, hd, ws=0):
+    """d(qkv) of the rel-pos attention (ws = 14 windowed on the unpartitioned tensors, ws = 0 global)"""
+    for t, n in ((qkv, "qkv"), (rel_h, "rel_pos_h"), (rel_w, "rel_pos_w"), (att, "att"), (datt, "datt"), (dqkv, "dqkv")):
+        _req(t, BF16, n)
+    S = ws if ws > 0 else G
+    assert rel_h.shape == (2 * S - 1, hd) and rel_w.shape == (2 * S - 1, hd)
+    nbytes = lib().grove_attn_relpos_bwd_workspace_bytes(F, G, heads, hd, ws)
+    wsb = torch.empty(nbytes // 4, device=qkv.device, dtype=F32)
+    check(lib().grove_attn_relpos_bwd(_p(qkv), _p(qkv_bias_bf16), _p(rel_h), _p(rel_w), _p(att), _p(datt), _p(dqkv), _p(wsb), F, G, heads, hd, ws,
+                                      _stream(qkv)), "grove_attn_relpos_bwd")
+    return dqkv
+
+
+def box_losses_bwd(boxes, logits, gt, sel, labels, cg, co):
+    B = boxes.shape[0]
+    db = torch.empty(B, 4, device=boxes.device, dtype=F32)
+    dl = torch.empty(B, device=boxes.device, dtype=F32)
+    check(lib().grove_box_losses_bwd(_p(_req(boxes, F32, "boxes")), _p(_req(logits, F32, "logits")), _p(_req(gt, F32, "gt")),
+                                     _p(_req(sel, torch.uint8, "sel")), _p(_req(labels, F32, "labels")), float(cg), float(co), _p(db), _p(dl), B,
+                                     _stream(boxes)), "grove_box_losses_bwd")
+    return db, dl
 
 
 def launch_count() -> int:

@@ -25,7 +25,7 @@ typedef cudaStream_t grove_stream_t;
 typedef void* grove_stream_t;
 #endif
 
-#define GROVE_B200_ABI_VERSION 1
+#define GROVE_B200_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------------- */
 int grove_abi_version(void);
@@ -45,6 +45,13 @@ typedef struct grove_gemm_epilogue {
   void* out2_bf16;         /* optional second, bf16 copy of the output, or NULL */
   int max_ctas;            /* 0 = one persistent CTA per SM; >0 caps the grid (tests) */
   int force_ctas;          /* 0 = auto; 1 = single-CTA tiles; 2 = CTA-pair (cta_group::2) tiles when N % 256 == 0 (tests) */
+  /* ---- training (ABI v2) ---- */
+  int out2_pre_act;        /* 0: out2 = copy of out | 1 (bf16 out): out2 = value BEFORE the activation (MLP lin1 pre-GELU, saved for
+                              backward) | 2 (fp32 out): out2 = value after the activation, before gate / residual (adapter ReLU output) */
+  const void* dact_pre;    /* bf16 [M,N] or NULL: multiply the result by act'(dact_pre) — backward of the fused activation (bf16 out) */
+  int dact;                /* with dact_pre: 1 = exact-GELU derivative, 2 = ReLU mask (pre > 0) */
+  int splits;              /* >1: split-K; `out` is fp32 [splits, M, N] raw partial sums (no other epilogue field allowed);
+                              finish with grove_reduce_partials_f32 */
 } grove_gemm_epilogue;
 
 /* out[M,N] = resid + gate * act(A[M,K] . W[N,K]^T + bias).  A, W bf16 row-major (nn.Linear layout).
@@ -106,9 +113,10 @@ int grove_dense_pe(const float* gauss, float* pe, int G, int F2, grove_stream_t 
 int grove_add_rowvec_bf16(const void* x, const float* vec, void* y, long long rows, int C, grove_stream_t stream);
 /* Token-to-image attention (transformer.py:231-240 inside cross_attn_token_to_image / final_attn_token_to_image):
  * q fp32 [B,T,H*dh] (already projected), k,v bf16 [*,N,H*dh] (projected keys; instance b reads row block src_of[b],
- * or b when src_of is NULL), out fp32 [B,T,H*dh] (before out_proj).  Built for T=6, dh=16. */
-int grove_decoder_t2i_attention(const float* q, const void* k, const void* v, const int* src_of, float* out, int B, int T, int N,
-                                int heads, int dh, grove_stream_t stream);
+ * or b when src_of is NULL), out fp32 [B,T,H*dh] (before out_proj).  Built for T=6, dh=16.
+ * lse_out (optional, fp32 [B,T,H]): log2-domain log-sum-exp of the scaled scores, saved for grove_decoder_t2i_attention_bwd. */
+int grove_decoder_t2i_attention(const float* q, const void* k, const void* v, const int* src_of, float* out, float* lse_out, int B, int T,
+                                int N, int heads, int dh, grove_stream_t stream);
 /* Image-to-token attention (cross_attn_image_to_token, transformer.py:173-179): qi bf16 [*,N,H*dh] = q_proj(keys+pe),
  * kt, vt fp32 [B,T,H*dh]; out bf16 [B,N,H*dh] (before out_proj). */
 int grove_decoder_i2t_attention(const void* qi, const float* kt, const float* vt, const int* src_of, void* out, int B, int T, int N,
@@ -147,6 +155,65 @@ int grove_box_iou(const void* a, int lda, const void* b, int ldb, const uint8_t*
 /* Greedy one-to-one matching (eval_iground.py:85-96): iou, sim fp64 [n,m] (clobbered); pairs int32 [min(n,m),2]; count int32[1]. */
 int grove_greedy_match(double* iou, double* sim, double iou_thr, double sim_thr, int* pairs, int* count, int n, int m,
                        grove_stream_t stream);
+
+
+/* ==== training step of the grounding branch (BASELINE config 4; SURVEY.md §8a row "4-bwd") ========================
+ * The reference trains this branch through autograd (train.py:761-782: model(**batch); model.backward(loss)); trainable
+ * there: the Conv3d adapters, the whole mask decoder with its heads, text_hidden_fcs (train.py:279-296) — the ViT blocks
+ * are frozen but sit between the adapters, so activations' gradients flow through every block after the first adapter.
+ * The contractions of the backward pass reuse grove_gemm_bf16 / grove_conv_gemm_bf16 with transposed / flipped weights
+ * (input gradients) and transposed activations (weight gradients, K = tokens, optional split-K). */
+
+/* dWp[N, taps*C] fp32 (tap-major, [splits, ...] partial planes when splits > 1) = sum_tokens dY[token, n] * X[token + shift(tap), c]:
+ * weight gradient of grove_conv_gemm_bf16 (Conv3d adapter, image_encoder.py:40-59).  dYt = dY transposed [N, tokens] bf16,
+ * Xt3 = X channel-major in three w-shifted planes [3, C, V,T,G,G] bf16 (grove_transpose_shift3_to_bf16; a TMA box cannot start at an
+ * odd element of the innermost dimension); the B operand is a 5-D TMA box whose origin carries the tap's (h,t) shift. */
+int grove_conv_wgrad_bf16(const void* dYt, const void* Xt3, float* dWp, int V, int T, int G, int C, int N, int kt, int splits,
+                          grove_stream_t stream);
+/* out[C,R] bf16 = transpose(in[R,C]) (in fp32 or bf16): operands of the weight-gradient GEMMs */
+int grove_transpose_to_bf16(const void* in, int in_is_f32, void* out, int R, int C, grove_stream_t stream);
+/* out[3, C, R] bf16: plane d = transpose(in[R,C]) shifted by d-1 along the grid's w axis (R = frames*G*G, zero outside [0,G)) */
+int grove_transpose_shift3_to_bf16(const void* in, int in_is_f32, void* out, int R, int C, int G, grove_stream_t stream);
+/* out[i] = (accumulate ? out[i] : 0) + scale * sum_s partials[s, i]: finishes a split-K GEMM */
+int grove_reduce_partials_f32(const float* partials, int splits, long long n, float* out, int accumulate, float scale, grove_stream_t stream);
+/* LayerNorm backward over rows of u = x (+ r) [fp32], or u = keys[src_of[row/N]*N + row%N] (bf16) + r (fp32) when x_is_keys_bf16
+ * (norm4 of the two-way block, transformer.py:180).  dx_out = (dx_in ? dx_in : 0) + dLN(dy); optional bf16 copy; optional
+ * d gamma / d beta (+=, atomics).  D % 128 == 0, D <= 1280. */
+int grove_layernorm_bwd(const void* x, const float* r, const int* src_of, int N, int x_is_keys_bf16, const float* gamma, const void* dy,
+                        int dy_is_f32, const float* dx_in, float* dx_out, void* dx_bf16, float* dgamma, float* dbeta, long long rows, int D,
+                        float eps, grove_stream_t stream);
+/* Adapter gate backward (image_encoder.py:54): dyc = dy * tanh(alpha) * [relu_out > 0] (bf16); dbias += colsum(dyc);
+ * dalpha += (1 - tanh^2(alpha)) * sum(dy * relu_out).  relu_out = relu(conv + b) saved by the forward GEMM (out2_pre_act = 2). */
+int grove_adapter_gate_bwd(const float* dy, const void* relu_out, const float* alpha, void* dyc, float* dbias, float* dalpha, long long rows,
+                           int D, grove_stream_t stream);
+/* out[c] += sum_r x[r,c] (bias gradients) ; out[f,:] = (+=) sum_{b in [off[f],off[f+1])} x[b,:] (phrases sharing a frame's keys) */
+int grove_colsum(const void* x, int x_is_f32, float* out, long long R, int C, grove_stream_t stream);
+int grove_segment_sum_f32(const float* x, const int* offsets, float* out, int segments, long long n, int accumulate, grove_stream_t stream);
+/* token-side fp32: dW[N,K] += dY[R,N]^T . X[R,K] ; dx = dy * act'(y) (kind 2 ReLU, 3 sigmoid, from the activation's OUTPUT y) */
+int grove_small_wgrad_f32(const float* dy, const float* x, float* dw, int R, int N, int K, grove_stream_t stream);
+int grove_act_bwd_f32(const float* dy, const float* y, float* dx, long long n, int kind, grove_stream_t stream);
+int grove_token_self_attention_bwd(const float* q, const float* k, const float* v, const float* dout, float* dq, float* dk, float* dv, int B,
+                                   int T, int heads, int dh, grove_stream_t stream);
+/* Cross-attention backward of the two-way block (transformer.py:164-180, 99-104); layouts as the forward entry points.
+ * t2i: dk, dv bf16 [B,N,H*dh] per instance.  i2t: dkt, dvt fp32 [B,T,H*dh] must be zero-initialised (accumulated). */
+int grove_decoder_t2i_attention_bwd(const float* q, const void* k, const void* v, const int* src_of, const float* att, const float* datt,
+                                    const float* lse, float* dq, void* dk, void* dv, int B, int T, int N, int heads, int dh,
+                                    grove_stream_t stream);
+int grove_decoder_i2t_attention_bwd(const void* qi, const float* kt, const float* vt, const int* src_of, const void* dout, void* dqi, float* dkt,
+                                    float* dvt, int B, int T, int N, int heads, int dh, grove_stream_t stream);
+/* out[n] fp32 = sum_b x[b, n] (bf16) */
+int grove_batch_sum_bf16(const void* x, float* out, int B, long long n, grove_stream_t stream);
+/* d(qkv) of Attention.forward + add_decomposed_rel_pos (image_encoder.py:301-326, 420-458) for frozen blocks: ws = 14 windowed
+ * (on the unpartitioned tensors, qkv_bias_bf16 = the k/v of window_partition's zero-padded tokens) or ws = 0 global.
+ * att = the forward output (before proj), datt its gradient, both bf16 [F,G,G,heads*hd]; dqkv bf16 [F,G,G,3,heads,hd].
+ * rel_pos_h/w: bf16 [2S-1, hd] with S = ws or G.  workspace: grove_attn_relpos_bwd_workspace_bytes() bytes, 16-byte aligned. */
+long long grove_attn_relpos_bwd_workspace_bytes(int F, int G, int heads, int hd, int ws);
+int grove_attn_relpos_bwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, const void* att,
+                          const void* datt, void* dqkv, void* workspace, int F, int G, int heads, int hd, int ws, grove_stream_t stream);
+/* d boxes [B,4] (cxcywh) and d logits [B] of the loss of _compute_loss_components_video (GROVE.py:339-381):
+ * cg = upstream * giou_weight / (n_gt + 1e-8) (GIoU and L1 share it, GROVE.py:375), co = upstream * objectness_weight / (n_pred + 1e-8). */
+int grove_box_losses_bwd(const float* boxes, const float* logits, const float* gt, const uint8_t* sel, const float* labels, float cg, float co,
+                         float* dboxes, float* dlogits, int B, grove_stream_t stream);
 
 #ifdef __cplusplus
 }
