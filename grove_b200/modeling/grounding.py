@@ -154,6 +154,133 @@ class GroundingBranch(nn.Module):
         obj = self.temp_objectness_loss_weight * sums[2] / (num_max + 1e-8)
         return {"loss": ce_loss + giou + l1 + obj, "ce_loss": ce_loss, "giou_loss": giou, "l1_loss": l1, "temp_objectness_loss": obj}
 
+    # ------------------------------------------------------------------ training step (BASELINE config 4)
+    def _loss_inputs(self, reps, T, gt_bboxes_list, gt_temp_objectness_list, dev):
+        """flatten the nested ground truth of _compute_loss_components_video (GROVE.py:350-371) into per-instance rows"""
+        gt_rows, sel_rows, lab_rows = [], [], []
+        num_bboxes = num_max = 0
+        i = 0
+        for v in range(len(gt_bboxes_list)):
+            for f in range(T):
+                n = reps[i]; i += 1
+                gb = torch.as_tensor(gt_bboxes_list[v][f]).detach().cpu().float().reshape(-1, 4)
+                go = torch.as_tensor(gt_temp_objectness_list[v][f]).detach().cpu()
+                assert go.numel() == n, f"objectness labels ({go.numel()}) do not match the number of predictions ({n})"
+                assert gb.shape[0] == go.sum(), f"Number of ground truth bboxes and objectness labels do not match: {gb.shape[0]} vs {go.sum()}"
+                sel = go.bool()
+                g_full = torch.zeros(n, 4)
+                g_full[sel] = gb
+                gt_rows.append(g_full); sel_rows.append(sel.to(torch.uint8)); lab_rows.append(go.float())
+                num_bboxes += gb.shape[0]
+                num_max += n
+        return torch.cat(gt_rows).to(dev), torch.cat(sel_rows).to(dev), torch.cat(lab_rows).to(dev), num_bboxes, num_max
+
+    @torch.no_grad()
+    def grounding_loss_and_grads(self, images, last_hidden_state, det_token_mask, gt_bboxes_list, gt_temp_objectness_list, ce_loss=None,
+                                 upstream: float = 1.0, apply: bool = True, _cotangent=None):
+        """One training step of the grounding branch — model_forward's grounding half + _compute_loss_components_video + backward
+        (GROVE.py:162-198, 339-381; train.py:761-770) — on the CUDA library, without autograd.
+
+        Returns (losses, d_last_hidden_state, grads): `losses` has the reference's keys; `d_last_hidden_state` ([V,L,hidden], fp32) is
+        the cotangent handed back to the language model; `grads` (GradStore) holds fp32 gradients of every trainable parameter of the
+        adapters, the mask decoder and text_hidden_fcs.  With apply=True they are also added to `.grad` (scaled by `upstream`)."""
+        from .decoder_train import GradStore, _wants
+        from .encoder_train import encode_backward, encode_train
+        if not self.config.use_temp_objectness:
+            raise NotImplementedError("grove_b200 builds the use_temp_objectness=True loss (the configuration every GROVE script uses)")
+        ge = self.grounding_encoder
+        dev = images.device
+        T = self.config.num_frames
+        grads = GradStore()
+        # ---- forward
+        emb_tok, enc_tape = encode_train(ge.image_encoder, images)
+        V, L, Hd = last_hidden_state.shape
+        idx = det_token_mask.reshape(-1).nonzero().flatten().to(torch.int32)
+        counts = det_token_mask.int().sum(-1).tolist()
+        n = idx.numel()
+        if n == 0:
+            raise ValueError("the training step needs at least one [DET] token")
+        fcs = self.text_hidden_fcs[0]
+        out_dim = fcs[2].out_features
+        rows = ((n + 127) // 128) * 128
+        a = torch.zeros(rows, Hd, device=dev, dtype=torch.bfloat16)
+        ops.gather_rows_bf16(last_hidden_state.reshape(V * L, Hd).contiguous(), idx, a)
+        w0 = self._pack.get("fc0.w", [fcs[0].weight], bf16); b0 = self._pack.get("fc0.b", [fcs[0].bias], f32)
+        w2 = self._pack.get("fc2.w", [fcs[2].weight], bf16); b2 = self._pack.get("fc2.b", [fcs[2].bias], f32)
+        h = torch.empty(rows, Hd, device=dev, dtype=torch.bfloat16)
+        ops.gemm(a, w0, h, bias=b0, act="relu")
+        p = torch.empty(rows, out_dim, device=dev, dtype=torch.float32)
+        ops.gemm(h, w2, p, bias=b2)
+        proj = p[:n].to(last_hidden_state.dtype).float()           # the module's output dtype (bf16 in production), as the reference
+        # instance b = (video v, frame t, phrase j) reads projected row offset_v + j  (repeat_interleave over frames, GROVE.py:253-257)
+        row_of, reps, s0 = [], [], 0
+        for c in counts:
+            for _ in range(T):
+                row_of += list(range(s0, s0 + c))
+                reps.append(c)
+            s0 += c
+        Fr = emb_tok.shape[0]
+        if len(reps) != Fr:
+            raise ValueError(f"{V} videos x {T} frames do not match the {Fr} encoded frames")
+        row_of_t = torch.tensor(row_of, dtype=torch.long, device=dev)
+        text = proj[row_of_t].contiguous()                          # [B, out_dim]
+        B = text.shape[0]
+        no_mask = ge.prompt_encoder.no_mask_embed.weight.reshape(-1).to(torch.float32).contiguous()
+        dense_pe = ge.prompt_encoder.get_dense_pe()
+        boxes, logits, dec_tape = ge.mask_decoder.predict_masks_train(emb_tok, dense_pe, text, no_mask, reps)
+        # ---- losses (GROVE.py:339-381) and their derivative
+        gt, sel, lab, num_bboxes, num_max = self._loss_inputs(reps, T, gt_bboxes_list, gt_temp_objectness_list, dev)
+        sums = ops.box_losses(boxes, logits, gt, sel, lab)
+        gw, ow = self.giou_loss_weight, self.temp_objectness_loss_weight
+        giou = gw * sums[0] / (num_bboxes + 1e-8)
+        l1 = gw * sums[1] / (num_bboxes + 1e-8)                     # the L1 term reuses the GIoU weight (GROVE.py:375)
+        obj = ow * sums[2] / (num_max + 1e-8)
+        ce = (ce_loss if ce_loss is not None else torch.zeros((), device=dev)) * self.ce_loss_weight
+        losses = {"loss": ce + giou + l1 + obj, "ce_loss": ce, "giou_loss": giou, "l1_loss": l1, "temp_objectness_loss": obj}
+        dboxes, dlogits = ops.box_losses_bwd(boxes, logits, gt, sel, lab, gw / (num_bboxes + 1e-8), ow / (num_max + 1e-8))
+        if _cotangent is not None:      # tests: a prescribed cotangent of (boxes, logits) instead of the loss' own — a pure VJP check
+            dboxes, dlogits = _cotangent[0].float().contiguous(), _cotangent[1].float().contiguous()
+        losses["boxes"], losses["logits"] = boxes, logits
+        # ---- backward: decoder -> encoder (adapters) and text projection
+        d_emb, d_text = ge.mask_decoder.backward(dec_tape, dboxes, dlogits, grads)
+        del dec_tape
+        encode_backward(ge.image_encoder, enc_tape, d_emb, grads)
+        del enc_tape
+        onehot = torch.zeros(B, n, device=dev, dtype=torch.float32)
+        onehot[torch.arange(B, device=dev), row_of_t] = 1.0
+        d_p = torch.zeros(rows, out_dim, device=dev, dtype=torch.float32)
+        ops.small_wgrad(onehot, d_text, d_p[:n])                    # d proj[row] = sum of the cotangents of the instances that read it
+        d_p16 = d_p.to(torch.bfloat16)
+        if _wants(fcs[2].weight):
+            ops.wgrad(d_p16, h, grads.buf(fcs[2].weight))
+        if _wants(fcs[2].bias):
+            ops.colsum(d_p, grads.buf(fcs[2].bias))
+        w2t = self._pack.get("fc2.wT", [fcs[2].weight], lambda w: bf16(w.t()))
+        d_h = torch.empty(rows, Hd, device=dev, dtype=torch.bfloat16)
+        ops.gemm(d_p16, w2t, d_h, dact_pre=h, dact="relu")          # ReLU mask from its (saved) output
+        if _wants(fcs[0].weight):
+            ops.wgrad(d_h, a, grads.buf(fcs[0].weight))
+        if _wants(fcs[0].bias):
+            ops.colsum(d_h, grads.buf(fcs[0].bias))
+        w0t = self._pack.get("fc0.wT", [fcs[0].weight], lambda w: bf16(w.t()))
+        d_a = torch.empty(rows, Hd, device=dev, dtype=torch.float32)
+        ops.gemm(d_h, w0t, d_a)
+        d_hidden = torch.zeros(V * L, Hd, device=dev, dtype=torch.float32)
+        d_hidden[idx.long()] = d_a[:n]
+        if upstream != 1.0:
+            d_hidden *= upstream
+        if apply:
+            grads.apply(upstream)
+        return losses, d_hidden.view(V, L, Hd), grads
+
+    def grounding_loss(self, images, last_hidden_state, det_token_mask, gt_bboxes_list, gt_temp_objectness_list):
+        """Autograd bridge: a scalar (giou + l1 + objectness, weighted as GROVE.py:372-378) whose .backward() delivers the CUDA
+        library's gradients to the trainable grounding parameters and to `last_hidden_state` (and on into the language model) —
+        the drop-in for `model.backward(loss)` (train.py:770)."""
+        params = [p for p in list(self.grounding_encoder.image_encoder.adapters.parameters()) + list(self.grounding_encoder.mask_decoder.parameters())
+                  + list(self.text_hidden_fcs.parameters()) if p.requires_grad]
+        return _GroundingLossFn.apply(self, images, last_hidden_state, det_token_mask, gt_bboxes_list, gt_temp_objectness_list, *params)
+
     # the grounding half of model_forward / evaluate (GROVE.py:162-186, 432-444)
     @torch.no_grad()
     def ground(self, images, last_hidden_state, det_token_mask, orig_sizes=None, infer=False):
@@ -161,3 +288,22 @@ class GroundingBranch(nn.Module):
         _, pred = self._process_hidden_states([last_hidden_state], det_token_mask, None, infer=infer)
         dense_pe = self.grounding_encoder.prompt_encoder.get_dense_pe()
         return emb, self._generate_and_postprocess_masks(pred, emb, orig_sizes, dense_pe, infer=infer)
+
+
+class _GroundingLossFn(torch.autograd.Function):
+    """forward = GroundingBranch.grounding_loss_and_grads (loss and all gradients in one pass over the CUDA library);
+    backward only scales the stored gradients by the incoming cotangent."""
+
+    @staticmethod
+    def forward(ctx, branch, images, hidden, mask, gt_boxes, gt_obj, *params):
+        losses, d_hidden, grads = branch.grounding_loss_and_grads(images, hidden.detach(), mask, gt_boxes, gt_obj, apply=False)
+        ctx.d_hidden = d_hidden.to(hidden.dtype)
+        ctx.pgrads = [grads.grad_of(p) for p in params]
+        ctx.pdtypes = [p.dtype for p in params]
+        branch.last_losses = losses
+        return (losses["giou_loss"] + losses["l1_loss"] + losses["temp_objectness_loss"]).detach().clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        gp = [None if t is None else (t * g).to(dt) for t, dt in zip(ctx.pgrads, ctx.pdtypes)]
+        return (None, None, ctx.d_hidden * g, None, None, None, *gp)

@@ -135,6 +135,45 @@ class MaskDecoder(nn.Module):
             logits[s:e] = l
         return boxes.to(out_dtype), logits.to(out_dtype)
 
+    # ------------------------------------------------------------------ training step (forward with tape, backward)
+    def predict_masks_train(self, emb_tokens: torch.Tensor, image_pe: torch.Tensor, text: torch.Tensor, no_mask: torch.Tensor, reps: List[int]):
+        """predict_masks for the training step: emb_tokens bf16 [F, N, C] (token-major encoder output), text fp32 [B, C] (one prompt
+        token per instance), no_mask fp32 [C].  Returns fp32 boxes [B,4], logits [B] and the tape for `backward`."""
+        from .decoder_train import decode_train
+        Fr, N, C = emb_tokens.shape
+        B = text.shape[0]
+        if len(reps) != Fr or sum(reps) != B or B == 0:
+            raise ValueError("reps must have one entry per frame summing to the (non-zero) number of prompts")
+        dev = emb_tokens.device
+        G = int(round(N ** 0.5))
+        pe = self._tokens_of(image_pe, torch.float32).reshape(N, C)
+        if not pe.is_contiguous():
+            pe = pe.contiguous()
+        keys0 = torch.empty(Fr * N, C, device=dev, dtype=torch.bfloat16)
+        ops.add_rowvec_bf16(emb_tokens.reshape(Fr * N, C), no_mask, keys0)
+        out_tok = torch.cat([self.iou_token.weight, self.mask_tokens.weight], 0).to(torch.float32)
+        frame_of = torch.repeat_interleave(torch.arange(Fr), torch.tensor(reps)).to(torch.int32).to(dev)
+        shared = self._layer0_shared(keys0, pe, N, C)
+        tokens = torch.cat([out_tok.unsqueeze(0).expand(B, -1, -1), text.to(torch.float32).unsqueeze(1)], 1).contiguous()
+        boxes, logits, tape = decode_train(self, tokens, keys0, shared, pe, frame_of, N, C)
+        tape["Fr"], tape["G"] = Fr, G
+        return boxes, logits, tape
+
+    def backward(self, tape, dboxes: torch.Tensor, dlogits, grads):
+        """Reverse schedule of predict_masks_train.  Returns (d emb_tokens fp32 [F*N, C], d text fp32 [B, C]) and accumulates the
+        decoder's parameter gradients (transformer, heads, iou/mask tokens) into `grads`."""
+        from .decoder_train import decode_backward
+        d_keys0, d_tokens = decode_backward(self, tape, dboxes, dlogits, grads, tape["Fr"])
+        B, T, C = d_tokens.shape
+        dsum = torch.zeros(T * C, device=d_tokens.device, dtype=torch.float32)
+        ops.colsum(d_tokens.reshape(B, T * C).contiguous(), dsum)
+        dsum = dsum.view(T, C)
+        if self.iou_token.weight.requires_grad:
+            grads.buf(self.iou_token.weight).add_(dsum[0:1])
+        if self.mask_tokens.weight.requires_grad:
+            grads.buf(self.mask_tokens.weight).add_(dsum[1:1 + self.num_mask_tokens])
+        return d_keys0, d_tokens[:, 1 + self.num_mask_tokens, :].contiguous()
+
     # ------------------------------------------------------------------ the two-way transformer
     def _pe_w(self, key, lin, pe):
         """(pe . W^T) [N, internal] fp32 — the positional part of (keys + pe) W.  Cached per (weight, pe tensor); the cache

@@ -273,6 +273,12 @@ def reduce_partials(partials, out, accumulate=False, scale=1.0):
     return out
 
 
+def _even_splits(splits, kblocks):
+    """the number of non-empty split-K planes the kernel writes for this request (gemm_tcgen05.cu: dispatch_gemm)"""
+    per = (kblocks + splits - 1) // splits
+    return (kblocks + per - 1) // per
+
+
 def wgrad(dy, x, out, accumulate=True):
     """out[N,K] (fp32) (+)= dy[M,N]^T @ x[M,K] on the tcgen05 GEMM (K runs over the M rows; split-K when the output has few tiles).
     dy, x: bf16 (or fp32, cast while transposing).  Requires K % 128 == 0, M % 8 == 0."""
@@ -283,7 +289,7 @@ def wgrad(dy, x, out, accumulate=True):
     xt = transpose_to_bf16(x)
     tiles = ((N + 255) // 256) * max(K // 256, 1)
     kblocks = (M + 63) // 64
-    splits = max(1, min(64, (74 + tiles - 1) // tiles, kblocks // 4))
+    splits = _even_splits(max(1, min(64, (74 + tiles - 1) // tiles, kblocks // 4)), kblocks)
     part = torch.empty(splits, N, K, device=dy.device, dtype=F32)
     gemm(dyt, xt, part if splits > 1 else part[0], splits=splits)
     return reduce_partials(part, out, accumulate=accumulate)
@@ -300,7 +306,7 @@ def conv_wgrad(dy, x, out, *, V, T, G, kt, accumulate=True):
     xt = torch.empty(3, Cc, tokens, device=x.device, dtype=BF16)
     check(lib().grove_transpose_shift3_to_bf16(_p(x), 1 if x.dtype == F32 else 0, _p(xt), tokens, Cc, G, _stream(x)), "grove_transpose_shift3_to_bf16")
     tiles = ((N + 255) // 256) * (taps * Cc // 256)
-    splits = max(1, min(16, 74 // max(tiles, 1), tokens // 64 // 8))
+    splits = _even_splits(max(1, min(16, 74 // max(tiles, 1), tokens // 64 // 8)), tokens // 64)
     part = torch.empty(splits, N, taps * Cc, device=dy.device, dtype=F32)
     check(lib().grove_conv_wgrad_bf16(_p(dyt), _p(xt), _p(part), V, T, G, Cc, N, kt, splits, _stream(dy)), "grove_conv_wgrad_bf16")
     return reduce_partials(part, out, accumulate=accumulate)
