@@ -4,7 +4,10 @@ The path shards into independent units — one 8-frame window of one video (the 
 window and nothing else, image_encoder.py:52-56) — so there is NO data-path collective.  The only exchange is the optional
 all-gather of packed per-frame records [frames, phrases, 5] = (cx, cy, w, h, objectness logit) when the windows of ONE video
 are split across ranks (BASELINE config 5); it replaces the reference's pickled `all_gather_object` of per-clip dicts
-(infer_iground.py:290-293).  Everything here is device-agnostic torch (NCCL on the B200 box, gloo in the CPU tests).
+(infer_iground.py:290-293).  Training (BASELINE config 4) is data parallel over clips: every rank runs the whole training step on its own clip and the
+gradients of the trainable grounding parameters are averaged with `allreduce_gradients` — flat fp32 buckets, one NCCL
+all-reduce each (the reference delegates this to DeepSpeed ZeRO-2's bucketed reduce, train.py:466-486, reduce_bucket_size 5e8).
+Everything here is device-agnostic torch (NCCL on the B200 box, gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -82,3 +85,44 @@ def pack_records(boxes_nested, logits_nested) -> torch.Tensor:
     for ONE video -> packed [T, P, 5]"""
     fb, fl = boxes_nested[0], logits_nested[0]
     return torch.stack([torch.cat([b.float(), l.float()[:, None]], 1) for b, l in zip(fb, fl)])
+
+
+def allreduce_gradients(grads: Sequence[torch.Tensor], *, group: Optional[dist.ProcessGroup] = None, bucket_elems: int = 1 << 26,
+                        average: bool = True) -> None:
+    """In-place mean (or sum) over the ranks of `group` of a list of fp32 gradient tensors.  The tensors are packed into flat
+    buckets of at most `bucket_elems` elements (256 MB) so that a ViT-H adapter (27 * 1280^2 = 44 M elements) is one collective and
+    the ~250 small decoder tensors share one; every rank must pass the tensors in the same order."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1 or not grads:
+        return
+    world = dist.get_world_size(group)
+    bucket: List[torch.Tensor] = []
+    size = 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket]) if len(bucket) > 1 else bucket[0].reshape(-1)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= world
+        if len(bucket) > 1 or flat.data_ptr() != bucket[0].data_ptr():
+            off = 0
+            for g in bucket:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        bucket, size = [], 0
+
+    for g in grads:
+        if g.dtype != torch.float32 or not g.is_contiguous():
+            raise ValueError("allreduce_gradients expects contiguous fp32 gradient tensors (GradStore accumulators)")
+        if size + g.numel() > bucket_elems and bucket:
+            flush()
+        bucket.append(g)
+        size += g.numel()
+    flush()
+
+
+def allreduce_gradstore(store, parameters: Sequence[torch.Tensor], **kw) -> None:
+    """all-reduce the accumulators of a modeling.decoder_train.GradStore, visiting `parameters` in their (rank-independent) order"""
+    allreduce_gradients([store.g[p] for p in parameters if p in store.g], **kw)

@@ -180,6 +180,74 @@ def glue_case(name, seed):
     print(name, {k: float(v) for k, v in loss.items()})
 
 
+def train_case(name, seed):
+    """BASELINE config 4 in miniature, through the REFERENCE's own modules and GROVE methods in float64 with autograd: the pin for the
+    oracle's gradients (the GPU training tests compare grove_b200's backward with autograd over the oracle)."""
+    _stub_mm()
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import model.GROVE as RG
+    from model.SAM.modeling import MaskDecoder, PromptEncoder, TwoWayTransformer
+    from model.SAM.modeling.image_encoder import ImageEncoderViT
+    C = RG.GROVEForCausalLM
+    D, depth, heads, gidx, img, dim, mlp, T, hidden, L, P = 64, 3, 2, (1, 2), 512, 256, 128, 8, 96, 600, 2
+    G = img // 16
+    enc = ImageEncoderViT(depth=depth, embed_dim=D, img_size=img, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_heads=heads,
+                          patch_size=16, qkv_bias=True, use_rel_pos=True, global_attn_indexes=gidx, window_size=14, out_chans=dim)
+    pe = PromptEncoder(embed_dim=dim, image_embedding_size=(G, G), input_image_size=(img, img), mask_in_chans=16)
+    md = MaskDecoder(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=dim, mlp_dim=mlp, num_heads=8),
+                     transformer_dim=dim, iou_head_depth=3, iou_head_hidden_dim=dim, decoding_type="query", use_temp_objectness=True)
+    fcs = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(hidden, hidden), torch.nn.ReLU(inplace=True),
+                                                   torch.nn.Linear(hidden, dim), torch.nn.Dropout(0.0))])
+    esd = synth.synth_state_dict(synth.encoder_param_shapes(D, depth, heads, gidx, G), seed)
+    dsd = synth.synth_state_dict(synth.decoder_param_shapes(dim, mlp), seed)
+    fsd = synth.synth_state_dict(synth.text_fcs_shapes(hidden, dim), seed)
+    assert not _load(enc, esd, "image_encoder.")
+    _load(pe, {k: v for k, v in dsd.items() if k.startswith("prompt_encoder.")}, "prompt_encoder.")
+    _load(md, {k: v for k, v in dsd.items() if k.startswith("mask_decoder.")}, "mask_decoder.")
+    _load(fcs, fsd, "text_hidden_fcs.")
+    for m in (enc, pe, md, fcs):
+        m.double().train()
+    self = NS(model=NS(text_hidden_fcs=fcs, grounding_encoder=NS(image_encoder=enc, prompt_encoder=pe, mask_decoder=md)),
+              config=NS(num_frames=T, use_temp_objectness=True, temp_objectness_threshold=0.5),
+              ce_loss_weight=1.0, giou_loss_weight=2.0, temp_objectness_loss_weight=2.0, det_token_idx=32005)
+    ids = torch.full((1, L - 575), 7, dtype=torch.long)
+    for p_ in synth.det_positions(L, P, seed):
+        ids[0, p_ - 575 + 1] = 32005
+    images = synth.synth_tensor(name + ".images", (1, 3, T, img, img), seed).double()
+    hid = synth.synth_tensor(name + ".hidden", (1, L, hidden), seed).double().requires_grad_(True)
+    rng = np.random.Generator(np.random.PCG64([seed, 77]))
+    gt_b, gt_o = [[]], [[]]
+    for f in range(T):
+        o = (rng.uniform(size=P) < 0.5).astype(np.float64)
+        if f == 0:
+            o[0] = 1.0
+        n = int(o.sum())
+        gt_b[0].append(torch.from_numpy(np.concatenate([rng.uniform(0.3, 0.7, (n, 2)), rng.uniform(0.1, 0.4, (n, 2))], 1)))
+        gt_o[0].append(torch.from_numpy(o))
+    emb = C.get_grounding_encoder_embs(self, images)                       # GROVE.py:134-136 (no no_grad)
+    mask = C._create_det_token_mask(self, ids)
+    _, pred_list = C._process_hidden_states(self, [hid], mask, None)
+    dense_pe = pe.get_dense_pe()
+    tb, tl = C._generate_and_postprocess_masks(self, pred_list, emb, [(1280, 720)], dense_pe, infer=False)
+    loss = C._compute_loss_components_video(self, tb, tl, gt_b, gt_o, NS(loss=torch.tensor(0.0, dtype=torch.float64)))
+    loss["loss"].backward()
+    out = {"losses": np.array([float(loss[k]) for k in ("loss", "ce_loss", "giou_loss", "l1_loss", "temp_objectness_loss")]),
+           "gt_boxes": torch.cat(gt_b[0]).numpy(), "gt_obj": torch.cat(gt_o[0]).numpy(), "meta": np.array([D, depth, heads, img, dim, mlp, hidden, L, P, seed])}
+    named = [("image_encoder." + k, v) for k, v in enc.named_parameters()] + [("mask_decoder." + k, v) for k, v in md.named_parameters()] + \
+            [("text_hidden_fcs." + k, v) for k, v in fcs.named_parameters()] + [("hidden", hid)]
+    keys = []
+    for k, v in named:
+        if v.grad is None:
+            continue
+        g = v.grad.detach().reshape(-1)
+        step = max(g.numel() // 64, 1)
+        out["gn:" + k] = np.array(float(g.norm()))
+        out["gs:" + k] = g[::step][:64].numpy()
+        keys.append(k)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: float(v) for k, v in loss.items()}, len(keys), "gradient tensors")
+
+
 def box_eval_case(name, seed):
     import importlib.util
     spec = importlib.util.spec_from_file_location("ref_eval_vidstg", os.path.join(REF, "eval_vidstg.py"))
@@ -244,6 +312,7 @@ def main():
     decoder_case("dec_ragged", dim=256, mlp=2048, G=32, frames=4, reps=[2, 0, 3, 1], seed=4)
     glue_case("glue", seed=5)
     box_eval_case("box_eval", seed=6)
+    train_case("train_tiny512", seed=7)
 
 
 if __name__ == "__main__":

@@ -132,3 +132,52 @@ def test_box_eval_utilities_bit_exact():
         assert sum(idx, []) == g[f"seg_idx_{n}"].tolist()
         assert sum(masks, []) == g[f"seg_mask_{n}"].tolist()
         assert [len(r) for r in idx] == g[f"seg_len_{n}"].tolist()
+
+
+def test_training_step_gradients_vs_reference_autograd():
+    """BASELINE config 4 in miniature: autograd over the ORACLE in float64 against the reference's own modules + GROVE methods run
+    with autograd in float64 (tests/golden/train_tiny512.npz: losses, gradient norms and strided gradient samples of every
+    parameter the loss reaches, and of the LLM hidden states).  This is the pin behind tests/test_gpu_training.py."""
+    g = _g("train_tiny512")
+    D, depth, heads, img, dim, mlp, hidden, L, P, seed = [int(x) for x in g["meta"]]
+    T, gidx = 8, (1, 2)
+    sd = {**synth.synth_state_dict(synth.encoder_param_shapes(D, depth, heads, gidx, img // 16), seed),
+          **synth.synth_state_dict(synth.decoder_param_shapes(dim, mlp), seed), **synth.synth_state_dict(synth.text_fcs_shapes(hidden, dim), seed)}
+    sd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    images = synth.synth_tensor("train_tiny512.images", (1, 3, T, img, img), seed).double()
+    hid = synth.synth_tensor("train_tiny512.hidden", (1, L, hidden), seed).double().requires_grad_(True)
+    ids = torch.full((1, L - 575), 7, dtype=torch.long)
+    for p_ in synth.det_positions(L, P, seed):
+        ids[0, p_ - 575 + 1] = 32005
+    mask = og.create_det_token_mask(ids, 32005)
+    _, boxes, logits, reps = og.grounding_forward(images, hid, mask, sd, depth=depth, heads=heads, global_idx=gidx, num_frames=T)
+    obj = torch.from_numpy(g["gt_obj"]).reshape(T, P)
+    gtb = torch.from_numpy(g["gt_boxes"])
+    gt_b, gt_o, s = [[]], [[]], 0
+    for f in range(T):
+        n = int(obj[f].sum())
+        gt_b[0].append(gtb[s:s + n]); gt_o[0].append(obj[f]); s += n
+    pb, pl = og.postprocess(boxes, logits, reps, T, None, infer=False)
+    losses = og.loss_components(pb, pl, gt_b, gt_o, torch.zeros((), dtype=torch.float64), 1.0, 2.0, 2.0)
+    np.testing.assert_allclose([float(losses[k]) for k in ("loss", "ce_loss", "giou_loss", "l1_loss", "temp_objectness_loss")], g["losses"],
+                               rtol=1e-6)
+    losses["loss"].backward()
+    checked = 0
+    for key in g.files:
+        if not key.startswith("gn:"):
+            continue
+        name = key[3:]
+        t = hid if name == "hidden" else sd[name]
+        assert t.grad is not None, name
+        gr = t.grad.reshape(-1)
+        step = max(gr.numel() // 64, 1)
+        scale = max(float(g[key]), 1e-12)
+        assert abs(float(gr.norm()) - float(g[key])) <= 2e-6 * scale + 1e-13, name
+        np.testing.assert_allclose(gr[::step][:64].numpy(), g["gs:" + name], rtol=0, atol=2e-6 * scale + 1e-13, err_msg=name)
+        checked += 1
+    assert checked >= 150
+    # and nothing else receives a gradient (the prompt encoder is frozen in GROVE and was not recorded: train.py:281-296)
+    reached = {k[3:] for k in g.files if k.startswith("gn:")}
+    for k, v in sd.items():
+        if k not in reached and not k.startswith("prompt_encoder."):
+            assert v.grad is None or float(v.grad.abs().max()) == 0.0, k

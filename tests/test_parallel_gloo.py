@@ -58,3 +58,31 @@ def test_window_schedule_matches_reference_port():
         assert parallel.sliding_segment_with_mask(n, 8) == box_eval.sliding_segment_with_mask(n, 8)
     assert parallel.units_of_rank(16, 8, 3) == [3, 11]
     assert sorted(sum((parallel.units_of_rank(5, 2, r) for r in range(2)), [])) == list(range(5))
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        grads = [torch.randn(s, generator=g) for s in ((300, 7), (5,), (1,), (64, 64), (1000,))]
+        parallel.allreduce_gradients(grads, bucket_elems=2200)          # forces three buckets, one of them a single tensor
+        ret[rank] = grads
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_buckets():
+    """config 4's data-parallel gradient averaging: bucketed all-reduce equals the mean of the per-rank gradients"""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    per_rank = []
+    for r in range(world):
+        g = torch.Generator().manual_seed(100 + r)
+        per_rank.append([torch.randn(s, generator=g) for s in ((300, 7), (5,), (1,), (64, 64), (1000,))])
+    for i in range(5):
+        mean = (per_rank[0][i] + per_rank[1][i]) / 2
+        for r in range(world):
+            assert torch.allclose(ret[r][i], mean, atol=1e-6), (r, i)
