@@ -9,3 +9,4 @@ from .modeling.mask_decoder import MaskDecoder  # noqa: F401
 from .modeling.prompt_encoder import PromptEncoder  # noqa: F401
 from .modeling.transformer import TwoWayTransformer  # noqa: F401
 from .modeling.grounding import GroundingBranch  # noqa: F401
+from .preprocess import ResizeLongestSide  # noqa: F401

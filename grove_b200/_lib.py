@@ -50,6 +50,8 @@ SIGNATURES = {
     "grove_box_losses_fwd": [_P, _P, _P, _P, _P, _P, _I, _P],
     "grove_box_iou": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "grove_greedy_match": [_P, _P, _D, _D, _P, _P, _I, _I, _P],
+    "grove_resize_rows_u8": [_P, _P, _P, _P, _I, _LL, _I, _I, _P],
+    "grove_frames_to_patches_u8": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P],
     # training step (backward pass)
     "grove_conv_wgrad_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "grove_transpose_to_bf16": [_P, _I, _P, _I, _I, _P],

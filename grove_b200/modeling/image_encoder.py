@@ -142,16 +142,39 @@ class ImageEncoderViT(nn.Module):
         V, _, T, H, W = x.shape
         if H != W or H % 16:
             raise ValueError("square inputs with side a multiple of 16 are required")
-        Fr, G, D, heads = V * T, H // 16, self.embed_dim, self.num_heads
-        hd, N = D // heads, (H // 16) ** 2
+        img = x.to(torch.bfloat16).contiguous()
+        patches = torch.empty(V * T * (H // 16) ** 2, 768, device=x.device, dtype=torch.bfloat16)
+        ops.im2col_patch16(img, patches)
+        return self._encode_patches(patches, V * T, H // 16)
+
+    @torch.no_grad()
+    def forward_frames(self, frames: torch.Tensor, transform=None) -> torch.Tensor:
+        """Decoded RGB frames, uint8 [V,T,h,w,3] on the GPU -> [V*T, out_chans, G, G]: the reference's host-side
+        ResizeLongestSide.apply_image + grounding_enc_processor + .bfloat16() (transforms.py:27-34, HowTo100M.py:168-178, train.py:751-753)
+        are fused into the patch embed's operand (grove_b200.preprocess); bit-identical to forward() on the host-processed tensor."""
+        from ..preprocess import ResizeLongestSide
+        if frames.dim() != 5 or frames.shape[-1] != 3 or frames.dtype != torch.uint8:
+            raise ValueError(f"expected uint8 frames of shape [V,T,h,w,3], got {tuple(frames.shape)} {frames.dtype}")
+        if not frames.is_cuda:
+            raise RuntimeError("grove_b200.ImageEncoderViT runs on CUDA only (no CPU fallback)")
+        V, T, h, w, _ = frames.shape
+        tr = transform if transform is not None else ResizeLongestSide(self.img_size)
+        patches = tr.patches(frames.reshape(V * T, h, w, 3).contiguous(), self.img_size)
+        G = self.img_size // 16
+        tok = self._encode_patches(patches, V * T, G)
+        out = tok.view(V * T, G, G, self.out_chans).permute(0, 3, 1, 2)
+        want = self.pos_embed.dtype if self.pos_embed is not None else torch.bfloat16
+        return out if want == torch.bfloat16 else out.to(want)
+
+    def _encode_patches(self, patches: torch.Tensor, Fr: int, G: int) -> torch.Tensor:
+        """patches bf16 [Fr*G*G, 768] (k = c*256 + py*16 + px) -> token-major embeddings [Fr, G*G, out_chans] bf16"""
+        D, heads = self.embed_dim, self.num_heads
+        hd, N = D // heads, G * G
         has_conv = any(isinstance(a, SpatioTemporalConvAdapter) for a in self.adapters)
         if has_conv and Fr % 8:
             raise ValueError("the spatio-temporal adapter groups frames by 8 (image_encoder.py:52): V*T must be a multiple of 8")
-        dev = x.device
+        dev = patches.device
         M = Fr * N
-        img = x.to(torch.bfloat16).contiguous()
-        patches = torch.empty(M, 768, device=dev, dtype=torch.bfloat16)
-        ops.im2col_patch16(img, patches)
         xs = torch.empty(M, D, device=dev, dtype=torch.float32)        # fp32 residual stream
         wpe = self._pack.get("pe.w", [self.patch_embed.proj.weight], lambda w: bf16(w.reshape(w.shape[0], -1)))
         bpe = self._pack.get("pe.b", [self.patch_embed.proj.bias], f32)

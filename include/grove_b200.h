@@ -157,6 +157,20 @@ int grove_greedy_match(double* iou, double* sim, double iou_thr, double sim_thr,
                        grove_stream_t stream);
 
 
+/* ==== frame pre-processing fused into the patch embed's operand ===============================
+ * ResizeLongestSide.apply_image (model/SAM/utils/transforms.py:27-34 — PIL bilinear, bit-exact restatement of Pillow's
+ * Resample.c: 22-bit fixed-point coefficients, horizontal then vertical pass, uint8 in between) followed by
+ * grounding_enc_processor (HowTo100M.py:168-178: (x - mean) / std, zero pad) and .bfloat16() (train.py:751-753).
+ * bounds [out, 2] = (first source index, tap count), coeffs [out, ksize] int32: built by the host exactly like precompute_coeffs. */
+/* horizontal pass over `rows` image rows: in [rows, w_in, 3] u8 -> out [rows, w_out, 3] u8 */
+int grove_resize_rows_u8(const uint8_t* in, uint8_t* out, const int* bounds, const int* coeffs, int ksize, long long rows, int w_in, int w_out,
+                         grove_stream_t stream);
+/* vertical pass + normalise + pad + patchify: in [F, h_in, w, 3] u8 -> patches [F*(img/16)^2, 768] bf16 (k = c*256 + py*16 + px), the A
+ * operand of the PatchEmbed GEMM (image_encoder.py:484-491).  Rows >= h_out and columns >= w are the zero padding; identity
+ * coefficients (count 1, 1 << 22) when the height is kept.  mean3 / std3: HOST pointers to three floats. */
+int grove_frames_to_patches_u8(const uint8_t* in, const int* vbounds, const int* vcoeffs, int vksize, void* patches, int F, int h_in, int w,
+                               int h_out, int img, const float* mean3, const float* std3, grove_stream_t stream);
+
 /* ==== training step of the grounding branch (BASELINE config 4; SURVEY.md §8a row "4-bwd") ========================
  * The reference trains this branch through autograd (train.py:761-782: model(**batch); model.backward(loss)); trainable
  * there: the Conv3d adapters, the whole mask decoder with its heads, text_hidden_fcs (train.py:279-296) — the ViT blocks

@@ -248,6 +248,35 @@ def train_case(name, seed):
     print(name, {k: float(v) for k, v in loss.items()}, len(keys), "gradient tensors")
 
 
+def preprocess_case(name, seed):
+    """ResizeLongestSide.apply_image (PIL bilinear) + grounding_enc_processor + .bfloat16() through the reference's own code."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_transforms", os.path.join(REF, "model", "SAM", "utils", "transforms.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    gp = _functions_from_source(os.path.join(REF, "infer_iground.py"), {"grounding_enc_processor"}, {"torch": torch, "F": torch.nn.functional})
+    rng = np.random.Generator(np.random.PCG64([seed, 3]))
+    out = {}
+    cases = [("down", 2, 90, 160, 64), ("up", 2, 20, 48, 64), ("tall", 1, 120, 45, 96), ("same", 1, 64, 64, 64), ("odd", 1, 77, 131, 80)]
+    for tag, T, h, w, L in cases:
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = (127 + 90 * np.sin(yy / 7.0)[..., None] * np.cos(xx / 5.0)[..., None] + rng.normal(0, 25, (T, h, w, 3))).clip(0, 255)
+        frames = base.astype(np.uint8)
+        resized = np.stack([tr.ResizeLongestSide(L).apply_image(f) for f in frames])
+        out[f"{tag}.frames"] = frames
+        out[f"{tag}.resized"] = resized
+        out[f"{tag}.meta"] = np.array([T, h, w, L])
+    # the normalise + pad + bf16 half has IMG_SIZE = 512 hard-coded (infer_iground.py:307): a small 40x64 clip, stored as bf16 bit patterns
+    frames = rng.integers(0, 256, (2, 40, 64, 3), dtype=np.uint8)
+    x = gp["grounding_enc_processor"](torch.from_numpy(frames).permute(3, 0, 1, 2).contiguous()).bfloat16()
+    out["proc.frames"] = frames
+    out["proc.bits_sub"] = x.view(torch.int16)[:, :, :48:1, :72:1].numpy()          # the image plus a rim of the zero padding
+    out["proc.pad_nonzero"] = np.array(int((x[:, :, 40:, :] != 0).sum() + (x[:, :, :, 64:] != 0).sum()))
+    out["proc.shape"] = np.array(x.shape)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith("resized")})
+
+
 def box_eval_case(name, seed):
     import importlib.util
     spec = importlib.util.spec_from_file_location("ref_eval_vidstg", os.path.join(REF, "eval_vidstg.py"))
@@ -313,6 +342,7 @@ def main():
     glue_case("glue", seed=5)
     box_eval_case("box_eval", seed=6)
     train_case("train_tiny512", seed=7)
+    preprocess_case("preprocess", seed=8)
 
 
 if __name__ == "__main__":

@@ -181,3 +181,20 @@ def test_training_step_gradients_vs_reference_autograd():
     for k, v in sd.items():
         if k not in reached and not k.startswith("prompt_encoder."):
             assert v.grad is None or float(v.grad.abs().max()) == 0.0, k
+
+
+def test_preprocessing_vs_reference_pil_chain():
+    """ResizeLongestSide.apply_image (Pillow bilinear through the reference's own class) and grounding_enc_processor + .bfloat16()
+    (infer_iground.py:304-318, train.py:751-753): the numpy restatement is bit-exact (tests/golden/preprocess.npz)."""
+    from oracle import preprocess as pp
+    g = _g("preprocess")
+    for tag in ("down", "up", "tall", "same", "odd"):
+        T, h, w, L = [int(v) for v in g[f"{tag}.meta"]]
+        frames = g[f"{tag}.frames"]
+        out = np.stack([pp.apply_image(f, L) for f in frames])
+        assert out.shape == g[f"{tag}.resized"].shape, tag
+        assert np.array_equal(out, g[f"{tag}.resized"]), tag
+    x = torch.from_numpy(pp.grounding_enc_processor(g["proc.frames"], 512)).bfloat16()
+    assert list(x.shape) == [int(v) for v in g["proc.shape"]]
+    assert np.array_equal(x.view(torch.int16)[:, :, :48, :72].numpy(), g["proc.bits_sub"])
+    assert int(g["proc.pad_nonzero"]) == 0 and float(x[:, :, 40:, :].abs().max()) == 0.0
