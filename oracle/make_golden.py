@@ -277,6 +277,21 @@ def preprocess_case(name, seed):
     print(name, {k: v.shape for k, v in out.items() if k.endswith("resized")})
 
 
+def posembed_case(name, seed):
+    """train.py:503-558 (resize_abs_pos_embedding / resize_rel_pos_embedding) executed from the reference's source"""
+    fn = _functions_from_source(os.path.join(REF, "train.py"), {"resize_abs_pos_embedding", "resize_rel_pos_embedding"},
+                                {"torch": torch, "F": torch.nn.functional, "nn": torch.nn})
+    pos = synth.synth_tensor(name + ".pos", (1, 8, 8, 24), seed)
+    rh, rw = synth.synth_tensor(name + ".rh", (15, 12), seed), synth.synth_tensor(name + ".rw", (15, 12), seed)
+    out = {}
+    for tgt in (64, 256):     # 8x8 -> 4x4 (down) and 16x16 (up)
+        out[f"abs{tgt}"] = fn["resize_abs_pos_embedding"](pos, tgt, 16, 24).numpy()
+        h, w = fn["resize_rel_pos_embedding"](rh, rw, tgt, 16, 12)
+        out[f"relh{tgt}"], out[f"relw{tgt}"] = h.numpy(), w.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 def box_eval_case(name, seed):
     import importlib.util
     spec = importlib.util.spec_from_file_location("ref_eval_vidstg", os.path.join(REF, "eval_vidstg.py"))
@@ -343,6 +358,7 @@ def main():
     box_eval_case("box_eval", seed=6)
     train_case("train_tiny512", seed=7)
     preprocess_case("preprocess", seed=8)
+    posembed_case("posembed", seed=9)
 
 
 if __name__ == "__main__":

@@ -55,3 +55,32 @@ def test_grounding_branch_surface_and_no_cpu_fallback():
     assert m.shape == (1, 575 + 64 + 1) and int(m[0].nonzero()) == 575 + 9
     with pytest.raises(RuntimeError, match="CUDA"):
         enc(torch.zeros(1, 3, 8, 512, 512))
+
+
+def test_checkpoint_tooling_matches_reference_surgery():
+    """grove_b200.checkpoint vs train.py:503-576 executed from the reference's source (tests/golden/posembed.npz), and the
+    strict=False key mapping of GROVE-prefixed checkpoints."""
+    import numpy as np
+    from conftest import GOLDEN
+    from grove_b200 import checkpoint as ck
+    from grove_b200.modeling.build_sam import sam_model_registry
+    g = np.load(os.path.join(GOLDEN, "posembed.npz"))
+    pos = synth.synth_tensor("posembed.pos", (1, 8, 8, 24), 9)
+    rh, rw = synth.synth_tensor("posembed.rh", (15, 12), 9), synth.synth_tensor("posembed.rw", (15, 12), 9)
+    for tgt in (64, 256):
+        np.testing.assert_allclose(ck.resize_abs_pos_embedding(pos, tgt).numpy(), g[f"abs{tgt}"], rtol=0, atol=1e-6)
+        h, w = ck.resize_rel_pos_embedding(rh, rw, tgt)
+        np.testing.assert_allclose(h.numpy(), g[f"relh{tgt}"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(w.numpy(), g[f"relw{tgt}"], rtol=0, atol=1e-6)
+    sam = sam_model_registry["vit_b"]()                       # reference default: 1024 encoder tables
+    enc = sam.image_encoder
+    ck.interpolate_positional_embeddings(enc, 512)
+    assert tuple(enc.pos_embed.shape) == (1, 32, 32, 768) and enc.img_size == 512
+    assert tuple(enc.blocks[2].attn.rel_pos_h.shape) == (63, 64) and tuple(enc.blocks[0].attn.rel_pos_h.shape) == (27, 64)
+    sd = {"model.grounding_encoder." + k: torch.zeros_like(v) for k, v in sam.state_dict().items()}
+    sd["model.layers.0.self_attn.q_proj.weight"] = torch.zeros(2, 2)
+    sd["model.text_hidden_fcs.0.0.bias"] = torch.ones(4096)
+    fcs = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(4096, 4096), torch.nn.ReLU(), torch.nn.Linear(4096, 256), torch.nn.Dropout(0.0))])
+    r = ck.load_sam_state_dict(sam, sd, fcs)
+    assert r["skipped"] == ["model.layers.0.self_attn.q_proj.weight"] and not r["unexpected"]
+    assert float(enc.pos_embed.abs().sum()) == 0.0 and float(fcs[0][0].bias.sum()) == 4096.0
