@@ -33,6 +33,7 @@ SIGNATURES = {
     "grove_attn_window_relpos_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_attn_window_relpos_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "grove_attn_global_relpos_fwd_lse": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd_mma": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_cast_f32_bf16": [_P, _P, _LL, _P],
     "grove_tokens_to_nchw_bf16": [_P, _P, _I, _I, _I, _P],
@@ -69,6 +70,7 @@ SIGNATURES = {
     "grove_batch_sum_bf16": [_P, _P, _I, _LL, _P],
     "grove_attn_relpos_bwd_workspace_bytes": [_I, _I, _I, _I, _I],
     "grove_attn_relpos_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_attn_relpos_bwd_lse": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_box_losses_bwd": [_P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _P],
 }
 _RESTYPES = {"grove_last_error": C.c_char_p, "grove_launch_count": C.c_longlong, "grove_reset_launch_count": None,

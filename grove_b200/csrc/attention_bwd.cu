@@ -272,14 +272,137 @@ attn_bwd_q_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qkv
   }
 }
 
+
+// =====================================================================================================================
+// Query side, global attention fast path (S = G, 64 % G == 0: a 64-key tile is 64/G whole grid rows).  The log-sum-exp comes
+// from the forward kernel (grove_attn_global_relpos_fwd_lse), so there is a single key sweep; rel_w lives in registers for the
+// whole kernel (each thread always sees the same key columns), rel_h is one value per (row, tile row); the bias cotangents
+// need no scratch: A_w accumulates in registers at fixed fragment positions, A_h is a quad-reduced row sum per tile written
+// straight to global.  65-80 KB of shared memory and <= 255 registers: two CTAs per SM.
+// =====================================================================================================================
+template <int G, int HD>
+__global__ void __launch_bounds__(128, 2)
+attn_bwd_q_global_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ dO, const float* __restrict__ rel, const float* __restrict__ Dsum,
+                         const float* __restrict__ lse, float* __restrict__ dq_out, float* __restrict__ A_out, int heads) {
+  constexpr int S = G, N = G * G, NT = N / 64, KS = HD / 16, NTD = HD / 8, TILEB = 64 * HD * 2, RPT = 64 / G, RH = G + 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = ((smem_u32(smem_raw) + 127u) & ~127u) - smem_u32(smem_raw);
+  const uint32_t s0 = smem_u32(smem_raw) + pad;
+  const uint32_t sQ = s0, sDO = s0 + TILEB, sK = s0 + 2 * TILEB, sV = s0 + 4 * TILEB;
+  float* sRelH = reinterpret_cast<float*>(smem_raw + pad + 6 * TILEB);   // [64][RH], pre-multiplied by log2(e)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int qt = blockIdx.x, h = blockIdx.y, f = blockIdx.z;
+  const int Dm = heads * HD;
+  const size_t tstride = (size_t)3 * Dm;
+  const bf16_t* qkv_f = qkv + (size_t)f * N * tstride + h * HD;
+  const size_t row0 = (size_t)f * N + qt * 64;                 // first query token (global row index) of this tile
+
+  load_tile64<HD>(sQ, [&](int r) { return qkv_f + (size_t)(qt * 64 + r) * tstride; }, tid);
+  load_tile64<HD>(sDO, [&](int r) { return dO + (row0 + r) * Dm + h * HD; }, tid);
+  auto load_kv = [&](int kt, int buf) {
+    load_tile64<HD>(sK + buf * TILEB, [&](int r) { return qkv_f + (size_t)(kt * 64 + r) * tstride + Dm; }, tid);
+    load_tile64<HD>(sV + buf * TILEB, [&](int r) { return qkv_f + (size_t)(kt * 64 + r) * tstride + 2 * Dm; }, tid);
+    cp_async_commit();
+  };
+  load_kv(0, 0);      // same commit group as Q / dO
+  for (int i = tid; i < 64 * G; i += 128) {
+    const int r = i / G, c = i % G;
+    sRelH[r * RH + c] = rel[((row0 + r) * heads + h) * (2 * S) + c] * kL2e;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  uint32_t qf[KS][4], dof[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    ldsm_x4(tile_addr<HD>(sQ, r0 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)), qf[ks]);
+    ldsm_x4(tile_addr<HD>(sDO, r0 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * ks + (lane >> 4)), dof[ks]);
+  }
+  const int row_l[2] = {r0 + g, r0 + g + 8};
+  float drow[2], lse2[2], relw[2][16], aw[2][16];
+#pragma unroll
+  for (int rs = 0; rs < 2; ++rs) {
+    const size_t rh = (row0 + row_l[rs]) * heads + h;
+    drow[rs] = Dsum[rh];
+    lse2[rs] = lse[rh];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        relw[rs][2 * j + e] = rel[rh * (2 * S) + S + (8 * j + 2 * t4 + e) % G] * kL2e;
+        aw[rs][2 * j + e] = 0.f;
+      }
+  }
+  const float scale = rsqrtf((float)HD), scale_l2 = scale * kL2e;
+  float dq[NTD][4];
+#pragma unroll
+  for (int j = 0; j < NTD; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+
+  for (int kt = 0; kt < NT; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < NT) { load_kv(kt + 1, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+    __syncthreads();
+    float s[8][4], dp[8][4];
+    mma_a_yt<HD>(s, qf, sK + buf * TILEB, lane);
+    mma_a_yt<HD>(dp, dof, sV + buf * TILEB, lane);
+    float ah[2][RPT];
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs)
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) ah[rs][q] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int rs = e >> 1, sub = (RPT == 1) ? 0 : (j * 8) / G;          // which grid row of the tile this column belongs to
+        const float v = s[j][e] * scale_l2 + sRelH[row_l[rs] * RH + kt * RPT + sub] + relw[rs][2 * j + (e & 1)];
+        const float ds = exp2f(v - lse2[rs]) * (dp[j][e] - drow[rs]);
+        s[j][e] = ds;
+        aw[rs][2 * j + (e & 1)] += ds;
+        ah[rs][sub] += ds;
+      }
+    mma_p_y<HD>(dq, s, sK + buf * TILEB, lane);
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs)
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        float a = ah[rs][q];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (t4 == 0) A_out[((row0 + row_l[rs]) * heads + h) * (2 * S) + kt * RPT + q] = a;
+      }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int rs = 0; rs < 2; ++rs) {
+    float* o = dq_out + (row0 + row_l[rs]) * Dm + h * HD + 2 * t4;
+#pragma unroll
+    for (int j = 0; j < NTD; ++j) *reinterpret_cast<float2*>(o + 8 * j) = make_float2(dq[j][2 * rs] * scale, dq[j][2 * rs + 1] * scale);
+    float* ao = A_out + ((row0 + row_l[rs]) * heads + h) * (2 * S) + S;
+    if (G == 64) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(ao + 8 * j + 2 * t4) = make_float2(aw[rs][2 * j], aw[rs][2 * j + 1]);
+    } else {   // G == 32: columns c and c + 32 of a tile are the same jx
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float2*>(ao + 8 * j + 2 * t4) = make_float2(aw[rs][2 * j] + aw[rs][2 * (j + 4)], aw[rs][2 * j + 1] + aw[rs][2 * (j + 4) + 1]);
+    }
+  }
+}
+
 // =====================================================================================================================
 // Key/value side (transposed orientation: rows = keys, columns = queries)
 // =====================================================================================================================
-template <int S, int HD, bool WIN>
-__global__ void __launch_bounds__(128, 1)
+// GFAST (global attention, 64 % S == 0): a 64-key tile is 64/S whole grid rows, so of each streamed query's 2S bias values only the
+// S rel_w entries and the tile's 64/S rel_h entries are fetched (half the L2 traffic of the generic layout), two CTAs per SM.
+template <int S, int HD, bool WIN, bool GFAST>
+__global__ void __launch_bounds__(128, GFAST ? 2 : 1)
 attn_bwd_kv_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qkv_bias, const bf16_t* __restrict__ dO, const float* __restrict__ rel,
                    const float* __restrict__ Dsum, const float* __restrict__ lse, bf16_t* __restrict__ dqkv, int G, int heads) {
-  constexpr int NT = (S * S + 63) / 64, KS = HD / 16, NTD = HD / 8, TILEB = 64 * HD * 2, RS = RelStride<S>::v;
+  constexpr int NT = (S * S + 63) / 64, KS = HD / 16, NTD = HD / 8, TILEB = 64 * HD * 2, RS = GFAST ? S + 4 : RelStride<S>::v;
+  constexpr int RPT = GFAST ? 64 / S : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = ((smem_u32(smem_raw) + 127u) & ~127u) - smem_u32(smem_raw);
   const uint32_t s0 = smem_u32(smem_raw) + pad;
@@ -334,13 +457,18 @@ attn_bwd_kv_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qk
     load_tile64<HD>(sQ + buf * TILEB, [&](int r) { const int t = map.tok(qt * 64 + r); return t >= 0 ? qkv_f + (size_t)t * tstride : nullptr; }, tid);
     load_tile64<HD>(sDO + buf * TILEB, [&](int r) { const int t = map.tok(qt * 64 + r); return t >= 0 ? dO + ((size_t)f * N + t) * Dm + h * HD : nullptr; },
                     tid);
-    constexpr int C4 = (2 * S) / 4;   // 16-byte chunks per bias row (2S floats; S even)
+    constexpr int C4 = (GFAST ? S : 2 * S) / 4;   // 16-byte chunks per bias row (2S floats, or only the S rel_w entries)
     for (int i = tid; i < 64 * C4; i += 128) {
       const int r = i / C4, c = i % C4, t = map.tok(qt * 64 + r);
       const uint32_t dst = sRel_u + ((buf * 64 + r) * RS + c * 4) * 4;
-      if (t >= 0) cp_async16(dst, rel + (((size_t)f * N + t) * heads + h) * (2 * S) + c * 4);
+      if (t >= 0) cp_async16(dst, rel + (((size_t)f * N + t) * heads + h) * (2 * S) + (GFAST ? S : 0) + c * 4);
       else st_smem16(dst, make_uint4(0, 0, 0, 0));
     }
+    if (GFAST)   // the rel_h entries of this key tile's grid rows
+      for (int i = tid; i < 64 * RPT; i += 128) {
+        const int r = i / RPT, q = i % RPT;
+        sRel[(buf * 64 + r) * RS + S + q] = rel[(((size_t)f * N + qt * 64 + r) * heads + h) * (2 * S) + kt * RPT + q];
+      }
     if (tid < 64) {
       const int t = map.tok(qt * 64 + tid);
       sLse[buf * 64 + tid] = t >= 0 ? lse[((size_t)f * N + t) * heads + h] : INFINITY;
@@ -367,7 +495,8 @@ attn_bwd_kv_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qk
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int rs = e >> 1, c = 8 * j + 2 * t4 + (e & 1);
-        const float v = s[j][e] * scale_l2 + (relb[c * RS + jy[rs]] + relb[c * RS + S + jx[rs]]) * kL2e;
+        const float v = s[j][e] * scale_l2 + (GFAST ? relb[c * RS + S + (jy[rs] - kt * RPT)] + relb[c * RS + jx[rs]]
+                                                    : relb[c * RS + jy[rs]] + relb[c * RS + S + jx[rs]]) * kL2e;
         const float p = kvalid[rs] ? exp2f(v - sLse[buf * 64 + c]) : 0.f;
         s[j][e] = p;
         dp[j][e] = p * (dp[j][e] - sD[buf * 64 + c]);
@@ -467,8 +596,9 @@ __global__ void rowdot_kernel(const bf16_t* __restrict__ a, const bf16_t* __rest
 
 template <int S, int HD, bool WIN>
 static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t* Rh, const bf16_t* Rw, const bf16_t* O, const bf16_t* dO, bf16_t* dqkv,
-                        float* ws, int F, int G, int heads, cudaStream_t st) {
+                        float* ws, const float* lse_fwd, int F, int G, int heads, cudaStream_t st) {
   constexpr int NT = (S * S + 63) / 64, TILEB = 64 * HD * 2, RS = RelStride<S>::v;
+  constexpr bool GFAST = !WIN && (64 % S == 0) && S >= 32;
   const long long M = (long long)F * G * G;
   float* rel = ws;
   float* A = rel + M * heads * 2 * S;
@@ -478,21 +608,31 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
   const int regions = WIN ? ((G + S - 1) / S) * ((G + S - 1) / S) : 1;
   const int smem_rel = (2 * (2 * S - 1) * (HD + 1) + 64 * (HD + 1 > 2 * S + 1 ? HD + 1 : 2 * S + 1)) * (int)sizeof(float);
   const int smem_q = 128 + 6 * TILEB + (2 * 64 * RS + 64 * 65) * 4 + 64 * 4;
-  const int smem_kv = 128 + 6 * TILEB + (2 * 64 * RS + 256) * 4 + 64 * 4;
+  const int smem_qf = 128 + 6 * TILEB + 64 * (S + 1) * 4;
+  const int smem_kv = 128 + 6 * TILEB + (2 * 64 * (GFAST ? S + 4 : RS) + 256) * 4 + 64 * 4;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(relpos_kernel<S, HD, WIN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rel);
     cudaFuncSetAttribute(relpos_kernel<S, HD, WIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rel);
     cudaFuncSetAttribute(attn_bwd_q_kernel<S, HD, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q);
-    cudaFuncSetAttribute(attn_bwd_kv_kernel<S, HD, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv);
+    cudaFuncSetAttribute(attn_bwd_kv_kernel<S, HD, WIN, GFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv);
+    if constexpr (GFAST) cudaFuncSetAttribute(attn_bwd_q_global_kernel<S, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_qf);
     attr = true;
   }
   const dim3 grid_rel((unsigned)(M / 64), heads);
   relpos_kernel<S, HD, WIN, 0><<<grid_rel, 256, smem_rel, st>>>(qkv, Rh, Rw, rel, nullptr, nullptr, nullptr, G, heads);
   rowdot_kernel<<<(unsigned)((M * heads + 255) / 256), 256, 0, st>>>(dO, O, Dsum, M * heads, HD);
   const dim3 grid(NT, regions * heads, F);
-  attn_bwd_q_kernel<S, HD, WIN><<<grid, 128, smem_q, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqc, A, G, heads);
-  attn_bwd_kv_kernel<S, HD, WIN><<<grid, 128, smem_kv, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqkv, G, heads);
+  bool fast_q = false;
+  if constexpr (GFAST) {
+    if (lse_fwd != nullptr) {      // the forward kernel's log-sum-exp: one key sweep instead of two
+      attn_bwd_q_global_kernel<S, HD><<<dim3(NT, heads, F), 128, smem_qf, st>>>(qkv, dO, rel, Dsum, lse_fwd, dqc, A, heads);
+      lse = const_cast<float*>(lse_fwd);
+      fast_q = true;
+    }
+  }
+  if (!fast_q) attn_bwd_q_kernel<S, HD, WIN><<<grid, 128, smem_q, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqc, A, G, heads);
+  attn_bwd_kv_kernel<S, HD, WIN, GFAST><<<grid, 128, smem_kv, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqkv, G, heads);
   relpos_kernel<S, HD, WIN, 1><<<grid_rel, 256, smem_rel, st>>>(qkv, Rh, Rw, nullptr, A, dqc, dqkv, G, heads);
   grove_count_launch(5);
   GROVE_CHECK_LAUNCH();
@@ -507,14 +647,15 @@ extern "C" long long grove_attn_relpos_bwd_workspace_bytes(int F, int G, int hea
   return (M * heads * 2 * S * 2 + M * heads * 2 + M * heads * hd) * (long long)sizeof(float);
 }
 
-extern "C" int grove_attn_relpos_bwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, const void* att,
-                                     const void* datt, void* dqkv, void* workspace, int F, int G, int heads, int hd, int ws, cudaStream_t stream) {
+extern "C" int grove_attn_relpos_bwd_lse(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, const void* att,
+                                         const void* datt, void* dqkv, void* workspace, const float* lse_fwd, int F, int G, int heads, int hd, int ws,
+                                         cudaStream_t stream) {
   GROVE_CHECK_ARG(qkv && rel_pos_h && rel_pos_w && att && datt && dqkv && workspace && F > 0 && G > 0 && heads > 0);
   GROVE_CHECK_ARG((G * G) % 64 == 0 && (ws == 0 || qkv_bias_bf16));
   GROVE_CHECK_ARG(((uintptr_t)workspace & 15) == 0);
   auto q = (const bf16_t*)qkv; auto qb = (const bf16_t*)qkv_bias_bf16; auto rh = (const bf16_t*)rel_pos_h; auto rw = (const bf16_t*)rel_pos_w;
   auto o = (const bf16_t*)att; auto d = (const bf16_t*)datt; auto out = (bf16_t*)dqkv; auto w = (float*)workspace;
-#define RUN(S_, HD_, WIN_) return run_attn_bwd<S_, HD_, WIN_>(q, qb, rh, rw, o, d, out, w, F, G, heads, stream)
+#define RUN(S_, HD_, WIN_) return run_attn_bwd<S_, HD_, WIN_>(q, qb, rh, rw, o, d, out, w, lse_fwd, F, G, heads, stream)
   if (ws == 14) {
     if (hd == 64) RUN(14, 64, true);
     if (hd == 80) RUN(14, 80, true);
@@ -529,4 +670,9 @@ extern "C" int grove_attn_relpos_bwd(const void* qkv, const void* qkv_bias_bf16,
 #undef RUN
   grove_set_error("attention backward is built for window 14 or global grids 16/32/64 with head dim 64/80 (got ws=%d G=%d hd=%d)", ws, G, hd);
   return GROVE_ERR_UNSUPPORTED;
+}
+
+extern "C" int grove_attn_relpos_bwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, const void* att,
+                                     const void* datt, void* dqkv, void* workspace, int F, int G, int heads, int hd, int ws, cudaStream_t stream) {
+  return grove_attn_relpos_bwd_lse(qkv, qkv_bias_bf16, rel_pos_h, rel_pos_w, att, datt, dqkv, workspace, nullptr, F, G, heads, hd, ws, stream);
 }

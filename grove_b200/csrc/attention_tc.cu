@@ -14,12 +14,16 @@
 // 16 exp2/clk MUFU rate, not by MMA).  Scores never leave the SM.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "grove_b200.h"
+#include "tmem_ldst.cuh"
 
 namespace grove {
 
-constexpr int kAttThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two threads per query row)
+// warp 0 TMA, warp 1 MMA, then 4 * SPLIT softmax warps: SPLIT threads per query row (= TMEM lane), each owning 128 / SPLIT keys of a block
+template <int SPLIT> constexpr int att_threads() { return 64 + 128 * SPLIT; }
 constexpr int kVStages = 2;
 template <int HD> constexpr int k_stages() { return HD == 64 ? 4 : 3; }
 
@@ -27,9 +31,10 @@ template <int HD> constexpr int k_stages() { return HD == 64 ? 4 : 3; }
 // tile is [128 x 64 | 128 x 16], Q.K^T takes a 5th k-step from the tails, P.V issues a second N=16 MMA into O columns 64-79.
 struct AttTmaps { CUtensorMap qkv, rh, rw, qkv_x, rh_x, rw_x; };
 
-template <int G, int HD>
-__global__ void __launch_bounds__(kAttThreads, 1)
-attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __restrict__ out, int heads) {
+template <int G, int HD, int SPLIT>
+__global__ void __launch_bounds__(att_threads<SPLIT>(), 1)
+attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out, int heads) {
+  constexpr int CPT = 4 / SPLIT;                    // 32-key chunks of a 128-key block per softmax thread
   constexpr bool kX = HD > 64;                      // has the 16-wide tail
   constexpr int TS = 16384 + (kX ? 4096 : 0);       // bytes of one [128 x HD] operand tile
   constexpr int kKStages = k_stages<HD>();
@@ -44,8 +49,8 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
   const uint32_t sV = sK + kKStages * TS;         // 2 V tiles; during the prologue: Rw | Rh tables
   const uint32_t sP = sV + kVStages * TS;      // 2 x 32 KB P buffers (two 64-key slabs each); prologue: fp32 staging [128][128]
   const uint32_t sRelH = sP + 65536;              // [G][128] fp32
-  const uint32_t sXch = sRelH + G * 128 * 4;      // 2 x [2][128] fp32: max and sum exchange between the two threads of a row
-  const uint32_t bar0 = sXch + 2048;
+  const uint32_t sXch = sRelH + G * 128 * 4;      // 2 x [SPLIT][128] fp32: max and sum exchange between the threads of a row
+  const uint32_t bar0 = sXch + 2 * SPLIT * 128 * 4;
   uint8_t* smem_al = smem_raw + (s0 - smem_u32(smem_raw));
   float* stage_f = reinterpret_cast<float*>(smem_al + (sP - s0));
   float* relh_f = reinterpret_cast<float*>(smem_al + (sRelH - s0));
@@ -66,8 +71,8 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
     for (int i = 0; i < kKStages; ++i) { mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1); }
     for (int i = 0; i < kVStages; ++i) { mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 8);
-      mbar_init(bar(P_FULL + i), 8); mbar_init(bar(P_EMPTY + i), 1);
+      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 4 * SPLIT);
+      mbar_init(bar(P_FULL + i), 4 * SPLIT); mbar_init(bar(P_EMPTY + i), 1);
     }
     fence_barrier_init();
   }
@@ -180,26 +185,26 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
   } else {
     // ===================== softmax warps: two threads per query row =====================
     const int quad = warp & 3;
-    const int hs = (warp - 2) >> 2;                      // 0: key chunks {0,2} of every block, 1: chunks {1,3}
+    const int hs = (warp - 2) >> 2;                      // this thread owns key chunks {hs, hs + SPLIT, ..} of every block
     const int row = quad * 32 + lane;                    // row inside the tile == TMEM lane
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
     const int q = q0 + row;
     const int qh = q / G, qw = q % G;
     constexpr float kL2e = 1.4426950408889634f;
-    auto softmax_sync = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    auto softmax_sync = []() { asm volatile("bar.sync 1, %0;" ::"n"(128 * SPLIT) : "memory"); };
     // staging row with the float4 slots XOR-swizzled by the row (conflict-free 128-bit stores of 32 different rows)
     auto stage_at = [&](int e) { return stage_f[row * 128 + ((((e >> 2) ^ (row & 7)) << 2) | (e & 3))]; };
     uint32_t sit = 0;
     float relw[32];                                      // this thread's kw half (G=64) / the whole grid row (G=32)
-    const int kw0 = (G == 64) ? hs * 32 : 0;
+    const int kw0 = (G == 64) ? (hs & 1) * 32 : 0;       // chunk c covers kw = (c % 2) * 32 .. + 32 of a 64-wide grid row; SPLIT is even
     // ---- prologue: rel_w -> registers, rel_h -> smem (both x log2 e)
 #pragma unroll
     for (int which = 0; which < 2; ++which, ++sit) {
       mbar_wait(bar(S_FULL + (sit & 1u)), (sit >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {                   // each thread of the pair moves half of the 128 table columns
-        const int c = 2 * cc + hs;
+      for (int cc = 0; cc < CPT; ++cc) {                 // the threads of a row share the 128 table columns
+        const int c = SPLIT * cc + hs;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tS0 + (sit & 1u) * 128 + c * 32 + tlane, r);
         tmem_ld_wait();
@@ -216,7 +221,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
 #pragma unroll
         for (int j = 0; j < 32; ++j) relw[j] = stage_at(qw + (G - 1) - (kw0 + j)) * kL2e;
       } else {
-        for (int kh = hs * (G / 2); kh < (hs + 1) * (G / 2); ++kh) relh_f[kh * 128 + row] = stage_at(qh + (G - 1) - kh) * kL2e;
+        for (int kh = hs * (G / SPLIT); kh < (hs + 1) * (G / SPLIT); ++kh) relh_f[kh * 128 + row] = stage_at(qh + (G - 1) - kh) * kL2e;
       }
       softmax_sync();                                    // staging is rewritten by the next table / rel_h complete
     }
@@ -227,50 +232,51 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       const uint32_t sb = sit & 1u;
       mbar_wait(bar(S_FULL + sb), (sit >> 1) & 1u);
       tc_fence_after();
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32b_x32(tS0 + sb * 128 + hs * 32 + tlane, ra);
-      tmem_ld_32x32b_x32(tS0 + sb * 128 + (2 + hs) * 32 + tlane, rb);
+      uint32_t rr[CPT][32];
+#pragma unroll
+      for (int cc = 0; cc < CPT; ++cc) tmem_ld_32x32b_x32(tS0 + sb * 128 + (SPLIT * cc + hs) * 32 + tlane, rr[cc]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));     // S is in registers: the MMA warp may overwrite this buffer
-      const int kha = (b * 128 + hs * 32) / G, khb = (b * 128 + (2 + hs) * 32) / G;
-      float mxa = -INFINITY, mxb = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        mxa = fmaxf(mxa, fmaf(__uint_as_float(ra[j]), c_scale, relw[j]));
-        mxb = fmaxf(mxb, fmaf(__uint_as_float(rb[j]), c_scale, relw[j]));
+      for (int cc = 0; cc < CPT; ++cc) {
+        const int kh = (b * 128 + (SPLIT * cc + hs) * 32) / G;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(rr[cc][j]), c_scale, relw[j]));
+        m = fmaxf(m, mx + relh_f[kh * 128 + row]);
       }
-      m = fmaxf(m, fmaxf(mxa + relh_f[kha * 128 + row], mxb + relh_f[khb * 128 + row]));
     }
     xch_f[hs * 128 + row] = m;
     softmax_sync();
-    m = fmaxf(m, xch_f[(hs ^ 1) * 128 + row]);
+#pragma unroll
+    for (int o = 1; o < SPLIT; ++o) m = fmaxf(m, xch_f[((hs + o) % SPLIT) * 128 + row]);
     // ---- phase 2: probabilities and P.V
     float lsum = 0.f;
     for (int b = 0; b < NB; ++b, ++sit) {
       const uint32_t sb = sit & 1u, pb = b & 1u;
       mbar_wait(bar(S_FULL + sb), (sit >> 1) & 1u);
       tc_fence_after();
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32b_x32(tS0 + sb * 128 + hs * 32 + tlane, ra);
-      tmem_ld_32x32b_x32(tS0 + sb * 128 + (2 + hs) * 32 + tlane, rb);
+      uint32_t rr[CPT][32];
+#pragma unroll
+      for (int cc = 0; cc < CPT; ++cc) tmem_ld_32x32b_x32(tS0 + sb * 128 + (SPLIT * cc + hs) * 32 + tlane, rr[cc]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
       mbar_wait(bar(P_EMPTY + pb), ((b >> 1) & 1u) ^ 1u);   // P.V of block b-2 has finished reading this P buffer
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = 2 * cc + hs;
+      for (int cc = 0; cc < CPT; ++cc) {
+        const int c = SPLIT * cc + hs;
         const int kh = (b * 128 + c * 32) / G;
         const float off = relh_f[kh * 128 + row] - m;
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float p0, p1;
-          const float e0 = fmaf(__uint_as_float(cc ? rb[j] : ra[j]), c_scale, relw[j]) + off;
-          const float e1 = fmaf(__uint_as_float(cc ? rb[j + 1] : ra[j + 1]), c_scale, relw[j + 1]) + off;
+          const float e0 = fmaf(__uint_as_float(rr[cc][j]), c_scale, relw[j]) + off;
+          const float e1 = fmaf(__uint_as_float(rr[cc][j + 1]), c_scale, relw[j + 1]) + off;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
           lsum += p0 + p1;
@@ -284,24 +290,29 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(P_FULL + pb));
     }
-    // ---- epilogue: O / l -> bf16 -> global (each thread of the pair stores 32 of the 64 head dims)
-    xch_f[256 + hs * 128 + row] = lsum;
+    // ---- epilogue: O / l -> bf16 -> global (each thread of a row stores 64 / SPLIT of the first 64 head dims)
+    xch_f[SPLIT * 128 + hs * 128 + row] = lsum;
     softmax_sync();
-    const float inv = 1.f / (lsum + xch_f[256 + (hs ^ 1) * 128 + row]);
+#pragma unroll
+    for (int o = 1; o < SPLIT; ++o) lsum += xch_f[SPLIT * 128 + ((hs + o) % SPLIT) * 128 + row];
+    const float inv = 1.f / lsum;
+    if (lse_out != nullptr && hs == 0) lse_out[((size_t)tok0 + q) * heads + h] = m + log2f(lsum);   // log2 domain, for the backward pass
     mbar_wait(bar(O_FULL), 0);
     tc_fence_after();
-    __nv_bfloat16* orow = out + ((size_t)tok0 + q) * D + h * HD + hs * 32;
+    constexpr int DPT = 64 / SPLIT;                      // head dims per thread
+    __nv_bfloat16* orow = out + ((size_t)tok0 + q) * D + h * HD + hs * DPT;
     {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tO + hs * 32 + tlane, r);
+      uint32_t r[DPT];
+      if constexpr (DPT == 32) tmem_ld_32x32b_x32(tO + hs * DPT + tlane, r);
+      else tmem_ld_x16(tO + hs * DPT + tlane, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j += 8)
+      for (int j = 0; j < DPT; j += 8)
         *reinterpret_cast<uint4*>(orow + j) =
             make_uint4(pack_bf16(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv), pack_bf16(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv),
                        pack_bf16(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv), pack_bf16(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv));
     }
-    if (kX) {   // head dims 64..79: 8 per thread of the pair
+    if (kX && hs < 2) {   // head dims 64..79: 8 per thread for two threads of the row
       uint32_t r[8];
       tmem_ld_32x32b_x8(tO + 64 + hs * 8 + tlane, r);
       tmem_ld_wait();
@@ -317,7 +328,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
 
 template <int G, int HD>
 constexpr int att_tc_smem() {
-  return (1 + k_stages<HD>() + kVStages) * (16384 + (HD > 64 ? 4096 : 0)) + 65536 + G * 128 * 4 + 2048 /*xch*/ + 1024 /*align*/ + 512 /*barriers*/;
+  return (1 + k_stages<HD>() + kVStages) * (16384 + (HD > 64 ? 4096 : 0)) + 65536 + G * 128 * 4 + 4096 /*xch*/ + 1024 /*align*/ + 512 /*barriers*/;
 }
 
 int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows);
@@ -325,8 +336,14 @@ int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t
 }  // namespace grove
 using namespace grove;
 
-template <int G, int HD>
-static int launch_att_tc(const void* qkv, const void* rh, const void* rw, void* out, int F, int heads, cudaStream_t stream) {
+static int att_split() {   // softmax threads per query row: 2 by default; GROVE_ATT_SPLIT=4 selects four (measured equal: the kernel is not
+  static int v = 0;        // bound by softmax-warp latency)
+  if (!v) { const char* e = getenv("GROVE_ATT_SPLIT"); v = (e && e[0] == '4') ? 4 : 2; }
+  return v;
+}
+
+template <int G, int HD, int SPLIT>
+static int launch_att_tc(const void* qkv, const void* rh, const void* rw, void* out, float* lse, int F, int heads, cudaStream_t stream) {
   const int N = G * G, D = heads * HD;
   AttTmaps tm;
   int rc;
@@ -341,16 +358,30 @@ static int launch_att_tc(const void* qkv, const void* rh, const void* rw, void* 
     tm.qkv_x = tm.qkv; tm.rh_x = tm.rh; tm.rw_x = tm.rw;
   }
   constexpr int smem = att_tc_smem<G, HD>();
-  cudaError_t e = cudaFuncSetAttribute(attn_global_tc_kernel<G, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(attn_global_tc_kernel<G, HD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-  attn_global_tc_kernel<G, HD><<<dim3(N / 128, heads, F), kAttThreads, smem, stream>>>(tm, (__nv_bfloat16*)out, heads);
+  attn_global_tc_kernel<G, HD, SPLIT><<<dim3(N / 128, heads, F), att_threads<SPLIT>(), smem, stream>>>(tm, (__nv_bfloat16*)out, lse, heads);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
 }
 
+template <int G, int HD>
+static int launch_att_tc_split(const void* qkv, const void* rh, const void* rw, void* out, float* lse, int F, int heads, cudaStream_t stream) {
+  return att_split() == 2 ? launch_att_tc<G, HD, 2>(qkv, rh, rw, out, lse, F, heads, stream)
+                          : launch_att_tc<G, HD, 4>(qkv, rh, rw, out, lse, F, heads, stream);
+}
+
+extern "C" int grove_attn_global_relpos_fwd_lse(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, float* lse, int F, int G,
+                                                int heads, int hd, cudaStream_t stream);
+
 extern "C" int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G, int heads,
                                             int hd, cudaStream_t stream) {
+  return grove_attn_global_relpos_fwd_lse(qkv, rel_pos_h, rel_pos_w, out, nullptr, F, G, heads, hd, stream);
+}
+
+extern "C" int grove_attn_global_relpos_fwd_lse(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, float* lse, int F, int G,
+                                                int heads, int hd, cudaStream_t stream) {
   GROVE_CHECK_ARG(qkv && rel_pos_h && rel_pos_w && out && F > 0 && heads > 0);
   if ((hd != 64 && hd != 80) || (G != 64 && G != 32)) {
     grove_set_error("grove_attn_global_relpos_fwd: head dim 64 / 80 and G in {32,64} are built (got hd=%d G=%d)", hd, G);
@@ -358,8 +389,8 @@ extern "C" int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos
   }
   GROVE_CHECK_ARG(F <= 65535 && heads <= 65535);
   GROVE_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)rel_pos_h & 15) == 0 && ((uintptr_t)rel_pos_w & 15) == 0);
-  if (hd == 64) return G == 64 ? launch_att_tc<64, 64>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream)
-                               : launch_att_tc<32, 64>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream);
-  return G == 64 ? launch_att_tc<64, 80>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream)
-                 : launch_att_tc<32, 80>(qkv, rel_pos_h, rel_pos_w, out, F, heads, stream);
+  if (hd == 64) return G == 64 ? launch_att_tc_split<64, 64>(qkv, rel_pos_h, rel_pos_w, out, lse, F, heads, stream)
+                               : launch_att_tc_split<32, 64>(qkv, rel_pos_h, rel_pos_w, out, lse, F, heads, stream);
+  return G == 64 ? launch_att_tc_split<64, 80>(qkv, rel_pos_h, rel_pos_w, out, lse, F, heads, stream)
+                 : launch_att_tc_split<32, 80>(qkv, rel_pos_h, rel_pos_w, out, lse, F, heads, stream);
 }

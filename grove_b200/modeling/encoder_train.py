@@ -68,6 +68,7 @@ def encode_train(enc, x: torch.Tensor):
         att = torch.empty(M, D, device=dev, dtype=torch.bfloat16) if keep else scratch["att"]
         ops.gemm(h, wq, qkv, bias=bq)
         S = blk.window_size if blk.window_size > 0 else G
+        lse = None
         if blk.window_size > 0:
             bqb = enc._pack.get(k + ".qkvb16", [blk.attn.qkv.bias], bf16)
             tab = enc._pack.get(k + ".reltab", [blk.attn.rel_pos_h, blk.attn.rel_pos_w],
@@ -76,7 +77,8 @@ def encode_train(enc, x: torch.Tensor):
         else:
             rh = enc._pack.get(k + ".rh", [blk.attn.rel_pos_h], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
             rw = enc._pack.get(k + ".rw", [blk.attn.rel_pos_w], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
-            ops.attn_global(qkv, rh, rw, att, F=Fr, G=G, heads=heads, hd=hd)
+            lse = torch.empty(M, heads, device=dev, dtype=torch.float32) if keep else None   # row log-sum-exp, reused by the backward pass
+            ops.attn_global(qkv, rh, rw, att, F=Fr, G=G, heads=heads, hd=hd, lse=lse)
         wp, bp = enc._linear(k + ".proj", blk.attn.proj)
         x1 = torch.empty(M, D, device=dev, dtype=torch.float32) if keep else xs
         ops.gemm(att, wp, x1, bias=bp, resid=xs)
@@ -91,7 +93,7 @@ def encode_train(enc, x: torch.Tensor):
         x2 = torch.empty(M, D, device=dev, dtype=torch.float32) if keep else x1
         ops.gemm(hid, w2, x2, bias=bb2, resid=x1, out2=xb if (conv or i == last) else None)
         if keep:
-            tape["blocks"][i] = {"x0": xs, "x1": x1, "qkv": qkv, "att": att, "pre": pre}
+            tape["blocks"][i] = {"x0": xs, "x1": x1, "qkv": qkv, "att": att, "pre": pre, "lse": lse if blk.window_size == 0 else None}
         xs = x2
         if conv:
             kk = gi.index(i)
@@ -191,7 +193,7 @@ def encode_backward(enc, tape, d_emb: torch.Tensor, grads: GradStore) -> None:
         rw = enc._pack.get(k + ".rw", [blk.attn.rel_pos_w], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
         bqb = enc._pack.get(k + ".qkvb16", [blk.attn.qkv.bias], bf16)
         ops.attn_relpos_bwd(B_["qkv"], bqb if blk.window_size > 0 else None, rh, rw, B_["att"], dh, dqkv, F=Fr, G=G, heads=heads, hd=hd,
-                            ws=blk.window_size)
+                            ws=blk.window_size, lse=B_["lse"])
         wqt = enc._pack.get(k + ".qkv.T", [blk.attn.qkv.weight], lambda w: bf16(w.t()))
         ops.gemm(dqkv, wqt, dh)
         ops.layernorm_bwd(B_["x0"], f32(blk.norm1.weight), dh, eps=blk.norm1.eps, dx_in=dxs, dx_out=dxs, dx_bf16=g16)

@@ -117,10 +117,15 @@ def attn_window_tc(qkv, qkv_bias_bf16, rel_table, out, *, F, G, heads, hd, ws=14
     return out
 
 
-def attn_global(qkv, rel_h, rel_w, out, *, F, G, heads, hd, legacy_mma=False):
+def attn_global(qkv, rel_h, rel_w, out, *, F, G, heads, hd, legacy_mma=False, lse=None):
     for t, n in ((qkv, "qkv"), (rel_h, "rel_pos_h"), (rel_w, "rel_pos_w"), (out, "out")):
         _req(t, BF16, n)
     assert qkv.numel() == F * G * G * 3 * heads * hd and rel_h.shape == (2 * G - 1, hd)
+    if lse is not None:
+        assert not legacy_mma and lse.numel() == F * G * G * heads
+        check(lib().grove_attn_global_relpos_fwd_lse(_p(qkv), _p(rel_h), _p(rel_w), _p(out), _p(_req(lse, F32, "lse")), F, G, heads, hd,
+                                                     _stream(qkv)), "grove_attn_global_relpos_fwd_lse")
+        return out
     fn = lib().grove_attn_global_relpos_fwd_mma if legacy_mma else lib().grove_attn_global_relpos_fwd
     check(fn(_p(qkv), _p(rel_h), _p(rel_w), _p(out), F, G, heads, hd, _stream(qkv)), "grove_attn_global_relpos_fwd")
     return out
@@ -393,7 +398,7 @@ def batch_sum_bf16(x, B):
     return out
 
 
-def attn_relpos_bwd(qkv, qkv_bias_bf16, rel_h, rel_w, att, datt, dqkv, *, F, G, heads, hd, ws=0):
+def attn_relpos_bwd(qkv, qkv_bias_bf16, rel_h, rel_w, att, datt, dqkv, *, F, G, heads, hd, ws=0, lse=None):
     """d(qkv) of the rel-pos attention (ws = 14 windowed on the unpartitioned tensors, ws = 0 global)"""
     for t, n in ((qkv, "qkv"), (rel_h, "rel_pos_h"), (rel_w, "rel_pos_w"), (att, "att"), (datt, "datt"), (dqkv, "dqkv")):
         _req(t, BF16, n)
@@ -401,8 +406,10 @@ def attn_relpos_bwd(qkv, qkv_bias_bf16, rel_h, rel_w, att, datt, dqkv, *, F, G, 
     assert rel_h.shape == (2 * S - 1, hd) and rel_w.shape == (2 * S - 1, hd)
     nbytes = lib().grove_attn_relpos_bwd_workspace_bytes(F, G, heads, hd, ws)
     wsb = torch.empty(nbytes // 4, device=qkv.device, dtype=F32)
-    check(lib().grove_attn_relpos_bwd(_p(qkv), _p(qkv_bias_bf16), _p(rel_h), _p(rel_w), _p(att), _p(datt), _p(dqkv), _p(wsb), F, G, heads, hd, ws,
-                                      _stream(qkv)), "grove_attn_relpos_bwd")
+    if lse is not None:
+        _req(lse, F32, "lse")
+    check(lib().grove_attn_relpos_bwd_lse(_p(qkv), _p(qkv_bias_bf16), _p(rel_h), _p(rel_w), _p(att), _p(datt), _p(dqkv), _p(wsb), _p(lse), F, G, heads,
+                                          hd, ws, _stream(qkv)), "grove_attn_relpos_bwd")
     return dqkv
 
 

@@ -93,6 +93,10 @@ int grove_attn_window_relpos_tc_fwd(const void* qkv, const void* qkv_bias_bf16, 
  * kernel (attention_tc.cu), exact two-phase softmax, scores never leave the SM.  qkv [F,G,G,3,heads,hd], out [F,G,G,heads*hd]. */
 int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
                                  int heads, int hd, grove_stream_t stream);
+/* Same, additionally writing lse[F*G*G, heads] fp32 = log2-domain log-sum-exp of every query row (max + log2 sum, scale and bias
+ * included) — saved by the training forward so that grove_attn_relpos_bwd can skip its own log-sum-exp sweep (lse may be NULL). */
+int grove_attn_global_relpos_fwd_lse(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, float* lse, int F, int G,
+                                     int heads, int hd, grove_stream_t stream);
 /* Same contract on the legacy warp-level tensor path (mma.sync flash kernel, attention.cu) — kept as an independent
  * cross-check for the tests; the modules never call it. */
 int grove_attn_global_relpos_fwd_mma(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
@@ -224,6 +228,11 @@ int grove_batch_sum_bf16(const void* x, float* out, int B, long long n, grove_st
 long long grove_attn_relpos_bwd_workspace_bytes(int F, int G, int heads, int hd, int ws);
 int grove_attn_relpos_bwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, const void* att,
                           const void* datt, void* dqkv, void* workspace, int F, int G, int heads, int hd, int ws, grove_stream_t stream);
+/* Same with the forward kernel's log-sum-exp (grove_attn_global_relpos_fwd_lse; fp32 [F*G*G, heads], may be NULL): global layers on
+ * 32x32 / 64x64 grids then take a single key sweep with the rel-pos terms in registers instead of recomputing the row statistics. */
+int grove_attn_relpos_bwd_lse(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, const void* att,
+                              const void* datt, void* dqkv, void* workspace, const float* lse_fwd, int F, int G, int heads, int hd, int ws,
+                              grove_stream_t stream);
 /* d boxes [B,4] (cxcywh) and d logits [B] of the loss of _compute_loss_components_video (GROVE.py:339-381):
  * cg = upstream * giou_weight / (n_gt + 1e-8) (GIoU and L1 share it, GROVE.py:375), co = upstream * objectness_weight / (n_pred + 1e-8). */
 int grove_box_losses_bwd(const float* boxes, const float* logits, const float* gt, const uint8_t* sel, const float* labels, float cg, float co,

@@ -246,7 +246,7 @@ def _ref_attention(qkv, bias, Rh, Rw, heads, hd, G, ws):
     return o.reshape(Fr, G, G, heads * hd)
 
 
-@pytest.mark.parametrize("G,ws,heads,hd,Fr", [(16, 0, 2, 64, 2), (32, 0, 2, 80, 1), (64, 0, 1, 64, 1), (64, 0, 1, 80, 1), (32, 14, 2, 64, 2),
+@pytest.mark.parametrize("G,ws,heads,hd,Fr", [(16, 0, 2, 64, 2), (32, 0, 2, 80, 1), (32, 0, 3, 64, 2), (64, 0, 1, 64, 1), (64, 0, 2, 80, 1), (32, 14, 2, 64, 2),
                                               (64, 14, 2, 80, 1), (16, 14, 3, 64, 1)])
 def test_attention_relpos_bwd(ops, G, ws, heads, hd, Fr):
     S = ws if ws else G
@@ -267,6 +267,19 @@ def test_attention_relpos_bwd(ops, G, ws, heads, hd, Fr):
         assert e < 2.5e-2, (name, e)
     # mean error is far below the max-norm bound (bf16 rounding of P and dS)
     assert float((dqkv.float() - ref).abs().mean() / ref.abs().mean()) < 8e-3
+    if ws == 0 and G in (32, 64):
+        # training path: attention output and row log-sum-exp from the tcgen05 forward kernel -> single-sweep backward kernels
+        lse = torch.empty(Fr * G * G, heads, device="cuda")
+        att2 = torch.empty_like(att)
+        ops.attn_global(qkv, Rh, Rw, att2, F=Fr, G=G, heads=heads, hd=hd, lse=lse)
+        dq2 = torch.full_like(qkv, float("nan"))
+        ops.attn_relpos_bwd(qkv, None, Rh, Rw, att2, datt, dq2, F=Fr, G=G, heads=heads, hd=hd, ws=0, lse=lse)
+        torch.cuda.synchronize()
+        assert torch.isfinite(dq2.float()).all()
+        for i, name in enumerate("qkv"):
+            e = _relerr(dq2[..., i, :, :].float(), ref[..., i, :, :])
+            assert e < 2.5e-2, ("fwd-lse path", name, e)
+        assert float((dq2.float() - ref).abs().mean() / ref.abs().mean()) < 8e-3
 
 
 # ------------------------------------------------------------------ loss derivative
