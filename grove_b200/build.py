@@ -13,7 +13,7 @@ SOURCES = ["lib.cu", "gemm_tcgen05.cu", "encoder_ops.cu", "attention.cu", "atten
            "backward_ops.cu", "attention_bwd.cu", "decoder_bwd.cu", "preprocess.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-I", os.path.join(ROOT, "include"), "-I", CSRC, "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "-I", os.path.join(ROOT, "include"), "-I", CSRC, "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("GROVE_NVCC_EXTRA", "").split()
 
 
 def _stale(out, deps):

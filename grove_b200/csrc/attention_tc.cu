@@ -55,7 +55,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
   float* stage_f = reinterpret_cast<float*>(smem_al + (sP - s0));
   float* relh_f = reinterpret_cast<float*>(smem_al + (sRelH - s0));
   float* xch_f = reinterpret_cast<float*>(smem_al + (sXch - s0));
-  enum { Q_FULL = 0, TAB_FREE, O_FULL, K_FULL, K_EMPTY = K_FULL + kKStages, V_FULL = K_EMPTY + kKStages, V_EMPTY = V_FULL + kVStages,
+  enum { Q_FULL = 0, TAB_FREE, O_FULL, Q_TMEM, K_FULL, K_EMPTY = K_FULL + kKStages, V_FULL = K_EMPTY + kKStages, V_EMPTY = V_FULL + kVStages,
          S_FULL = V_EMPTY + kVStages, S_EMPTY = S_FULL + 2, P_FULL = S_EMPTY + 2, P_EMPTY = P_FULL + 2, NUM_BARS = P_EMPTY + 2 };
   auto bar = [&](int i) { return bar0 + 8u * i; };
   const uint32_t tmem_slot = bar0 + 8u * NUM_BARS;
@@ -67,7 +67,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
-    mbar_init(bar(Q_FULL), 1); mbar_init(bar(TAB_FREE), 1); mbar_init(bar(O_FULL), 1);
+    mbar_init(bar(Q_FULL), 1); mbar_init(bar(TAB_FREE), 1); mbar_init(bar(O_FULL), 1); mbar_init(bar(Q_TMEM), 4 * SPLIT);
     for (int i = 0; i < kKStages; ++i) { mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1); }
     for (int i = 0; i < kVStages; ++i) { mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
@@ -82,7 +82,8 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS0 = tmem_base, tO = tmem_base + 256, tP0 = tmem_base + 384;   // S0|S1 (2x128), O (<=80), P0|P1 (2x64: bf16 pairs)
+  // S0|S1 (2x128), O (<=80), Q (HD/2 <= 40: bf16 pairs, the A operand of every Q.K^T), P0|P1 (2x64: bf16 pairs)
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 256, tQ = tmem_base + 336, tP0 = tmem_base + 384;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -120,55 +121,57 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) is MN-major
     constexpr uint32_t idesc_ox = umma_idesc_bf16(128, 16) | (1u << 16);  // the 16-wide tail of V -> O columns 64..79
     uint32_t sit = 0, kit = 0, vit = 0;
-    auto issue_s = [&](uint32_t b_smem) {   // S[sit&1] = Q . B^T  (B: [128 rows][64] K-major)
+    // S[sit&1] = Q . B^T  (B: [128 rows][HD] K-major in shared memory).  The two rel-pos tables take Q from shared memory (SS); every
+    // key block takes Q from TENSOR memory (TS): an SS-mode 128x128x16 UMMA reads 8 KB of operands per 64-clk instruction, which is the
+    // whole 128 B/clk shared-memory bandwidth of the SM and made Q.K^T run at half rate next to the TMA writes and the softmax's traffic.
+    auto issue_s = [&](uint32_t b_smem, bool q_tmem) {
       const uint32_t sb = sit & 1u;
-      mbar_wait(bar(S_EMPTY + sb), ((sit >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
+        if (q_tmem) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tS0 + sb * 128, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(b_smem + k * 32), idesc_s, k != 0);
-        if (kX) tc_mma_f16(tS0 + sb * 128, umma_desc_sw32(sQ + 16384), umma_desc_sw32(b_smem + 16384), idesc_s, 1);
+          for (int k = 0; k < 4; ++k) tc_mma_f16_ts(tS0 + sb * 128, tQ + k * 8, umma_desc_sw128(b_smem + k * 32), idesc_s, k != 0);
+          if (kX) tc_mma_f16_ts(tS0 + sb * 128, tQ + 32, umma_desc_sw32(b_smem + 16384), idesc_s, 1);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(tS0 + sb * 128, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(b_smem + k * 32), idesc_s, k != 0);
+          if (kX) tc_mma_f16(tS0 + sb * 128, umma_desc_sw32(sQ + 16384), umma_desc_sw32(b_smem + 16384), idesc_s, 1);
+        }
       }
       __syncwarp();
     };
+    // S buffer `sit & 1` is free for the first two uses; afterwards wait for the softmax warps to have drained it
+    auto s_empty_par = [&]() { return ((sit >> 1) & 1u) ^ 1u; };
     mbar_wait(bar(Q_FULL), 0);
-    tc_fence_after();
-    issue_s(sV);                                       // T_w
-    if (lane == 0) tc_commit(bar(S_FULL + 0));
+    issue_s(sV, false);                                // T_w
+    if (elect_one()) tc_commit(bar(S_FULL + 0));
     __syncwarp();
     ++sit;
-    issue_s(sV + TS);                                  // T_h
-    if (lane == 0) { tc_commit(bar(S_FULL + 1)); tc_commit(bar(TAB_FREE)); }
+    issue_s(sV + TS, false);                           // T_h
+    if (elect_one()) { tc_commit(bar(S_FULL + 1)); tc_commit(bar(TAB_FREE)); }
     __syncwarp();
     ++sit;
-    for (int b = 0; b < NB; ++b, ++kit, ++sit) {       // phase 1
+    mbar_wait(bar(Q_TMEM), 0);                         // the softmax warps have copied Q into tensor memory
+    // one key block: wait for (K landed, S buffer drained) with both polls in flight, then 4-5 UMMAs and two commits
+    auto issue_qk = [&]() {
       const int s = kit % kKStages;
-      mbar_wait(bar(K_FULL + s), (kit / kKStages) & 1u);
-      tc_fence_after();
-      issue_s(sK + s * TS);
-      if (lane == 0) { tc_commit(bar(K_EMPTY + s)); tc_commit(bar(S_FULL + (sit & 1u))); }
-      __syncwarp();
-    }
-    // phase 2: S(b+1) is issued before P(b).V(b) so the softmax of block b+1 overlaps the P.V of block b
-    auto issue_qk2 = [&]() {
-      const int s = kit % kKStages;
-      mbar_wait(bar(K_FULL + s), (kit / kKStages) & 1u);
-      tc_fence_after();
-      issue_s(sK + s * TS);
-      if (lane == 0) { tc_commit(bar(K_EMPTY + s)); tc_commit(bar(S_FULL + (sit & 1u))); }
+      mbar_wait2(bar(K_FULL + s), (kit / kKStages) & 1u, bar(S_EMPTY + (sit & 1u)), s_empty_par());
+      issue_s(sK + s * TS, true);
+      if (elect_one()) { tc_commit(bar(K_EMPTY + s)); tc_commit(bar(S_FULL + (sit & 1u))); }
       __syncwarp();
       ++kit; ++sit;
     };
-    issue_qk2();
+    for (int b = 0; b < NB; ++b) issue_qk();           // phase 1
+    // phase 2: S(b+1) is issued before P(b).V(b) so the softmax of block b+1 overlaps the P.V of block b
+    issue_qk();
     for (int b = 0; b < NB; ++b, ++vit) {
-      if (b + 1 < NB) issue_qk2();
+      if (b + 1 < NB) issue_qk();
       const uint32_t pb = b & 1u;
       const int v = vit % kVStages;
-      mbar_wait(bar(V_FULL + v), (vit / kVStages) & 1u);
-      mbar_wait(bar(P_FULL + pb), (b >> 1) & 1u);
+      mbar_wait2(bar(V_FULL + v), (vit / kVStages) & 1u, bar(P_FULL + pb), (b >> 1) & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t ta = tP0 + pb * 64 + kk * 8;        // P[:, 16 keys] = 8 packed columns of tensor memory
@@ -195,6 +198,32 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
     // staging row with the float4 slots XOR-swizzled by the row (conflict-free 128-bit stores of 32 different rows)
     auto stage_at = [&](int e) { return stage_f[row * 128 + ((((e >> 2) ^ (row & 7)) << 2) | (e & 3))]; };
     uint32_t sit = 0;
+    // ---- Q tile: shared memory (128B-swizzled rows as TMA landed them) -> tensor memory, row = lane, bf16 pairs along the head dim
+    {
+      constexpr int CH = 8 / SPLIT;                      // 16-byte chunks (8 head dims) of the 64-wide part per thread
+      mbar_wait(bar(Q_FULL), 0);
+      uint32_t qr[4 * CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int ch = hs * CH + c;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(qr[4 * c]), "=r"(qr[4 * c + 1]), "=r"(qr[4 * c + 2]), "=r"(qr[4 * c + 3])
+                     : "r"(sQ + row * 128 + ((ch ^ (row & 7)) << 4)));
+      }
+      if constexpr (CH == 4) tmem_st_32x32b_x16(tQ + hs * 16 + tlane, qr);
+      else tmem_st_x8(tQ + hs * 8 + tlane, qr);
+      if (kX && hs == 0) {                               // head dims 64..79: 32-byte rows, SWIZZLE_32B
+        uint32_t qx[8];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(qx[4 * c]), "=r"(qx[4 * c + 1]), "=r"(qx[4 * c + 2]), "=r"(qx[4 * c + 3])
+                       : "r"(sQ + 16384 + row * 32 + ((c ^ ((row >> 2) & 1)) << 4)));
+        tmem_st_x8(tQ + 32 + tlane, qx);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(Q_TMEM));
+    }
     float relw[32];                                      // this thread's kw half (G=64) / the whole grid row (G=32)
     const int kw0 = (G == 64) ? (hs & 1) * 32 : 0;       // chunk c covers kw = (c % 2) * 32 .. + 32 of a 64-wide grid row; SPLIT is even
     // ---- prologue: rel_w -> registers, rel_h -> smem (both x log2 e)
@@ -256,7 +285,8 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
     float lsum = 0.f;
     for (int b = 0; b < NB; ++b, ++sit) {
       const uint32_t sb = sit & 1u, pb = b & 1u;
-      mbar_wait(bar(S_FULL + sb), (sit >> 1) & 1u);
+      // S(b) complete, and P.V of block b-2 has finished reading this P buffer (both polls in flight together)
+      mbar_wait2(bar(S_FULL + sb), (sit >> 1) & 1u, bar(P_EMPTY + pb), ((b >> 1) & 1u) ^ 1u);
       tc_fence_after();
       uint32_t rr[CPT][32];
 #pragma unroll
@@ -265,7 +295,6 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
-      mbar_wait(bar(P_EMPTY + pb), ((b >> 1) & 1u) ^ 1u);   // P.V of block b-2 has finished reading this P buffer
 #pragma unroll
       for (int cc = 0; cc < CPT; ++cc) {
         const int c = SPLIT * cc + hs;

@@ -77,6 +77,17 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
+// One leader lane of a fully converged warp (elect.sync).  tcgen05.mma / tcgen05.commit / TMA are uniform-datapath instructions:
+// issued under `if (lane == 0)` ptxas wraps EVERY one of them in a serialising ELECT ... BRA.U.ANY loop with R2UR moves (~60-100 clk
+// per instruction, measured), which made the single MMA-issuing warp the bottleneck of the attention kernels; under an elect.sync
+// predicate the instruction is issued directly.  The election is deterministic for a given member mask, so the same lane issues
+// the MMAs and the commits that track them.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -99,6 +110,20 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // Wait with a watchdog: a protocol bug must trap (launch error reported to the caller) instead of
 // hanging the GPU.  try_wait suspends in hardware, so the poll loop is cheap.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef GROVE_MBAR_SPIN
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins == 0x10000000u) __trap();
+  }
+#else
   uint32_t done = 0, spins = 0;
   uint64_t t0 = 0;
   while (true) {
@@ -116,6 +141,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       else if (now - t0 > 4000000000ull) __trap();  // 4 s
     }
   }
+#endif
+}
+
+// Wait for TWO barriers with both polls in flight at once.  An mbarrier.try_wait costs ~90 clk even when the phase has already
+// completed; a single MMA-issuing warp that waits for "operand landed" and "accumulator drained" one after the other pays that
+// latency twice per tile, which was the pacing term of the attention kernels (measured with in-kernel clock probes).
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+  uint32_t da, db;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "selp.u32 %1, 1, 0, q;\n\t}"
+      : "=r"(da), "=r"(db)
+      : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b)
+      : "memory");
+  if (!da) mbar_wait(bar_a, par_a);
+  if (!db) mbar_wait(bar_b, par_b);
 }
 
 // ------------------------------------------------------------------ TMA
