@@ -144,7 +144,7 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
       auto load_box = [&](uint32_t dst_main, uint32_t dst_tail, uint32_t b, int col, int wx, int wy, int f) {
         asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_main),
                      "l"(reinterpret_cast<uint64_t>(&tm.qkv)), "r"(b), "r"(col), "r"(wx * kWS), "r"(wy * kWS), "r"(f) : "memory");
@@ -152,21 +152,26 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
           asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_tail),
                        "l"(reinterpret_cast<uint64_t>(&tm.qkv_x)), "r"(b), "r"(col + 64), "r"(wx * kWS), "r"(wy * kWS), "r"(f) : "memory");
       };
-      mbar_expect_tx(bar(TAB_FULL), Cfg::kTabBytes);
-      tma_load_2d(sTab, &tm.tab, bar(TAB_FULL), 0, 0);
-      if (kX) tma_load_2d(sTab + Cfg::kTabMain, &tm.tab_x, bar(TAB_FULL), 64, 0);
+      if (elect_one()) {
+        mbar_expect_tx(bar(TAB_FULL), Cfg::kTabBytes);
+        tma_load_2d(sTab, &tm.tab, bar(TAB_FULL), 0, 0);
+        if (kX) tma_load_2d(sTab + Cfg::kTabMain, &tm.tab_x, bar(TAB_FULL), 64, 0);
+      }
+      __syncwarp();
       uint32_t cnt = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++cnt) {
         int h, wy, wx, f;
         decode(u, h, wy, wx, f);
-        mbar_wait(bar(QK_EMPTY), (cnt & 1u) ^ 1u);
-        mbar_expect_tx(bar(QK_FULL), 2 * Cfg::kTxTile);
-        load_box(sQ, sQ + Cfg::kQMain, bar(QK_FULL), h * HD, wx, wy, f);
-        load_box(sK, sK + Cfg::kKMain, bar(QK_FULL), D + h * HD, wx, wy, f);
         const uint32_t vb = cnt & 1u;
-        mbar_wait(bar(V_EMPTY + vb), ((cnt >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(bar(V_FULL + vb), Cfg::kTxTile);
-        load_box(sV + vb * Cfg::kKBytes, sV + vb * Cfg::kKBytes + Cfg::kKMain, bar(V_FULL + vb), 2 * D + h * HD, wx, wy, f);
+        mbar_wait2(bar(QK_EMPTY), (cnt & 1u) ^ 1u, bar(V_EMPTY + vb), ((cnt >> 1) & 1u) ^ 1u);
+        if (elect_one()) {     // uniform-datapath instructions: see elect_one() in common.cuh
+          mbar_expect_tx(bar(QK_FULL), 2 * Cfg::kTxTile);
+          load_box(sQ, sQ + Cfg::kQMain, bar(QK_FULL), h * HD, wx, wy, f);
+          load_box(sK, sK + Cfg::kKMain, bar(QK_FULL), D + h * HD, wx, wy, f);
+          mbar_expect_tx(bar(V_FULL + vb), Cfg::kTxTile);
+          load_box(sV + vb * Cfg::kKBytes, sV + vb * Cfg::kKBytes + Cfg::kKMain, bar(V_FULL + vb), 2 * D + h * HD, wx, wy, f);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -183,11 +188,10 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++cnt) {
       const uint32_t vb = cnt & 1u;
       const uint32_t vbase = sV + vb * Cfg::kKBytes;
-      mbar_wait(bar(QK_FULL), cnt & 1u);
-      mbar_wait(bar(K_FIX), cnt & 1u);
+      mbar_wait2(bar(QK_FULL), cnt & 1u, bar(K_FIX), cnt & 1u);
       if (cnt > 0) mbar_wait(bar(O_READ), 1u);            // previous unit's second epilogue has drained the T/O columns
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         qk_mma(tTO, sQ, sQ + Cfg::kQMain, sTab, sTab + Cfg::kTabMain, idesc_t);
         tc_commit(bar(T_FULL));
         qk_mma(tS0, sQ, sQ + Cfg::kQMain, sK, sK + Cfg::kKMain, idesc_s);
@@ -196,7 +200,7 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
       __syncwarp();
       mbar_wait(bar(T_READ), 0u);                           // tile 0's T is in registers
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         qk_mma(tTO, sQ + 16384, sQ + Cfg::kQMain + 4096, sTab, sTab + Cfg::kTabMain, idesc_t);
         tc_commit(bar(T_FULL));
         qk_mma(tS0 + kWK, sQ + 16384, sQ + Cfg::kQMain + 4096, sK, sK + Cfg::kKMain, idesc_s);
@@ -205,14 +209,13 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
       }
       __syncwarp();
       mbar_wait(bar(T_READ), 1u);
-      mbar_wait(bar(V_FULL + vb), (cnt >> 1) & 1u);
-      mbar_wait(bar(V_FIX + vb), (cnt >> 1) & 1u);
+      mbar_wait2(bar(V_FULL + vb), (cnt >> 1) & 1u, bar(V_FIX + vb), (cnt >> 1) & 1u);
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
         mbar_wait(bar(P_FULL + t), cnt & 1u);
         if (t == 1) mbar_wait(bar(O_READ), 0u);             // tile 0's O has been read
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kWK / 16; ++kk) {
             const uint32_t ta = tS0 + t * kWK + kk * 8;

@@ -108,8 +108,8 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread per CTA) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the schedule, one elected lane issues) =====================
+    {
       uint32_t it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int sp = tile / tiles_mn, tmn = tile % tiles_mn;
@@ -133,6 +133,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const int brow = n_blk * BN + (int)cta_rank * Cfg::kBRows;
+          if (!elect_one()) continue;     // uniform-datapath instructions below: see elect_one() in common.cuh
           if (CTAS == 1) {
             mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
             if (p.conv != 1) {
@@ -199,7 +200,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
           const uint32_t ph = (it / Cfg::kStages) & 1u;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sa = smem_base + s * Cfg::kStageBytes;
             const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
