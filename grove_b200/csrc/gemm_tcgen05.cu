@@ -9,6 +9,7 @@
 //
 // out[m, n] = resid[m (mod resid_mod), n] + gate * act( sum_k A[m, k] * W[n, k] + bias[n] )
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -60,7 +61,12 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BN;           // two accumulator stages (power of two: 256 or 512)
 };
 
-template <int BN, int CTAS>
+// EPI selects the epilogue: 0 = general (every fused option, run-time flags); 1 / 2 = bf16 output with bias and no / GELU
+// activation and nothing else (the qkv and fc1 GEMMs of every encoder block) as straight-line code: with K = 768 these tiles
+// are epilogue-bound (the MMA warp was measured waiting ~4k clk per tile for a drained accumulator), and the general epilogue's
+// run-time branches, 5k-instruction body (instruction-cache misses) and fp32 staging cost 13.7k clk per tile against an 8.5k clk
+// main loop.
+template <int BN, int CTAS, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b) {
   using Cfg = GemmCfg<BN, CTAS>;
@@ -234,6 +240,148 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     const uint32_t stg = epi_base + (warp - 2) * (32 * Cfg::kStageRowF * 4);
     constexpr int kPasses = BN / 2 / 32;
     uint32_t tile_it = 0;
+    if constexpr (EPI == 1 || EPI == 2) {
+      // ---- bf16 output, bias, optional GELU.  Per warp and pass: one tcgen05.ld of 32 rows x 32 columns (lane = row), bias +
+      // activation in registers, pack to bf16, stage 32 rows x 64 B through an XOR-swizzled (conflict-free both ways) private
+      // buffer, then 8 rows x 64 B per store instruction.  The accumulator is released right after the last tcgen05.ld.
+      const uint32_t bias_s = stg + 2048;                  // this warp's 128 bias values (fp32), 512 B behind the 2 KB staging
+      __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
+        const int m_blk = (tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
+        const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+        const int row_base = m_blk * BM + quad * 32;
+        const int colw = n_blk * BN + half * (BN / 2);     // first output column of this warp
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + colw) + lane);
+        __syncwarp();                                      // the previous tile's bias reads are done
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(bias_s + lane * 16), "f"(bv.x), "f"(bv.y), "f"(bv.z), "f"(bv.w) : "memory");
+        __syncwarp();
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ps = 0; ps < kPasses; ++ps) {
+          uint32_t r0[32];
+          tmem_ld_32x32b_x32(tmem_base + acc * BN + half * (BN / 2) + ps * 32 + ((uint32_t)(quad * 32) << 16), r0);
+          tmem_ld_wait();
+          if (ps == kPasses - 1) {                         // accumulator drained: the MMA warp may start the tile after next
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CTAS == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+              else mbar_arrive(tempty_bar(acc));
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_s + (ps * 32 + j) * 4));
+            float v0 = __uint_as_float(r0[j]) + b4.x, v1 = __uint_as_float(r0[j + 1]) + b4.y;
+            float v2 = __uint_as_float(r0[j + 2]) + b4.z, v3 = __uint_as_float(r0[j + 3]) + b4.w;
+            if (EPI == 2) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3); }
+            pk[j >> 1] = pack_bf16(v0, v1);
+            pk[(j >> 1) + 1] = pack_bf16(v2, v3);
+          }
+          // lane = row: four 16-byte chunks (8 columns each), chunk c stored at position c ^ ((row >> 1) & 3) of the 64-byte row
+          const uint32_t wrow = stg + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + ((c ^ sw) << 4)), "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]),
+                         "r"(pk[4 * c + 3]) : "memory");
+          __syncwarp();
+          const int col0 = colw + ps * 32 + (lane & 3) * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = 8 * i + (lane >> 2);
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                         : "r"(stg + rl * 64 + (((lane & 3) ^ ((rl >> 1) & 3)) << 4)));
+            if (row_base + rl < p.M) *reinterpret_cast<uint4*>(outp + (size_t)(row_base + rl) * p.N + col0) = o;
+          }
+          __syncwarp();                                    // staging is rewritten by the next pass
+        }
+      }
+    } else if constexpr (EPI == 3) {
+      // ---- fp32 output = resid + gate * act(acc + bias) (+ bf16 copy): the residual-stream GEMMs (proj, fc2, Conv3d adapter).
+      // These tiles move 256 KB of fp32 per CTA through 8 warps; the residual rows are fetched one pass ahead (and across the
+      // tile boundary) so their latency overlaps the previous pass.  (Measured: an extra L2 prefetch a tile ahead and
+      // L1::no_allocate loads change nothing -- the path sits at ~3.3 TB/s of combined traffic per kernel.)
+      const float relu_floor = p.act == 2 ? 0.f : -INFINITY;
+      float* const outp = reinterpret_cast<float*>(p.out);
+      const int c = (lane & 7) * 4;                        // lane -> (row 4i + lane/8, 4 columns at c)
+      auto res_ptr = [&](int tile_, int ps_, int i_) {
+        const int m_blk_ = (tile_ / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk_ = tile_ % p.num_n_blocks;
+        const int row_ = m_blk_ * BM + quad * 32 + 4 * i_ + (lane >> 3);
+        return p.resid + (size_t)min(row_, p.M - 1) * p.N + n_blk_ * BN + half * (BN / 2) + ps_ * 32 + c;
+      };
+      float4 res[8];
+      if (tile0 < num_tiles) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res[i] = *reinterpret_cast<const float4*>(res_ptr(tile0, 0, i));
+      }
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
+        const int m_blk = (tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
+        const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+        const int row_base = m_blk * BM + quad * 32;
+        const int colw = n_blk * BN + half * (BN / 2);
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ps = 0; ps < kPasses; ++ps) {
+          const int col0 = colw + ps * 32 + c;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0));
+          {
+            uint32_t r0[32];
+            tmem_ld_32x32b_x32(tmem_base + acc * BN + half * (BN / 2) + ps * 32 + ((uint32_t)(quad * 32) << 16), r0);
+            tmem_ld_wait();
+            if (ps == kPasses - 1) {                       // accumulator drained
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CTAS == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+                else mbar_arrive(tempty_bar(acc));
+              }
+            }
+            const uint32_t wrow = stg + lane * (Cfg::kStageRowF * 4);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + j * 4), "r"(r0[j]), "r"(r0[j + 1]), "r"(r0[j + 2]), "r"(r0[j + 3]) : "memory");
+          }
+          __syncwarp();
+          // next pass's residual rows (next tile's first pass after the last one) go in flight before this pass is consumed
+          float4 nres[8];
+          const bool last = ps == kPasses - 1;
+          const int ntile = last ? tile + tile_step : tile;
+          const bool more = ntile < num_tiles;
+          if (more) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) nres[i] = *reinterpret_cast<const float4*>(res_ptr(ntile, last ? 0 : ps + 1, i));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + (lane >> 3);
+            const int row = row_base + rl;
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stg + (rl * Cfg::kStageRowF + c) * 4));
+            v.x = fmaxf(v.x + bias4.x, relu_floor); v.y = fmaxf(v.y + bias4.y, relu_floor);
+            v.z = fmaxf(v.z + bias4.z, relu_floor); v.w = fmaxf(v.w + bias4.w, relu_floor);
+            v.x = fmaf(v.x, gate, res[i].x); v.y = fmaf(v.y, gate, res[i].y); v.z = fmaf(v.z, gate, res[i].z); v.w = fmaf(v.w, gate, res[i].w);
+            if (row < p.M) {
+              const size_t o = (size_t)row * p.N + col0;
+              *reinterpret_cast<float4*>(outp + o) = v;
+              if (p.out2) *reinterpret_cast<uint2*>(p.out2 + o) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            }
+          }
+          if (more) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = nres[i];
+          }
+          __syncwarp();                                    // staging is rewritten by the next pass
+        }
+      }
+    } else
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
       const int sp = tile / tiles_mn, tmn = tile % tiles_mn;
       const int m_blk = (tmn / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tmn % p.num_n_blocks;
@@ -455,12 +603,12 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, int EPI = 0>
 static int launch_gemm(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb, int max_ctas, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
     attr_set = true;
   }
@@ -479,11 +627,17 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& ta, const CUtenso
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS>, p, ta, tb);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS, EPI>, p, ta, tb);
   grove_count_launch();
   if (e != cudaSuccess) { grove_set_error("gemm launch failed: %s", cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
+}
+
+static bool generic_epilogue_only() {   // GROVE_GEMM_GENERIC_EPI=1: route everything through the general epilogue (A/B measurements)
+  static int v = -1;
+  if (v < 0) v = getenv("GROVE_GEMM_GENERIC_EPI") != nullptr;
+  return v != 0;
 }
 
 // tile configuration: CTA pairs (256 x 256 tiles) whenever the problem has them, else single-CTA 128 x {256,128} tiles
@@ -511,6 +665,13 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
     if ((rc = make_tmap_bf16(&tb, W, 2, db, bb))) return rc;
   }
   (void)conv;
+  // straight-line epilogues for the two hot bf16-output forms (bias, optional GELU, nothing else)
+  const bool plain_bf16 = !p.out_f32 && !p.resid && !p.gate_alpha && !p.out2 && !p.dact_pre && p.splits == 1 && p.conv != 2 && (p.act == 0 || p.act == 1) &&
+                          !generic_epilogue_only();
+  if (ctas == 2 && plain_bf16) return p.act == 1 ? launch_gemm<256, 2, 2>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 1>(p, ta, tb, max_ctas, st);
+  const bool resid_f32 = p.out_f32 && p.resid && p.resid_mod == 0 && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2_pre &&
+                         !generic_epilogue_only();
+  if (ctas == 2 && resid_f32) return launch_gemm<256, 2, 3>(p, ta, tb, max_ctas, st);
   if (ctas == 2) return launch_gemm<256, 2>(p, ta, tb, max_ctas, st);
   return BN == 256 ? launch_gemm<256, 1>(p, ta, tb, max_ctas, st) : launch_gemm<128, 1>(p, ta, tb, max_ctas, st);
 }
