@@ -5,13 +5,12 @@
 // needs only one max / one sum exchange per tile and every SM sub-partition has two softmax warps to hide latency.
 //   prologue  T_w = Q.Rw^T and T_h = Q.Rh^T as two UMMAs (128x128x64) -> each thread gathers its own
 //             rel_w[kw] = T_w[qw-kw+G-1] into registers and rel_h[kh] into shared memory (pre-scaled by log2 e)
-//   phase 1   S = Q.K^T per 128-key block (UMMA 128x128x64, double-buffered in TMEM) -> exact row max of
-//             scale*S + rel_h + rel_w                                (no exponentials, no P.V)
-//   phase 2   S again -> p = exp2(scale*S + bias - max) -> bf16 P written straight into the 128B-swizzled K-major
-//             smem layout UMMA expects -> O += P.V (UMMA 128x64x128, V consumed MN-major exactly as TMA lands it)
-// Knowing the exact max up front removes the online-softmax rescale of O (no TMEM round trip, no data-dependent
-// control flow); it costs one extra Q.K^T, which runs on an otherwise idle tensor pipe (the kernel is bound by the
-// 16 exp2/clk MUFU rate, not by MMA).  Scores never leave the SM.
+//   main loop  one pass over the keys, 128 per block: S = Q.K^T (UMMA 128x128x64, Q read from tensor memory, S double-buffered in
+//             TMEM) -> block max -> p = exp2(scale*S + bias - m) -> bf16 P written with tcgen05.st into tensor memory -> O += P.V
+//             (TS-mode UMMA 128x64x128, V consumed MN-major exactly as TMA lands it).  m is a LAZY running maximum: it is raised
+//             (and the 32 rows x HD accumulator slice of that warp rescaled in TMEM) only when a row's block max exceeds it by
+//             more than 8 (log2 domain), so p <= 256 and the correction runs a handful of times per tile, not once per block.
+// Scores never leave the SM.  (Round-1 history: a two-phase exact-max variant spent 29 % of its time recomputing Q.K^T.)
 #include <cuda.h>
 
 #include <cstdlib>
@@ -21,6 +20,28 @@
 #include "tmem_ldst.cuh"
 
 namespace grove {
+
+// In-kernel timeline probes (compile with -DGROVE_ATT_PROBE; read with grove_att_probe_read, see scratch/att_probe.py): clock64 of
+// one CTA's MMA warp and softmax warps at every hand-off.  Compiled out by default.
+#ifdef GROVE_ATT_PROBE
+__device__ long long g_att_probe[8192];
+#define PROBE(slot) do { if (probe_on) g_att_probe[(slot)] = clock64(); } while (0)
+#else
+#define PROBE(slot) do { } while (0)
+#endif
+
+// 2^x for x <= 0 on the FMA pipe (Cody-Waite split with the 1.5 * 2^23 rounding constant, degree-3 minimax of 2^f on [-0.5, 0.5],
+// exponent patched in with an integer add): relative error 2.8e-4, well inside the bf16 rounding of P.  The softmax is bound by
+// the 16 ex2/clk/SM MUFU rate, so one exponential in four is computed here instead (the FlashAttention-4 trick).
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.0565415754f, 0.242068237f);
+  p = fmaf(p, f, 0.692983806f);
+  p = fmaf(p, f, 0.999953968f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 
 // warp 0 TMA, warp 1 MMA, then 4 * SPLIT softmax warps: SPLIT threads per query row (= TMEM lane), each owning 128 / SPLIT keys of a block
 template <int SPLIT> constexpr int att_threads() { return 64 + 128 * SPLIT; }
@@ -49,8 +70,8 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
   const uint32_t sV = sK + kKStages * TS;         // 2 V tiles; during the prologue: Rw | Rh tables
   const uint32_t sP = sV + kVStages * TS;      // 2 x 32 KB P buffers (two 64-key slabs each); prologue: fp32 staging [128][128]
   const uint32_t sRelH = sP + 65536;              // [G][128] fp32
-  const uint32_t sXch = sRelH + G * 128 * 4;      // 2 x [SPLIT][128] fp32: max and sum exchange between the threads of a row
-  const uint32_t bar0 = sXch + 2 * SPLIT * 128 * 4;
+  const uint32_t sXch = sRelH + G * 128 * 4;      // 3 x [SPLIT][128] fp32: block max (double-buffered) and final sum exchange between the threads of a row
+  const uint32_t bar0 = sXch + 3 * SPLIT * 128 * 4;
   uint8_t* smem_al = smem_raw + (s0 - smem_u32(smem_raw));
   float* stage_f = reinterpret_cast<float*>(smem_al + (sP - s0));
   float* relh_f = reinterpret_cast<float*>(smem_al + (sRelH - s0));
@@ -62,6 +83,9 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, f = blockIdx.z;
+#ifdef GROVE_ATT_PROBE
+  const bool probe_on = blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z == 0 && lane == 0;
+#endif
   const int D = heads * HD;
   const int tok0 = f * N;                // first token row of this frame in the [F*N, 3D] qkv matrix
 
@@ -97,19 +121,13 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       load_tile(sV, &tmap_rw, &tm.rw_x, bar(Q_FULL), 0, 0);          // Rw table -> first V slot (rows >= 2G-1 zero-filled)
       load_tile(sV + TS, &tmap_rh, &tm.rh_x, bar(Q_FULL), 0, 0);     // Rh table -> second V slot
       uint32_t kit = 0, vit = 0;
-      for (int b = 0; b < NB; ++b, ++kit) {                    // phase 1: K only
-        const int s = kit % kKStages;
-        mbar_wait(bar(K_EMPTY + s), ((kit / kKStages) & 1u) ^ 1u);
-        mbar_expect_tx(bar(K_FULL + s), TS);
-        load_tile(sK + s * TS, &tmap_qkv, &tm.qkv_x, bar(K_FULL + s), D + h * HD, tok0 + b * 128);
-      }
-      mbar_wait(bar(TAB_FREE), 0);                             // prologue MMAs have finished reading the tables
-      for (int b = 0; b < NB; ++b, ++kit, ++vit) {             // phase 2: K and V
+      for (int b = 0; b < NB; ++b, ++kit, ++vit) {             // K and V of every 128-key block
         const int s = kit % kKStages;
         mbar_wait(bar(K_EMPTY + s), ((kit / kKStages) & 1u) ^ 1u);
         mbar_expect_tx(bar(K_FULL + s), TS);
         load_tile(sK + s * TS, &tmap_qkv, &tm.qkv_x, bar(K_FULL + s), D + h * HD, tok0 + b * 128);
         const int v = vit % kVStages;
+        if (b == 0) mbar_wait(bar(TAB_FREE), 0);               // the prologue MMAs have finished reading the tables (they sit in the V slots)
         mbar_wait(bar(V_EMPTY + v), ((vit / kVStages) & 1u) ^ 1u);
         mbar_expect_tx(bar(V_FULL + v), TS);
         load_tile(sV + v * TS, &tmap_qkv, &tm.qkv_x, bar(V_FULL + v), 2 * D + h * HD, tok0 + b * 128);
@@ -126,7 +144,9 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
     // whole 128 B/clk shared-memory bandwidth of the SM and made Q.K^T run at half rate next to the TMA writes and the softmax's traffic.
     auto issue_s = [&](uint32_t b_smem, bool q_tmem) {
       const uint32_t sb = sit & 1u;
+#ifndef GROVE_ATT_NOFENCE
       tc_fence_after();
+#endif
       if (elect_one()) {
         if (q_tmem) {
 #pragma unroll
@@ -156,21 +176,32 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
     // one key block: wait for (K landed, S buffer drained) with both polls in flight, then 4-5 UMMAs and two commits
     auto issue_qk = [&]() {
       const int s = kit % kKStages;
+      PROBE(1000 + 3 * kit);
       mbar_wait2(bar(K_FULL + s), (kit / kKStages) & 1u, bar(S_EMPTY + (sit & 1u)), s_empty_par());
+      PROBE(1001 + 3 * kit);
+#ifdef GROVE_ATT_QSS
+      issue_s(sK + s * TS, false);
+#else
       issue_s(sK + s * TS, true);
-      if (elect_one()) { tc_commit(bar(K_EMPTY + s)); tc_commit(bar(S_FULL + (sit & 1u))); }
+#endif
+      PROBE(4000 + 3 * kit);
+      if (elect_one()) { tc_commit(bar(K_EMPTY + s)); PROBE(4001 + 3 * kit); tc_commit(bar(S_FULL + (sit & 1u))); PROBE(4002 + 3 * kit); }
       __syncwarp();
+      PROBE(1002 + 3 * kit);
       ++kit; ++sit;
     };
-    for (int b = 0; b < NB; ++b) issue_qk();           // phase 1
-    // phase 2: S(b+1) is issued before P(b).V(b) so the softmax of block b+1 overlaps the P.V of block b
+    // S(b+1) is issued before P(b).V(b) so the softmax of block b+1 overlaps the P.V of block b
     issue_qk();
     for (int b = 0; b < NB; ++b, ++vit) {
       if (b + 1 < NB) issue_qk();
       const uint32_t pb = b & 1u;
       const int v = vit % kVStages;
+      PROBE(1300 + 3 * b);
       mbar_wait2(bar(V_FULL + v), (vit / kVStages) & 1u, bar(P_FULL + pb), (b >> 1) & 1u);
+      PROBE(1301 + 3 * b);
+#ifndef GROVE_ATT_NOFENCE
       tc_fence_after();
+#endif
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
@@ -184,6 +215,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
         if (b == NB - 1) tc_commit(bar(O_FULL));
       }
       __syncwarp();
+      PROBE(1302 + 3 * b);
     }
   } else {
     // ===================== softmax warps: two threads per query row =====================
@@ -255,37 +287,13 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       softmax_sync();                                    // staging is rewritten by the next table / rel_h complete
     }
     const float c_scale = (HD == 64 ? 0.125f : 0.11180339887498949f) * kL2e;   // hd^-0.5 * log2(e)
-    // ---- phase 1: exact row max
-    float m = -INFINITY;
-    for (int b = 0; b < NB; ++b, ++sit) {
-      const uint32_t sb = sit & 1u;
-      mbar_wait(bar(S_FULL + sb), (sit >> 1) & 1u);
-      tc_fence_after();
-      uint32_t rr[CPT][32];
-#pragma unroll
-      for (int cc = 0; cc < CPT; ++cc) tmem_ld_32x32b_x32(tS0 + sb * 128 + (SPLIT * cc + hs) * 32 + tlane, rr[cc]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));     // S is in registers: the MMA warp may overwrite this buffer
-#pragma unroll
-      for (int cc = 0; cc < CPT; ++cc) {
-        const int kh = (b * 128 + (SPLIT * cc + hs) * 32) / G;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(rr[cc][j]), c_scale, relw[j]));
-        m = fmaxf(m, mx + relh_f[kh * 128 + row]);
-      }
-    }
-    xch_f[hs * 128 + row] = m;
-    softmax_sync();
-#pragma unroll
-    for (int o = 1; o < SPLIT; ++o) m = fmaxf(m, xch_f[((hs + o) % SPLIT) * 128 + row]);
-    // ---- phase 2: probabilities and P.V
-    float lsum = 0.f;
+    // ---- main loop: lazy running max, probabilities, P.V
+    auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(2 + quad), "n"(32 * SPLIT) : "memory"); };   // the SPLIT warps that share 32 rows
+    float m = -INFINITY, lsum = 0.f;
     for (int b = 0; b < NB; ++b, ++sit) {
       const uint32_t sb = sit & 1u, pb = b & 1u;
       // S(b) complete, and P.V of block b-2 has finished reading this P buffer (both polls in flight together)
+      PROBE(2100 + (warp - 2) * 400 + 4 * b);
       mbar_wait2(bar(S_FULL + sb), (sit >> 1) & 1u, bar(P_EMPTY + pb), ((b >> 1) & 1u) ^ 1u);
       tc_fence_after();
       uint32_t rr[CPT][32];
@@ -294,7 +302,60 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
+      if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));     // S is in registers: the MMA warp may overwrite this buffer
+      PROBE(2101 + (warp - 2) * 400 + 4 * b);
+      // block maximum of scale*S + rel_h + rel_w over this thread's keys, then over the SPLIT threads of the row
+      float mb = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < CPT; ++cc) {
+        const int kh = (b * 128 + (SPLIT * cc + hs) * 32) / G;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          mx0 = fmaxf(mx0, fmaf(__uint_as_float(rr[cc][j]), c_scale, relw[j]));
+          mx1 = fmaxf(mx1, fmaf(__uint_as_float(rr[cc][j + 1]), c_scale, relw[j + 1]));
+        }
+        mb = fmaxf(mb, fmaxf(mx0, mx1) + relh_f[kh * 128 + row]);
+      }
+      float* xb = xch_f + (b & 1) * SPLIT * 128;         // double-buffered: the write of block b+2 is behind the barrier of block b+1
+      xb[hs * 128 + row] = mb;
+      quad_sync();
+#pragma unroll
+      for (int o = 1; o < SPLIT; ++o) mb = fmaxf(mb, xb[((hs + o) % SPLIT) * 128 + row]);
+      // lazy rescale: raise m only when some row of this warp outgrew it by more than 2^8 (always on the first block).  Every
+      // thread of a row sees the same mb and m, so the SPLIT warps of the quad take this branch together.
+      const bool grow = mb > m + 8.0f;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mb : m;
+        float fac;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(fac) : "f"(m - m_new));   // 1 for rows that keep m, 0 on the first block
+        if (b > 0) {
+          // every P.V issued so far (the last one is block b-1; P.V of block b waits for our P_FULL arrive) has retired
+          mbar_wait(bar(P_EMPTY + (pb ^ 1u)), ((b - 1) >> 1) & 1u);
+          tc_fence_after();
+          constexpr int DPT = 64 / SPLIT;                // accumulator columns of this thread
+          uint32_t o[DPT];
+          if constexpr (DPT == 32) tmem_ld_32x32b_x32(tO + hs * DPT + tlane, o);
+          else tmem_ld_x16(tO + hs * DPT + tlane, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < DPT; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * fac);
+          if constexpr (DPT == 32) tmem_st_x32(tO + hs * DPT + tlane, o);
+          else tmem_st_32x32b_x16(tO + hs * DPT + tlane, o);
+          if (kX && hs < 2) {
+            uint32_t ox[8];
+            tmem_ld_32x32b_x8(tO + 64 + hs * 8 + tlane, ox);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ox[j] = __float_as_uint(__uint_as_float(ox[j]) * fac);
+            tmem_st_x8(tO + 64 + hs * 8 + tlane, ox);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        lsum *= fac;
+        m = m_new;
+      }
 #pragma unroll
       for (int cc = 0; cc < CPT; ++cc) {
         const int c = SPLIT * cc + hs;
@@ -307,6 +368,10 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
           const float e0 = fmaf(__uint_as_float(rr[cc][j]), c_scale, relw[j]) + off;
           const float e1 = fmaf(__uint_as_float(rr[cc][j + 1]), c_scale, relw[j + 1]) + off;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
+#ifndef GROVE_ATT_NOPOLY
+          if (j & 2) p1 = ex2_fma(e1);
+          else
+#endif
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
           lsum += p0 + p1;
           pk[j >> 1] = pack_bf16(p0, p1);
@@ -314,16 +379,18 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
         // keys [c*32, c*32+32) of the block -> 16 packed bf16x2 columns of the P buffer in tensor memory (the A operand of P.V)
         tmem_st_32x32b_x16(tP0 + pb * 64 + c * 16 + tlane, pk);
       }
+      PROBE(2102 + (warp - 2) * 400 + 4 * b);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(P_FULL + pb));
+      PROBE(2103 + (warp - 2) * 400 + 4 * b);
     }
     // ---- epilogue: O / l -> bf16 -> global (each thread of a row stores 64 / SPLIT of the first 64 head dims)
-    xch_f[SPLIT * 128 + hs * 128 + row] = lsum;
+    xch_f[2 * SPLIT * 128 + hs * 128 + row] = lsum;
     softmax_sync();
 #pragma unroll
-    for (int o = 1; o < SPLIT; ++o) lsum += xch_f[SPLIT * 128 + ((hs + o) % SPLIT) * 128 + row];
+    for (int o = 1; o < SPLIT; ++o) lsum += xch_f[2 * SPLIT * 128 + ((hs + o) % SPLIT) * 128 + row];
     const float inv = 1.f / lsum;
     if (lse_out != nullptr && hs == 0) lse_out[((size_t)tok0 + q) * heads + h] = m + log2f(lsum);   // log2 domain, for the backward pass
     mbar_wait(bar(O_FULL), 0);
@@ -357,7 +424,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
 
 template <int G, int HD>
 constexpr int att_tc_smem() {
-  return (1 + k_stages<HD>() + kVStages) * (16384 + (HD > 64 ? 4096 : 0)) + 65536 + G * 128 * 4 + 4096 /*xch*/ + 1024 /*align*/ + 512 /*barriers*/;
+  return (1 + k_stages<HD>() + kVStages) * (16384 + (HD > 64 ? 4096 : 0)) + 65536 + G * 128 * 4 + 6144 /*xch*/ + 1024 /*align*/ + 512 /*barriers*/;
 }
 
 int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows);
@@ -403,6 +470,13 @@ static int launch_att_tc_split(const void* qkv, const void* rh, const void* rw, 
 
 extern "C" int grove_attn_global_relpos_fwd_lse(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, float* lse, int F, int G,
                                                 int heads, int hd, cudaStream_t stream);
+
+#ifdef GROVE_ATT_PROBE
+extern "C" int grove_att_probe_read(long long* host, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host, g_att_probe, sizeof(long long) * n) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G, int heads,
                                             int hd, cudaStream_t stream) {

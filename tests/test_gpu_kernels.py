@@ -137,6 +137,37 @@ def test_global_attention(ops, G, Fr, heads, legacy, hd):
     assert float((out.float() - ref).abs().mean()) < 2e-3
 
 
+@pytest.mark.parametrize("hd,G", [(64, 64), (80, 64), (64, 32)])
+def test_global_attention_growing_scores(ops, hd, G):
+    """Keys whose norm grows along the sequence: the running row maximum of the single-pass softmax rises by far more than its lazy
+    rescale threshold (2^8) several times per query tile, so the in-TMEM accumulator correction is exercised; also checks the
+    log-sum-exp the backward pass consumes."""
+    Fr, heads = 1, 2
+    N = G * G
+    qkv = _rand((Fr, G, G, 3, heads, hd), 27, dtype=torch.bfloat16).float()
+    ramp = torch.linspace(0.25, 9.0, N, device="cuda").view(1, G, G, 1, 1)
+    qkv[:, :, :, 1] *= ramp                                  # logits' spread grows ~36x from the first to the last key block
+    qkv[:, :, :, 0] *= 1.5
+    qkv = qkv.to(torch.bfloat16)
+    rh, rw = _rand((2 * G - 1, hd), 28, 0.1, dtype=torch.bfloat16), _rand((2 * G - 1, hd), 29, 0.1, dtype=torch.bfloat16)
+    out = torch.full((Fr, G, G, heads * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((Fr * N, heads), float("nan"), device="cuda")
+    ops.attn_global(qkv, rh, rw, out, F=Fr, G=G, heads=heads, hd=hd, lse=lse)
+    torch.cuda.synchronize()
+    ref = _ref_attention(qkv, rh, rw, Fr, G, heads, hd)
+    assert float((out.float() - ref).abs().max()) < 3e-2
+    assert float((out.float() - ref).abs().mean()) < 2e-3
+    # log2-domain log-sum-exp of the biased scores
+    q, k, _ = qkv.float().reshape(Fr, N, 3, heads, hd).permute(2, 0, 3, 1, 4).reshape(3, Fr * heads, N, hd).unbind(0)
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    Rh, Rw = og.rel_pos_table(G, rh.float()), og.rel_pos_table(G, rw.float())
+    rq = q.reshape(Fr * heads, G, G, hd)
+    attn = (attn.view(Fr * heads, G, G, G, G) + torch.einsum("bhwc,hkc->bhwk", rq, Rh)[..., :, None]
+            + torch.einsum("bhwc,wkc->bhwk", rq, Rw)[..., None, :]).view(Fr * heads, N, N)
+    ref_lse = (torch.logsumexp(attn, -1) / math.log(2.0)).view(Fr, heads, N).permute(0, 2, 1).reshape(Fr * N, heads)
+    assert float((lse - ref_lse).abs().max()) < 5e-2
+
+
 @pytest.mark.parametrize("tc", [True, False])
 @pytest.mark.parametrize("hd", [64, 80])
 @pytest.mark.parametrize("G,Fr,heads", [(64, 2, 2), (32, 1, 3), (28, 1, 1), (64, 3, 16)])
