@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="grove_b200", choices=["grove_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graphs", action="store_true", help="replay the encoder's CUDA graph instead of launching kernel by kernel")
     ap.add_argument("--vit", default="vit_b", choices=["vit_b", "vit_l", "vit_h"], help="non-default workloads are for profiling only")
     ap.add_argument("--videos", type=int, default=1, help="videos per GPU per step (BASELINE configs[2] = vit_h with 2)")
     args = ap.parse_args()
@@ -234,6 +235,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from grove_b200 import ops
     gb, sd, cfg = build_model(dev)
+    gb.grounding_encoder.image_encoder.enable_cuda_graphs(args.graphs)   # opt-in: measured 3 % SLOWER than eager launches
     host_sets = [tuple(t.pin_memory() for t in s) for s in synth_inputs(4, 100 + 10 * rank)]
     dev_sets = [tuple(t.to(dev) for t in s) for s in host_sets]
 
@@ -249,6 +251,32 @@ def main():
         b = torch.cat([x for v in boxes for x in v]).float()
         l = torch.cat([x for v in logits for x in v]).float()
         return torch.cat([b, l[:, None]], 1).cpu()      # device -> host read of the step's result (boxes + objectness)
+
+    def loop_e2e(first, n):
+        # the serving loop of the public API: pinned host batches in, packed host results out, uploads / read-backs overlapped
+        outs = 0
+        for r in gb.ground_host_stream(host_sets[(first + i) % len(host_sets)] for i in range(n)):
+            outs += r.shape[0]
+        assert outs == n * FRAMES * VIDEOS * PHRASES
+
+    def timed_loop(loop, steps, warmup):
+        loop(0, warmup)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop(warmup, steps)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
 
     def timed(fn, steps, warmup):
         for i in range(warmup):
@@ -278,7 +306,8 @@ def main():
         sampler.start()
     ms, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    ms_e2e_sync, _ = timed(step_e2e, args.steps, max(args.warmup, 3))       # one blocking call per step (no overlap)
+    ms_e2e = timed_loop(loop_e2e, args.steps, max(args.warmup, 3))           # GroundingBranch.ground_host_stream
 
     # ---- per-kernel device time of the tensor-core GEMM (the dominant kernel), CUDA events on the launching stream
     rec = []
@@ -296,6 +325,7 @@ def main():
     g_w = wrap(orig_gemm, lambda a, w, out, **k: 2.0 * a.shape[0] * a.shape[1] * w.shape[0])
     c_w = wrap(orig_conv, lambda x, wp, out, **k: 2.0 * out.shape[0] * wp.shape[0] * wp.shape[1])
     ops.gemm, ops.conv_gemm = g_w, c_w
+    gb.grounding_encoder.image_encoder.enable_cuda_graphs(False)    # per-launch events need kernel-by-kernel launches
     for i in range(2):
         rec.clear()
         step_resident(i)
@@ -319,7 +349,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
-                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOT * PHRASES * 5 * 4},
+                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOT * PHRASES * 5 * 4,
+                        "api": "GroundingBranch.ground_host_stream (pinned host batches in, host results out; next upload and previous "
+                               "read-back overlap the current step)",
+                        "blocking_per_step_value": world * TOT * args.steps / (ms_e2e_sync * 1e-3)},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                              "frac": achieved / pk["bf16_tflops_sustained"], "traffic": NCU_TRAFFIC_BYTES,

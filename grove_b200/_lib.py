@@ -26,6 +26,7 @@ SIGNATURES = {
     "grove_last_error": [],
     "grove_launch_count": [],
     "grove_reset_launch_count": [],
+    "grove_add_launch_count": [C.c_longlong],
     "grove_gemm_bf16": [_P, _P, _P, _I, _I, _I, C.POINTER(GemmEpilogue), _P],
     "grove_conv_gemm_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(GemmEpilogue), _P],
     "grove_im2col_patch16": [_P, _P, _I, _I, _I, _I, _P],
@@ -73,7 +74,7 @@ SIGNATURES = {
     "grove_attn_relpos_bwd_lse": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_box_losses_bwd": [_P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _P],
 }
-_RESTYPES = {"grove_last_error": C.c_char_p, "grove_launch_count": C.c_longlong, "grove_reset_launch_count": None,
+_RESTYPES = {"grove_last_error": C.c_char_p, "grove_launch_count": C.c_longlong, "grove_reset_launch_count": None, "grove_add_launch_count": None,
              "grove_attn_relpos_bwd_workspace_bytes": C.c_longlong}
 
 _lib = None

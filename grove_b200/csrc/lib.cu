@@ -21,3 +21,4 @@ extern "C" int grove_abi_version(void) { return GROVE_B200_ABI_VERSION; }
 extern "C" const char* grove_last_error(void) { return g_err; }
 extern "C" long long grove_launch_count(void) { return g_launches.load(); }
 extern "C" void grove_reset_launch_count(void) { g_launches.store(0); }
+extern "C" void grove_add_launch_count(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

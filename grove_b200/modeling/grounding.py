@@ -290,6 +290,63 @@ class GroundingBranch(nn.Module):
         return emb, self._generate_and_postprocess_masks(pred, emb, orig_sizes, dense_pe, infer=infer)
 
 
+    @torch.no_grad()
+    def ground_host_stream(self, host_batches, orig_sizes=None, infer=False):
+        """End-to-end serving loop over HOST batches (the shape of infer_iground.py:150-295: decode on the host, ground on the GPU,
+        collect numpy-ready results): yields one packed fp32 host tensor `[sum P, 5]` (cx, cy, w, h | x1, y1, x2, y2 when infer, and
+        the objectness logit) per batch, in order.
+
+        `host_batches` iterates `(images, last_hidden_state, input_ids)` in pinned host memory.  Batch i+1 is uploaded on a side
+        stream while batch i is computed and the result of batch i is read back asynchronously, so a step costs
+        max(copy, compute) instead of their sum; every byte still crosses PCIe inside the loop."""
+        dev = next(self.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+
+        def upload(batch):
+            with torch.cuda.stream(side):
+                t = tuple(x.to(dev, non_blocking=True) for x in batch)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return t, ev
+
+        it = iter(host_batches)
+        try:
+            nxt = upload(next(it))
+        except StopIteration:
+            return
+        pending = None                                       # (pinned host result, event) of the previous batch
+        pool, n_out = [None, None], 0
+        while nxt is not None:
+            (images, hidden, ids), ev = nxt
+            main.wait_event(ev)
+            for x in (images, hidden, ids):
+                x.record_stream(main)
+            try:
+                nxt = upload(next(it))
+            except StopIteration:
+                nxt = None
+            mask = self._create_det_token_mask(ids)
+            _, (boxes, logits) = self.ground(images, hidden, mask, orig_sizes=orig_sizes, infer=infer)
+            b = torch.cat([x for v in boxes for x in v]).float()
+            l = torch.cat([x for v in logits for x in v]).float()
+            packed = torch.cat([b, l[:, None]], 1)
+            slot = pool[n_out & 1]                           # two pinned result buffers, alternated (cudaHostAlloc per step is slow)
+            if slot is None or slot.shape[0] < packed.shape[0]:
+                slot = pool[n_out & 1] = torch.empty((max(packed.shape[0], 1), 5 if not infer else packed.shape[1]), dtype=packed.dtype, pin_memory=True)
+            host = slot[:packed.shape[0]]
+            n_out += 1
+            host.copy_(packed, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0].clone()                     # the pinned slot is reused two batches later
+            pending = (host, done)
+        pending[1].synchronize()
+        yield pending[0].clone()
+
+
 class _GroundingLossFn(torch.autograd.Function):
     """forward = GroundingBranch.grounding_loss_and_grads (loss and all gradients in one pass over the CUDA library);
     backward only scales the stored gradients by the incoming cotangent."""

@@ -121,6 +121,8 @@ class ImageEncoderViT(nn.Module):
             nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False), LayerNorm2d(out_chans))
         self.global_attn_indexes = global_attn_indexes
         self._pack = PackCache()
+        self._use_graphs = False
+        self._graph = None          # (signature, CUDAGraph, static patches, static embeddings, kernels per replay)
 
     # ------------------------------------------------------------------ weight packing (cached)
     def _linear(self, key, lin: nn.Linear):
@@ -130,6 +132,34 @@ class ImageEncoderViT(nn.Module):
 
     def _ln(self, key, ln):
         return self._pack.get(key + ".g", [ln.weight], f32), self._pack.get(key + ".b", [ln.bias], f32)
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the block stack (serving)
+    def enable_cuda_graphs(self, on: bool = True) -> None:
+        """Serving mode: capture the ~100 launches from the patch-embed GEMM to the neck into one CUDA graph per input shape and
+        replay it (no per-kernel launch gaps, no host work per kernel).  The graph bakes in the packed weights' addresses; it is
+        re-captured when any parameter is reassigned, moved or modified in place (same signature rule as PackCache)."""
+        self._use_graphs = bool(on)
+        self._graph = None
+
+    def _encode_patches_cached(self, patches: torch.Tensor, Fr: int, G: int) -> torch.Tensor:
+        if not self._use_graphs:
+            return self._encode_patches(patches, Fr, G)
+        sig = (Fr, G, patches.device, tuple(patches.shape), tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        if self._graph is None or self._graph[0] != sig:
+            self._graph = None
+            self._encode_patches(patches, Fr, G)            # warm-up: packs the weights, sets the kernels' shared-memory attributes
+            torch.cuda.synchronize(patches.device)
+            static_in = torch.empty_like(patches)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(graph):
+                static_out = self._encode_patches(static_in, Fr, G)
+            self._graph = (sig, graph, static_in, static_out, ops.launch_count() - n0)
+        _, graph, static_in, static_out, n_kernels = self._graph
+        static_in.copy_(patches)
+        graph.replay()
+        ops.add_launch_count(n_kernels)
+        return static_out.clone()
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -145,7 +175,7 @@ class ImageEncoderViT(nn.Module):
         img = x.to(torch.bfloat16).contiguous()
         patches = torch.empty(V * T * (H // 16) ** 2, 768, device=x.device, dtype=torch.bfloat16)
         ops.im2col_patch16(img, patches)
-        return self._encode_patches(patches, V * T, H // 16)
+        return self._encode_patches_cached(patches, V * T, H // 16)
 
     @torch.no_grad()
     def forward_frames(self, frames: torch.Tensor, transform=None) -> torch.Tensor:
@@ -161,7 +191,7 @@ class ImageEncoderViT(nn.Module):
         tr = transform if transform is not None else ResizeLongestSide(self.img_size)
         patches = tr.patches(frames.reshape(V * T, h, w, 3).contiguous(), self.img_size)
         G = self.img_size // 16
-        tok = self._encode_patches(patches, V * T, G)
+        tok = self._encode_patches_cached(patches, V * T, G)
         out = tok.view(V * T, G, G, self.out_chans).permute(0, 3, 1, 2)
         want = self.pos_embed.dtype if self.pos_embed is not None else torch.bfloat16
         return out if want == torch.bfloat16 else out.to(want)

@@ -429,3 +429,7 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     lib().grove_reset_launch_count()
+
+
+def add_launch_count(n: int) -> None:
+    lib().grove_add_launch_count(int(n))

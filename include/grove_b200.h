@@ -33,6 +33,8 @@ const char* grove_last_error(void);
 /* kernels launched by this library since the last reset (bench.py's gpu_launches) */
 long long grove_launch_count(void);
 void grove_reset_launch_count(void);
+/* kernels launched by replaying a captured CUDA graph are reported by the host side (a replay does not pass through the entry points) */
+void grove_add_launch_count(long long n);
 
 /* ---- dense contractions on tcgen05 (gemm_tcgen05.cu) ------------------------------------------ */
 typedef struct grove_gemm_epilogue {

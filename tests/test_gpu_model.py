@@ -206,3 +206,48 @@ def test_sharded_long_clip_single_rank():
     rec = window_fn(windows[1])
     assert torch.equal(out[windows[1]], rec.float())
     assert torch.isfinite(out).all() and float(out[..., :4].min()) > 0 and float(out[..., :4].max()) < 1
+
+
+def test_serving_loop_graph_replay_and_host_stream():
+    """Serving mode: the encoder's CUDA-graph replay is bit-identical to kernel-by-kernel launches (also after a weight update, which
+    must trigger a re-capture), and GroundingBranch.ground_host_stream (pinned host batches in, packed host results out, copies
+    overlapped) returns exactly what per-batch ground() calls return, in order."""
+    from grove_b200.modeling.grounding import GroundingBranch
+    seed, img, L, P = 31, 512, 640, 3
+    gb = GroundingBranch(vit="vit_b", num_frames=8, image_size=img).cuda()
+    enc = gb.grounding_encoder.image_encoder
+    with torch.no_grad():
+        for blk in enc.blocks:                       # non-trivial rel-pos / adapters (zero-initialised in the reference)
+            blk.attn.rel_pos_h.normal_(std=0.02); blk.attn.rel_pos_w.normal_(std=0.02)
+        for a in enc.adapters:
+            a.alpha.fill_(0.5)
+    batches = []
+    for i in range(3):
+        images = synth.synth_tensor(f"serve.images{i}", (1, 3, 8, img, img), seed).to(torch.bfloat16)
+        hid = synth.synth_tensor(f"serve.hidden{i}", (1, L, 4096), seed).to(torch.bfloat16)
+        ids = torch.full((1, L - 575), 7, dtype=torch.long)
+        for p in synth.det_positions(L, P, seed + i):
+            ids[0, p - 575 + 1] = gb.det_token_idx
+        batches.append(tuple(t.pin_memory() for t in (images, hid, ids)))
+
+    def direct(batch):
+        images, hid, ids = (t.cuda() for t in batch)
+        _, (boxes, logits) = gb.ground(images, hid, gb._create_det_token_mask(ids), infer=False)
+        b = torch.cat([x for v in boxes for x in v]).float()
+        l = torch.cat([x for v in logits for x in v]).float()
+        return torch.cat([b, l[:, None]], 1).cpu()
+
+    eager = [direct(b) for b in batches]
+    enc.enable_cuda_graphs(True)
+    replay = [direct(b) for b in batches]
+    for a, b in zip(eager, replay):
+        assert torch.equal(a, b)
+    streamed = list(gb.ground_host_stream(iter(batches)))
+    assert len(streamed) == 3
+    for a, b in zip(eager, streamed):
+        assert torch.equal(a, b)
+    with torch.no_grad():                            # in-place weight update -> new signature -> re-capture
+        enc.blocks[0].mlp.lin1.bias.add_(0.25)
+    changed = direct(batches[0])
+    enc.enable_cuda_graphs(False)
+    assert torch.equal(changed, direct(batches[0])) and not torch.equal(changed, eager[0])
