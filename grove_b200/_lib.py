@@ -15,7 +15,8 @@ class GemmEpilogue(C.Structure):
     """mirror of `struct grove_gemm_epilogue`"""
     _fields_ = [("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_row_mod", C.c_int), ("gate_alpha", C.c_void_p),
                 ("act", C.c_int), ("out_f32", C.c_int), ("out2_bf16", C.c_void_p), ("max_ctas", C.c_int), ("force_ctas", C.c_int),
-                ("out2_pre_act", C.c_int), ("dact_pre", C.c_void_p), ("dact", C.c_int), ("splits", C.c_int)]
+                ("out2_pre_act", C.c_int), ("dact_pre", C.c_void_p), ("dact", C.c_int), ("splits", C.c_int),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
 
 
 _P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
@@ -91,7 +92,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if l.grove_abi_version() != 2:
+        if l.grove_abi_version() != 3:
             raise RuntimeError("libgrove_b200.so ABI version mismatch; rebuild")
         _lib = l
     return _lib

@@ -30,7 +30,9 @@ struct GemmParams {
                        // 2: conv weight gradient — K runs over tokens, B is X^T [C,V,T,G,G] fetched at shifted (w,h,t)
   int G, rows_per_tile, tiles_per_frame, T, kt, kc_blocks;
   int cblocks_per_tap, kblocks_per_frame, rows_per_kblock, wg_C;   // conv == 2
-  int splits, kb_per_split;                                   // split-K: partial sums to out + split*M*N (fp32)
+  int splits, kb_per_split;                                   // split-K: partial sums to out + split*plane_rows*N (fp32)
+  int m_blk0;          // first m-block (of 128*CTAS rows) of this launch: a launch may cover a row range of the problem
+  int plane_rows;      // split-K: rows of one partial plane (the launch's own row range), partial row = row - m_blk0*128*CTAS
   const __nv_bfloat16* dact_pre;  // bf16 [M,N] or null: multiply by act'(dact_pre) (backward of GELU / ReLU)
   int dact;            // 1 exact-GELU derivative, 2 ReLU mask
   const float* bias;   // [N] or null
@@ -119,7 +121,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
       uint32_t it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int sp = tile / tiles_mn, tmn = tile % tiles_mn;
-        const int m_blk = (tmn / p.num_n_blocks) * CTAS + (int)cta_rank;   // this CTA's 128-row block
+        const int m_blk = (p.m_blk0 + tmn / p.num_n_blocks) * CTAS + (int)cta_rank;   // this CTA's 128-row block
         const int n_blk = tmn % p.num_n_blocks;
         const int kb_begin = sp * p.kb_per_split, kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
         int f = 0, h0 = 0;
@@ -247,7 +249,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
       const uint32_t bias_s = stg + 2048;                  // this warp's 128 bias values (fp32), 512 B behind the 2 KB staging
       __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(p.out);
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
-        const int m_blk = (tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
+        const int m_blk = (p.m_blk0 + tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
         const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
         const int row_base = m_blk * BM + quad * 32;
         const int colw = n_blk * BN + half * (BN / 2);     // first output column of this warp
@@ -311,7 +313,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
       float* const outp = reinterpret_cast<float*>(p.out);
       const int c = (lane & 7) * 4;                        // lane -> (row 4i + lane/8, 4 columns at c)
       auto res_ptr = [&](int tile_, int ps_, int i_) {
-        const int m_blk_ = (tile_ / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk_ = tile_ % p.num_n_blocks;
+        const int m_blk_ = (p.m_blk0 + tile_ / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk_ = tile_ % p.num_n_blocks;
         const int row_ = m_blk_ * BM + quad * 32 + 4 * i_ + (lane >> 3);
         return p.resid + (size_t)min(row_, p.M - 1) * p.N + n_blk_ * BN + half * (BN / 2) + ps_ * 32 + c;
       };
@@ -321,7 +323,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
         for (int i = 0; i < 8; ++i) res[i] = *reinterpret_cast<const float4*>(res_ptr(tile0, 0, i));
       }
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
-        const int m_blk = (tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
+        const int m_blk = (p.m_blk0 + tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
         const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
         const int row_base = m_blk * BM + quad * 32;
         const int colw = n_blk * BN + half * (BN / 2);
@@ -384,10 +386,11 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     } else
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
       const int sp = tile / tiles_mn, tmn = tile % tiles_mn;
-      const int m_blk = (tmn / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tmn % p.num_n_blocks;
+      const int m_blk = (p.m_blk0 + tmn / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tmn % p.num_n_blocks;
       const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
       const int row_base = m_blk * BM + quad * 32;
-      float* const out_f = reinterpret_cast<float*>(p.out) + (size_t)sp * p.M * p.N;   // split-K partial plane
+      // split-K: partial plane `sp` of this launch's row range; otherwise the output itself
+      float* const out_f = reinterpret_cast<float*>(p.out) + (p.splits > 1 ? ((long long)sp * p.plane_rows - (long long)p.m_blk0 * CTAS * BM) * p.N : 0ll);
       bool waited = false;
 #pragma unroll 1
       for (int ps = 0; ps < kPasses; ++ps) {
@@ -634,15 +637,51 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& ta, const CUtenso
   return GROVE_OK;
 }
 
+static bool tail_split_disabled() {   // GROVE_GEMM_NO_TAIL_SPLIT=1 (A/B measurements)
+  static int v = -1;
+  if (v < 0) v = getenv("GROVE_GEMM_NO_TAIL_SPLIT") != nullptr;
+  return v != 0;
+}
+
 static bool generic_epilogue_only() {   // GROVE_GEMM_GENERIC_EPI=1: route everything through the general epilogue (A/B measurements)
   static int v = -1;
   if (v < 0) v = getenv("GROVE_GEMM_GENERIC_EPI") != nullptr;
   return v != 0;
 }
 
+// Tail fix-up of a wave-quantised GEMM: out[r, n] = resid[r, n] + gate * act(sum_s part[s, r - row0, n] + bias[n]) (+ bf16 copy)
+// for the rows [row0, row1) whose tiles were computed as split-K partial planes (see dispatch_gemm).
+__global__ void __launch_bounds__(256) gemm_tail_fixup_kernel(const float* __restrict__ part, int splits, int plane_rows, int row0, int row1, int N,
+                                                              const float* __restrict__ bias, const float* resid, const float* __restrict__ gate_alpha,
+                                                              int act, float* out, __nv_bfloat16* out2) {
+  const float gate = gate_alpha ? tanhf(__ldg(gate_alpha)) : 1.0f;
+  const float floor_v = act == 2 ? 0.f : -INFINITY;
+  const int n4 = N / 4;
+  const long long total = (long long)(row1 - row0) * n4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / n4), c = (int)(i % n4) * 4;
+    float4 a = *reinterpret_cast<const float4*>(part + (size_t)r * N + c);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = *reinterpret_cast<const float4*>(part + ((size_t)s * plane_rows + r) * N + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const size_t o = (size_t)(row0 + r) * N + c;
+    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (resid) rv = *reinterpret_cast<const float4*>(resid + o);
+    float4 v;
+    v.x = fmaf(fmaxf(a.x + bv.x, floor_v), gate, rv.x); v.y = fmaf(fmaxf(a.y + bv.y, floor_v), gate, rv.y);
+    v.z = fmaf(fmaxf(a.z + bv.z, floor_v), gate, rv.z); v.w = fmaf(fmaxf(a.w + bv.w, floor_v), gate, rv.w);
+    *reinterpret_cast<float4*>(out + o) = v;
+    if (out2) *reinterpret_cast<uint2*>(out2 + o) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
 // tile configuration: CTA pairs (256 x 256 tiles) whenever the problem has them, else single-CTA 128 x {256,128} tiles
 static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K_total, int N, int M, bool conv, const uint64_t* adims,
-                         const uint32_t* abox, int arank, int max_ctas, int force_ctas, cudaStream_t st, const uint64_t* bdims5 = nullptr) {
+                         const uint32_t* abox, int arank, int max_ctas, int force_ctas, cudaStream_t st, const uint64_t* bdims5 = nullptr,
+                         void* workspace = nullptr, size_t workspace_bytes = 0) {
   const int BN = (N % 256 == 0) ? 256 : 128;
   int ctas = (BN == 256 && M >= 256) ? 2 : 1;
   if (force_ctas == 1 || force_ctas == 2) ctas = (force_ctas == 2 && BN == 256) ? 2 : 1;
@@ -651,6 +690,8 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
   if (p.splits < 1) p.splits = 1;
   p.kb_per_split = (p.num_k_blocks + p.splits - 1) / p.splits;
   p.splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
+  p.m_blk0 = 0;
+  p.plane_rows = p.M;
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_tmap_bf16(&ta, A_or_X, arank, adims, abox))) return rc;
@@ -671,7 +712,49 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
   if (ctas == 2 && plain_bf16) return p.act == 1 ? launch_gemm<256, 2, 2>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 1>(p, ta, tb, max_ctas, st);
   const bool resid_f32 = p.out_f32 && p.resid && p.resid_mod == 0 && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2_pre &&
                          !generic_epilogue_only();
-  if (ctas == 2 && resid_f32) return launch_gemm<256, 2, 3>(p, ta, tb, max_ctas, st);
+  if (ctas == 2 && resid_f32) {
+    // Wave quantisation: 256x256 tiles on P = 74 CTA pairs.  With N = 768 and M = 32768 (proj, fc2, the Conv3d adapter) there are
+    // 384 tiles = 5.19 waves, so the last wave runs 14 tiles on 74 pairs.  When the remainder is small the trailing m-blocks are
+    // computed instead as split-K partial planes (t*nb tiles x s splits <= P units of K/s k-blocks each, one short wave) and a
+    // fix-up kernel applies the epilogue to those rows: 5 + 1/s waves instead of 6.
+    const int pairs = (max_ctas > 0 ? max_ctas : num_sms()) / 2;
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    const int full_waves = pairs > 0 ? tiles / pairs : 0, rem = pairs > 0 ? tiles % pairs : 0;
+    // (measured: pays off for the K = 20736 adapter conv, 858 -> 778 us; LOSES on fc2 with K = 3072, 124 -> 134 us, where the two extra
+    // launches and the partial-plane traffic outweigh 0.75 of a 20 us wave -- hence the k-block threshold)
+    if (workspace && full_waves >= 1 && rem > 0 && 2 * rem <= pairs && p.M % (BM * 2) == 0 && p.num_k_blocks >= 96 && !tail_split_disabled()) {
+      const int t = (rem + p.num_n_blocks - 1) / p.num_n_blocks;            // trailing m-blocks taken out of the main launch
+      const int tail_tiles = t * p.num_n_blocks;
+      int s = tail_tiles > 0 ? pairs / tail_tiles : 0;
+      if (s > 8) s = 8;
+      while (s >= 2 && p.num_k_blocks / s < 8) --s;                        // keep every unit at least 8 k-blocks long
+      const size_t need = (size_t)s * t * BM * 2 * p.N * sizeof(float);
+      if (s >= 2 && t < p.num_m_blocks && need <= workspace_bytes) {
+        GemmParams pa = p;
+        pa.num_m_blocks = p.num_m_blocks - t;
+        int rc = launch_gemm<256, 2, 3>(pa, ta, tb, max_ctas, st);
+        if (rc) return rc;
+        GemmParams pb = p;
+        pb.m_blk0 = p.num_m_blocks - t; pb.num_m_blocks = t;
+        pb.splits = s; pb.kb_per_split = (p.num_k_blocks + s - 1) / s;
+        pb.splits = (p.num_k_blocks + pb.kb_per_split - 1) / pb.kb_per_split;
+        pb.plane_rows = t * BM * 2;
+        pb.out = workspace; pb.out_f32 = 1;
+        pb.bias = nullptr; pb.resid = nullptr; pb.gate_alpha = nullptr; pb.act = 0; pb.out2 = nullptr;
+        rc = launch_gemm<256, 2>(pb, ta, tb, max_ctas, st);
+        if (rc) return rc;
+        const int row0 = pb.m_blk0 * BM * 2;
+        const long long n4 = (long long)(p.M - row0) * (p.N / 4);
+        const int grid = (int)((n4 + 255) / 256 < 4 * num_sms() ? (n4 + 255) / 256 : 4 * num_sms());
+        gemm_tail_fixup_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), pb.splits, pb.plane_rows, row0, p.M, p.N, p.bias, p.resid,
+                                                     p.gate_alpha, p.act, reinterpret_cast<float*>(p.out), p.out2);
+        grove_count_launch();
+        GROVE_CHECK_LAUNCH();
+        return GROVE_OK;
+      }
+    }
+    return launch_gemm<256, 2, 3>(p, ta, tb, max_ctas, st);
+  }
   if (ctas == 2) return launch_gemm<256, 2>(p, ta, tb, max_ctas, st);
   return BN == 256 ? launch_gemm<256, 1>(p, ta, tb, max_ctas, st) : launch_gemm<128, 1>(p, ta, tb, max_ctas, st);
 }
@@ -716,7 +799,8 @@ extern "C" int grove_gemm_bf16(const void* A, const void* W, void* out, int M, i
   if (rc) return rc;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
   uint32_t ba[2] = {BK, BM};
-  return dispatch_gemm(p, A, W, K, N, M, false, da, ba, 2, epi ? epi->max_ctas : 0, epi ? epi->force_ctas : 0, stream);
+  return dispatch_gemm(p, A, W, K, N, M, false, da, ba, 2, epi ? epi->max_ctas : 0, epi ? epi->force_ctas : 0, stream, nullptr,
+                       epi ? epi->workspace : nullptr, epi && epi->workspace ? (size_t)epi->workspace_bytes : 0);
 }
 
 extern "C" int grove_conv_gemm_bf16(const void* X, const void* Wp, void* out, int V, int T, int G, int C, int N, int kt,
@@ -737,7 +821,8 @@ extern "C" int grove_conv_gemm_bf16(const void* X, const void* Wp, void* out, in
   if (rc) return rc;
   uint64_t da[5] = {(uint64_t)C, (uint64_t)G, (uint64_t)G, (uint64_t)T, (uint64_t)V};
   uint32_t ba[5] = {BK, (uint32_t)G, (uint32_t)(BM / G), 1, 1};
-  return dispatch_gemm(p, X, Wp, ntaps * C, N, p.M, true, da, ba, 5, epi ? epi->max_ctas : 0, epi ? epi->force_ctas : 0, stream);
+  return dispatch_gemm(p, X, Wp, ntaps * C, N, p.M, true, da, ba, 5, epi ? epi->max_ctas : 0, epi ? epi->force_ctas : 0, stream, nullptr,
+                       epi ? epi->workspace : nullptr, epi && epi->workspace ? (size_t)epi->workspace_bytes : 0);
 }
 
 /* Weight gradient of the implicit-GEMM convolutions: dWp[N, taps*C] (tap-major, fp32) = sum over tokens of

@@ -43,7 +43,20 @@ def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, 
     e.out2_bf16 = None if out2 is None else _req(out2, BF16, "out2").data_ptr()
     e.max_ctas = int(max_ctas)
     e.force_ctas = int(force_ctas)
+    if out.dtype == F32 and resid is not None and splits == 1:      # residual-stream GEMM: scratch for the wave-quantisation tail split
+        ws = _gemm_workspace(out.device)
+        e.workspace, e.workspace_bytes = ws.data_ptr(), ws.numel()
     return e
+
+
+_WORKSPACES = {}
+
+
+def _gemm_workspace(device):
+    ws = _WORKSPACES.get(device)
+    if ws is None:
+        ws = _WORKSPACES[device] = torch.empty(32 << 20, device=device, dtype=torch.uint8)
+    return ws
 
 
 def gemm(a, w, out, *, bias=None, resid=None, resid_row_mod=0, gate_alpha=None, act=None, out2=None, max_ctas=0, force_ctas=0,

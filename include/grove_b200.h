@@ -25,7 +25,7 @@ typedef cudaStream_t grove_stream_t;
 typedef void* grove_stream_t;
 #endif
 
-#define GROVE_B200_ABI_VERSION 2
+#define GROVE_B200_ABI_VERSION 3
 
 /* ---- library ---------------------------------------------------------------------------------- */
 int grove_abi_version(void);
@@ -54,6 +54,11 @@ typedef struct grove_gemm_epilogue {
   int dact;                /* with dact_pre: 1 = exact-GELU derivative, 2 = ReLU mask (pre > 0) */
   int splits;              /* >1: split-K; `out` is fp32 [splits, M, N] raw partial sums (no other epilogue field allowed);
                               finish with grove_reduce_partials_f32 */
+  /* ---- ABI v3 ---- */
+  void* workspace;         /* optional device scratch (16-byte aligned) or NULL.  With it, a residual-stream GEMM whose last wave of
+                              256x256 tiles would be mostly empty computes its trailing rows as split-K partial planes here and
+                              finishes them with a fix-up kernel (needs splits * rows * N * 4 bytes, <= 32 MB for the encoder) */
+  long long workspace_bytes;
 } grove_gemm_epilogue;
 
 /* out[M,N] = resid + gate * act(A[M,K] . W[N,K]^T + bias).  A, W bf16 row-major (nn.Linear layout).

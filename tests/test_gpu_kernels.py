@@ -66,6 +66,25 @@ def test_gemm_epilogues(ops, force_ctas):
     assert _relerr(o3, ref3) < 2e-5
 
 
+def test_gemm_tail_split(ops):
+    """Wave-quantisation tail: with 12 CTA pairs, 6 m-blocks x 3 n-blocks = 18 tiles leave 6 for a second wave, so the last two
+    m-blocks are computed as split-K partial planes + fix-up kernel (long-K problems only); the result must equal the plain schedule
+    (fp32 sums in a different order) and the reference."""
+    M, N, K = 1536, 768, 6144
+    a, w = _rand((M, K), 41, dtype=torch.bfloat16), _rand((N, K), 42, 1 / math.sqrt(K), dtype=torch.bfloat16)
+    bias, resid = _rand((N,), 43), _rand((M, N), 44)
+    alpha = torch.tensor([0.3], device="cuda")
+    ref = resid + math.tanh(0.3) * torch.relu(a.float() @ w.float().t() + bias)
+    x = resid.clone()
+    o2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, x, bias=bias, resid=x, act="relu", gate_alpha=alpha, out2=o2, max_ctas=24)
+    assert _relerr(x, ref) < 2e-5
+    assert _relerr(o2.float(), ref) < 6e-3
+    y = resid.clone()
+    ops.gemm(a, w, y, bias=bias, resid=y, act="relu", gate_alpha=alpha, max_ctas=36)     # 18 pairs: one exact wave, no split
+    assert _relerr(x, y) < 5e-6
+
+
 @pytest.mark.parametrize("force_ctas", [1, 2])
 @pytest.mark.parametrize("V,T,G,C,N,kt", [(1, 8, 64, 128, 256, 3), (2, 8, 32, 64, 128, 3), (3, 1, 64, 256, 256, 1), (1, 8, 16, 64, 128, 3)])
 def test_conv_implicit_gemm(ops, V, T, G, C, N, kt, force_ctas):
