@@ -311,9 +311,13 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
         const int kh = (b * 128 + (SPLIT * cc + hs) * 32) / G;
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          mx0 = fmaxf(mx0, fmaf(__uint_as_float(rr[cc][j]), c_scale, relw[j]));
-          mx1 = fmaxf(mx1, fmaf(__uint_as_float(rr[cc][j + 1]), c_scale, relw[j + 1]));
+        for (int j = 0; j < 32; j += 2) {                 // scale*S + rel_w is kept in place: the exponential pass adds only a per-chunk offset
+          const float e0 = fmaf(__uint_as_float(rr[cc][j]), c_scale, relw[j]);
+          const float e1 = fmaf(__uint_as_float(rr[cc][j + 1]), c_scale, relw[j + 1]);
+          rr[cc][j] = __float_as_uint(e0);
+          rr[cc][j + 1] = __float_as_uint(e1);
+          mx0 = fmaxf(mx0, e0);
+          mx1 = fmaxf(mx1, e1);
         }
         mb = fmaxf(mb, fmaxf(mx0, mx1) + relh_f[kh * 128 + row]);
       }
@@ -365,8 +369,8 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float p0, p1;
-          const float e0 = fmaf(__uint_as_float(rr[cc][j]), c_scale, relw[j]) + off;
-          const float e1 = fmaf(__uint_as_float(rr[cc][j + 1]), c_scale, relw[j + 1]) + off;
+          const float e0 = __uint_as_float(rr[cc][j]) + off;
+          const float e1 = __uint_as_float(rr[cc][j + 1]) + off;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
 #ifndef GROVE_ATT_NOPOLY
           if (j & 2) p1 = ex2_fma(e1);
