@@ -39,6 +39,7 @@ SIGNATURES = {
     "grove_attn_global_relpos_fwd_mma": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_cast_f32_bf16": [_P, _P, _LL, _P],
     "grove_tokens_to_nchw_bf16": [_P, _P, _I, _I, _I, _P],
+    "grove_adaptive_avgpool3d_tokens": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "grove_nchw_to_tokens_bf16": [_P, _P, _I, _I, _I, _P],
     "grove_gather_rows_bf16": [_P, _I, _P, _P, _I, _I, _P],
     "grove_dense_pe": [_P, _P, _I, _I, _P],

@@ -147,3 +147,70 @@ extern "C" int grove_tokens_to_nchw_bf16(const void* tok, void* nchw, int F, int
 extern "C" int grove_nchw_to_tokens_bf16(const void* nchw, void* tok, int F, int N, int C, cudaStream_t stream) {
   return transpose16(nchw, tok, F, C, N, stream);
 }
+
+// ------------------------------------------------------------------ AdaptiveAvgPooling3D over token-major video features
+// (model/llava/model/multimodal_encoder/pooling.py:6-25: '(b t) (h w) c -> b c t h w', nn.AdaptiveAvgPool3d((OT, OH, OW)),
+// 'b c t h w -> b (t h w) c').  The two rearranges are folded into the indexing: one thread owns 8 (bf16) / 4 (fp32) channels of one
+// output token, sums its window in fp32 (window = [floor(i*I/O), ceil((i+1)*I/O)) per axis, as ATen's adaptive pooling) and divides by
+// the window size.  HBM-bound: every input element is read once or twice (overlapping windows), 16-byte accesses along c.
+namespace grove {
+template <bool F32>
+__global__ void __launch_bounds__(256) adaptive_avgpool3d_tokens_kernel(const void* __restrict__ x, void* __restrict__ out, int B, int T, int H, int W,
+                                                                        int C, int OT, int OH, int OW) {
+  constexpr int VEC = F32 ? 4 : 8;
+  const int cv = C / VEC;
+  const long long total = (long long)B * OT * OH * OW * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * VEC;
+    long long r = i / cv;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH); r /= OH;
+    const int ot = (int)(r % OT);
+    const int b = (int)(r / OT);
+    const int t0 = (ot * T) / OT, t1 = ((ot + 1) * T + OT - 1) / OT;
+    const int h0 = (oh * H) / OH, h1 = ((oh + 1) * H + OH - 1) / OH;
+    const int w0 = (ow * W) / OW, w1 = ((ow + 1) * W + OW - 1) / OW;
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int t = t0; t < t1; ++t)
+      for (int h = h0; h < h1; ++h)
+        for (int w = w0; w < w1; ++w) {
+          const size_t off = (((size_t)(b * T + t) * H + h) * W + w) * C + c0;
+          if (F32) {
+            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + off);
+            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+          } else {
+            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + off);
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 f = unpack_bf16(u[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+          }
+        }
+    const float inv = 1.0f / (float)((t1 - t0) * (h1 - h0) * (w1 - w0));
+    const size_t o = ((((size_t)b * OT + ot) * OH + oh) * OW + ow) * C + c0;
+    if (F32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    } else {
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o) =
+          make_uint4(pack_bf16(acc[0] * inv, acc[1] * inv), pack_bf16(acc[2] * inv, acc[3] * inv), pack_bf16(acc[4] * inv, acc[5] * inv),
+                     pack_bf16(acc[6] * inv, acc[7] * inv));
+    }
+  }
+}
+}  // namespace grove
+
+extern "C" int grove_adaptive_avgpool3d_tokens(const void* x, void* out, int is_f32, int B, int T, int H, int W, int C, int OT, int OH, int OW,
+                                               cudaStream_t stream) {
+  GROVE_CHECK_ARG(x && out && B > 0 && T > 0 && H > 0 && W > 0 && OT > 0 && OH > 0 && OW > 0);
+  GROVE_CHECK_ARG(OT <= T && OH <= H && OW <= W && C % 8 == 0);
+  GROVE_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0);
+  const long long total = (long long)B * OT * OH * OW * (C / (is_f32 ? 4 : 8));
+  const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  if (is_f32) grove::adaptive_avgpool3d_tokens_kernel<true><<<grid, 256, 0, stream>>>(x, out, B, T, H, W, C, OT, OH, OW);
+  else grove::adaptive_avgpool3d_tokens_kernel<false><<<grid, 256, 0, stream>>>(x, out, B, T, H, W, C, OT, OH, OW);
+  grove_count_launch();
+  GROVE_CHECK_LAUNCH();
+  return GROVE_OK;
+}
+

@@ -149,6 +149,16 @@ def cast_f32_bf16(x, out):
     return out
 
 
+def adaptive_avgpool3d_tokens(x, out, *, B, T, H, W, OT, OH, OW):
+    """x [(B*T), H*W, C] -> out [B, OT*OH*OW, C] (bf16 or fp32, same dtype): pooling.py:6-25 with the rearranges folded in"""
+    assert x.is_contiguous() and out.is_contiguous() and x.dtype == out.dtype and x.dtype in (BF16, F32)
+    Cc = x.shape[-1]
+    assert x.numel() == B * T * H * W * Cc and out.numel() == B * OT * OH * OW * Cc
+    check(lib().grove_adaptive_avgpool3d_tokens(_p(x), _p(out), 1 if x.dtype == F32 else 0, B, T, H, W, Cc, OT, OH, OW, _stream(x)),
+          "grove_adaptive_avgpool3d_tokens")
+    return out
+
+
 def tokens_to_nchw(tok, out, F, N, Cc):
     check(lib().grove_tokens_to_nchw_bf16(_p(_req(tok, BF16, "tok")), _p(_req(out, BF16, "out")), F, N, Cc, _stream(tok)), "tokens_to_nchw")
     return out

@@ -112,6 +112,11 @@ int grove_attn_global_relpos_fwd_mma(const void* qkv, const void* rel_pos_h, con
 int grove_cast_f32_bf16(const float* x, void* y, long long n, grove_stream_t stream);
 int grove_tokens_to_nchw_bf16(const void* tok, void* nchw, int F, int N, int C, grove_stream_t stream);
 int grove_nchw_to_tokens_bf16(const void* nchw, void* tok, int F, int N, int C, grove_stream_t stream);
+/* AdaptiveAvgPooling3D of the CLIP video features (model/llava/model/multimodal_encoder/pooling.py:6-25):
+ * x [(B*T), H*W, C] token-major (bf16, or fp32 when is_f32) -> out [B, OT*OH*OW, C] (same dtype), windows as
+ * nn.AdaptiveAvgPool3d((OT, OH, OW)); the reference's two einops rearranges are folded into the indexing.  C % 8 == 0. */
+int grove_adaptive_avgpool3d_tokens(const void* x, void* out, int is_f32, int B, int T, int H, int W, int C, int OT, int OH, int OW,
+                                    grove_stream_t stream);
 
 /* ---- text projection / prompt encoder / box decoder (decoder_ops.cu) --------------------------- */
 /* dst[i,:] = bf16(src[row_idx[i],:]) — gathers the [DET] rows BEFORE projecting them (GROVE.py:249-257 projects all

@@ -341,6 +341,47 @@ def box_eval_case(name, seed):
     print(name, "iou", iou64.shape, "matches", matches)
 
 
+def _classes_from_source(path, names, scope):
+    """exec only the named top-level classes of a reference module (modeling_clip.py imports a transformers version that is not
+    installed here); nothing is written to the repo."""
+    tree = ast.parse(open(path).read())
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in names:
+            exec(compile(ast.Module([node], []), path, "exec"), scope)
+    return scope
+
+
+def clip_case(name, seed):
+    """the CLIP-side SpatioTemporalConvAdapter (modeling_clip.py:591-612) and AdaptiveAvgPooling3D (pooling.py:6-25),
+    executed from the reference's own source in fp32 and fp64."""
+    import importlib.util
+    from einops import rearrange
+    from oracle import synth
+    enc_dir = os.path.join(REF, "model", "llava", "model", "multimodal_encoder")
+    scope = _classes_from_source(os.path.join(enc_dir, "modeling_clip.py"), {"SpatioTemporalConvAdapter"},
+                                 {"nn": torch.nn, "torch": torch, "Conv3d": torch.nn.Conv3d, "rearrange": rearrange})
+    spec = importlib.util.spec_from_file_location("ref_pooling", os.path.join(enc_dir, "pooling.py"))
+    pooling = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pooling)
+    out = {}
+    C, b = 32, 1
+    x = synth.synth_tensor(name + ".adapter.x", (b * 8, 257, C), seed)
+    w = synth.synth_tensor(name + ".adapter.w", (C, C, 3, 3, 3), seed) * (27 * C) ** -0.5
+    bias = synth.synth_tensor(name + ".adapter.b", (C,), seed) * 0.1
+    for dt, tag in ((torch.float64, "64"),):                                 # fp64 only: the fixture stays small
+        ad = scope["SpatioTemporalConvAdapter"](C, C, (3, 3, 3)).to(dt)
+        with torch.no_grad():
+            ad.conv3d.weight.copy_(w.to(dt)); ad.conv3d.bias.copy_(bias.to(dt)); ad.alpha.fill_(0.5)
+            out["adapter" + tag] = ad((x.to(dt),))[0].numpy()
+        for pname, shape in (("pool_a", (1 * 8, 256, 16)), ("pool_b", (1 * 8, 576, 8))):
+            xp = synth.synth_tensor(f"{name}.{pname}.x", shape, seed).to(dt)
+            with torch.no_grad():
+                out[pname + tag] = pooling.AdaptiveAvgPooling3D(num_frames=8)(xp).numpy()
+    out["meta"] = np.array([C, b, seed])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, REF)
@@ -359,6 +400,7 @@ def main():
     train_case("train_tiny512", seed=7)
     preprocess_case("preprocess", seed=8)
     posembed_case("posembed", seed=9)
+    clip_case("clip_adapters", seed=10)
 
 
 if __name__ == "__main__":

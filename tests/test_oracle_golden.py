@@ -198,3 +198,29 @@ def test_preprocessing_vs_reference_pil_chain():
     assert list(x.shape) == [int(v) for v in g["proc.shape"]]
     assert np.array_equal(x.view(torch.int16)[:, :, :48, :72].numpy(), g["proc.bits_sub"])
     assert int(g["proc.pad_nonzero"]) == 0 and float(x[:, :, 40:, :].abs().max()) == 0.0
+
+
+def _clip_inputs(name="clip_adapters"):
+    g = _g(name)
+    C, b, seed = [int(x) for x in g["meta"]]
+    x = synth.synth_tensor(name + ".adapter.x", (b * 8, 257, C), seed)
+    w = synth.synth_tensor(name + ".adapter.w", (C, C, 3, 3, 3), seed) * (27 * C) ** -0.5
+    bias = synth.synth_tensor(name + ".adapter.b", (C,), seed) * 0.1
+    pools = {"pool_a": synth.synth_tensor(f"{name}.pool_a.x", (8, 256, 16), seed), "pool_b": synth.synth_tensor(f"{name}.pool_b.x", (8, 576, 8), seed)}
+    return g, x, w, bias, pools
+
+
+def test_clip_adapters_vs_reference_classes():
+    """oracle/clip_adapters.py against the reference's SpatioTemporalConvAdapter (modeling_clip.py:591-612) and
+    AdaptiveAvgPooling3D (pooling.py:6-25) executed in float64 (tests/golden/clip_adapters.npz)."""
+    from oracle import clip_adapters as oc
+    g, x, w, bias, pools = _clip_inputs()
+    alpha = torch.tensor([0.5])
+    with torch.no_grad():
+        y64 = oc.clip_st_adapter(x.double(), w.double(), bias.double(), alpha.double())
+        y32 = oc.clip_st_adapter(x, w, bias, alpha)
+    np.testing.assert_allclose(y64.numpy(), g["adapter64"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(y32.numpy(), g["adapter64"], rtol=0, atol=2e-5)
+    for k, xp in pools.items():
+        np.testing.assert_allclose(oc.adaptive_avgpool3d_tokens(xp.double()).numpy(), g[k + "64"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(oc.adaptive_avgpool3d_tokens(xp).numpy(), g[k + "64"], rtol=0, atol=1e-6)
