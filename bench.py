@@ -232,6 +232,7 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner there)
         dist.init_process_group("nccl", device_id=dev)
     from grove_b200 import ops
     gb, sd, cfg = build_model(dev)
