@@ -21,7 +21,7 @@
 
 namespace grove {
 
-// In-kernel timeline probes (compile with -DGROVE_ATT_PROBE; read with grove_att_probe_read, see scratch/att_probe.py): clock64 of
+// In-kernel timeline probes (compile with -DGROVE_ATT_PROBE; read with grove_att_probe_read, see profiles/att_probe.py): clock64 of
 // one CTA's MMA warp and softmax warps at every hand-off.  Compiled out by default.
 #ifdef GROVE_ATT_PROBE
 __device__ long long g_att_probe[8192];

@@ -17,6 +17,14 @@
 
 namespace grove {
 
+// In-kernel timeline probes (-DGROVE_WIN_PROBE; read with grove_win_probe_read, profiles/win_probe.py).  Compiled out by default.
+#ifdef GROVE_WIN_PROBE
+__device__ long long g_win_probe[4096];
+#define WPROBE(slot) do { if (probe_on) g_win_probe[(slot)] = clock64(); } while (0)
+#else
+#define WPROBE(slot) do { } while (0)
+#endif
+
 constexpr int kWinThreads = 352;
 constexpr int kWS = 14, kWQ = 196, kWK = 208;   // window side, tokens, keys padded to 13 UMMA k-steps
 
@@ -112,6 +120,9 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = p.heads * HD;
   const int nWW = p.nW * p.nW;
+#ifdef GROVE_WIN_PROBE
+  const bool probe_on = blockIdx.x == 5 && lane == 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm.qkv);
@@ -188,8 +199,11 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++cnt) {
       const uint32_t vb = cnt & 1u;
       const uint32_t vbase = sV + vb * Cfg::kKBytes;
+      WPROBE(100 + 16 * (cnt & 7) + 0);
       mbar_wait2(bar(QK_FULL), cnt & 1u, bar(K_FIX), cnt & 1u);
+      WPROBE(100 + 16 * (cnt & 7) + 1);
       if (cnt > 0) mbar_wait(bar(O_READ), 1u);            // previous unit's second epilogue has drained the T/O columns
+      WPROBE(100 + 16 * (cnt & 7) + 2);
       tc_fence_after();
       if (elect_one()) {
         qk_mma(tTO, sQ, sQ + Cfg::kQMain, sTab, sTab + Cfg::kTabMain, idesc_t);
@@ -198,7 +212,9 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
         tc_commit(bar(S_FULL + 0));
       }
       __syncwarp();
+      WPROBE(100 + 16 * (cnt & 7) + 3);
       mbar_wait(bar(T_READ), 0u);                           // tile 0's T is in registers
+      WPROBE(100 + 16 * (cnt & 7) + 4);
       tc_fence_after();
       if (elect_one()) {
         qk_mma(tTO, sQ + 16384, sQ + Cfg::kQMain + 4096, sTab, sTab + Cfg::kTabMain, idesc_t);
@@ -208,12 +224,17 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
         tc_commit(bar(QK_EMPTY));                            // Q and K may be overwritten by the next unit's loads
       }
       __syncwarp();
+      WPROBE(100 + 16 * (cnt & 7) + 5);
       mbar_wait(bar(T_READ), 1u);
+      WPROBE(100 + 16 * (cnt & 7) + 6);
       mbar_wait2(bar(V_FULL + vb), (cnt >> 1) & 1u, bar(V_FIX + vb), (cnt >> 1) & 1u);
+      WPROBE(100 + 16 * (cnt & 7) + 7);
 #pragma unroll 1
       for (int t = 0; t < 2; ++t) {
         mbar_wait(bar(P_FULL + t), cnt & 1u);
+        WPROBE(100 + 16 * (cnt & 7) + 8 + 3 * t);
         if (t == 1) mbar_wait(bar(O_READ), 0u);             // tile 0's O has been read
+        WPROBE(100 + 16 * (cnt & 7) + 9 + 3 * t);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -226,6 +247,7 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
           if (t == 1) tc_commit(bar(V_EMPTY + vb));
         }
         __syncwarp();
+        WPROBE(100 + 16 * (cnt & 7) + 10 + 3 * t);
       }
     }
   } else if (warp == 10) {
@@ -286,7 +308,9 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
         const int q = min(t * 128 + row, kWQ - 1);          // rows >= 196 compute on a clamped position and are never stored
         const int qh = q / kWS, qw = q % kWS;
         // ---- rel-pos products of this tile: T_h = columns [0,27), T_w = columns [32,59)
+        WPROBE(1000 + (warp - 2) * 256 + 32 * (cnt & 7) + 8 * t + 0);
         mbar_wait(bar(T_FULL), (uint32_t)t);
+        WPROBE(1000 + (warp - 2) * 256 + 32 * (cnt & 7) + 8 * t + 1);
         tc_fence_after();
         {
           uint32_t r[32];
@@ -311,19 +335,24 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
         for (int i = 0; i < 14; ++i) relw[i] = stage_at(32 + qw + (kWS - 1) - i) * kL2e;
         softmax_sync();
         // ---- softmax of this tile
+        WPROBE(1000 + (warp - 2) * 256 + 32 * (cnt & 7) + 8 * t + 2);
         mbar_wait(bar(S_FULL + t), cnt & 1u);
+        WPROBE(1000 + (warp - 2) * 256 + 32 * (cnt & 7) + 8 * t + 3);
         tc_fence_after();
         const uint32_t tS = tS0 + t * kWK;
         lsum[t] = hs == 0 ? win_softmax_tile<0>(tS, tlane, relh, relw, c_scale, xch_f, row) : win_softmax_tile<1>(tS, tlane, relh, relw, c_scale, xch_f, row);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(P_FULL + t));
+        WPROBE(1000 + (warp - 2) * 256 + 32 * (cnt & 7) + 8 * t + 4);
         xch_f[256 + (t * 2 + hs) * 128 + row] = lsum[t];
       }
       softmax_sync();
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
+        WPROBE(1000 + (warp - 2) * 256 + 32 * (cnt & 7) + 8 * t + 5);
         mbar_wait(bar(O_FULL), (uint32_t)t);
+        WPROBE(1000 + (warp - 2) * 256 + 32 * (cnt & 7) + 8 * t + 6);
         tc_fence_after();
         uint32_t r[32], rx[8];
         tmem_ld_x32(tTO + hs * 32 + tlane, r);
@@ -348,6 +377,7 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
                            pack_bf16(__uint_as_float(rx[4]) * inv, __uint_as_float(rx[5]) * inv), pack_bf16(__uint_as_float(rx[6]) * inv, __uint_as_float(rx[7]) * inv));
         }
       }
+      WPROBE(1000 + (warp - 2) * 256 + 32 * (cnt & 7) + 16 + 7);
       softmax_sync();   // the sum exchange slots are rewritten by the next unit
     }
   }
@@ -361,6 +391,13 @@ int make_tmap_bf16_nd(CUtensorMap* m, const void* base, int rank, const uint64_t
 
 }  // namespace grove
 using namespace grove;
+
+#ifdef GROVE_WIN_PROBE
+extern "C" int grove_win_probe_read(long long* host, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host, g_win_probe, sizeof(long long) * n) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 template <int HD>
 static int launch_window_tc(const void* qkv, const void* qkv_bias, const void* tab, void* out, int F, int G, int heads, cudaStream_t stream) {
