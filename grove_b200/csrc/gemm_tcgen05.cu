@@ -315,7 +315,8 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
       auto res_ptr = [&](int tile_, int ps_, int i_) {
         const int m_blk_ = (p.m_blk0 + tile_ / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk_ = tile_ % p.num_n_blocks;
         const int row_ = m_blk_ * BM + quad * 32 + 4 * i_ + (lane >> 3);
-        return p.resid + (size_t)min(row_, p.M - 1) * p.N + n_blk_ * BN + half * (BN / 2) + ps_ * 32 + c;
+        const int rr_ = min(row_, p.M - 1);
+        return p.resid + (size_t)(p.resid_mod > 0 ? rr_ % p.resid_mod : rr_) * p.N + n_blk_ * BN + half * (BN / 2) + ps_ * 32 + c;
       };
       float4 res[8];
       if (tile0 < num_tiles) {
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(256) gemm_tail_fixup_kernel(const float* __res
     float4 v;
     v.x = fmaf(fmaxf(a.x + bv.x, floor_v), gate, rv.x); v.y = fmaf(fmaxf(a.y + bv.y, floor_v), gate, rv.y);
     v.z = fmaf(fmaxf(a.z + bv.z, floor_v), gate, rv.z); v.w = fmaf(fmaxf(a.w + bv.w, floor_v), gate, rv.w);
-    *reinterpret_cast<float4*>(out + o) = v;
+    if (out) *reinterpret_cast<float4*>(out + o) = v;
     if (out2) *reinterpret_cast<uint2*>(out2 + o) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   }
 }
@@ -706,11 +707,41 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
     if ((rc = make_tmap_bf16(&tb, W, 2, db, bb))) return rc;
   }
   (void)conv;
+  // Few tiles, long K (the text projection: 4 [DET] rows x 4096 x 4096 is 16 tiles, then ONE tile, each streaming its weights
+  // through a single CTA at ~0.9 TB/s): spread K over the idle SMs as split-K partial planes and finish with the fix-up kernel.
+  {
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    const bool simple = p.splits == 1 && p.conv == 0 && !p.resid && !p.gate_alpha && !p.dact_pre && !p.out2 && p.act != 1;
+    if (simple && workspace && tiles * ctas * 2 <= num_sms() && p.num_k_blocks >= 32 && max_ctas == 0 && !tail_split_disabled()) {
+      int s = num_sms() / (tiles * ctas);
+      if (s > 16) s = 16;
+      while (s > 1 && p.num_k_blocks / s < 4) --s;
+      const int plane_rows = p.num_m_blocks * BM * ctas;
+      if (s >= 2 && (size_t)s * plane_rows * p.N * sizeof(float) <= workspace_bytes) {
+        GemmParams pb = p;
+        pb.splits = s; pb.kb_per_split = (p.num_k_blocks + s - 1) / s;
+        pb.splits = (p.num_k_blocks + pb.kb_per_split - 1) / pb.kb_per_split;
+        pb.plane_rows = plane_rows;
+        pb.out = workspace; pb.out_f32 = 1; pb.bias = nullptr; pb.act = 0;
+        int rc2 = ctas == 2 ? launch_gemm<256, 2>(pb, ta, tb, max_ctas, st)
+                            : (BN == 256 ? launch_gemm<256, 1>(pb, ta, tb, max_ctas, st) : launch_gemm<128, 1>(pb, ta, tb, max_ctas, st));
+        if (rc2) return rc2;
+        const long long n4 = (long long)p.M * (p.N / 4);
+        const int grid = (int)((n4 + 255) / 256 < 4 * num_sms() ? (n4 + 255) / 256 : 4 * num_sms());
+        gemm_tail_fixup_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), pb.splits, plane_rows, 0, p.M, p.N, p.bias, nullptr, nullptr,
+                                                     p.act, p.out_f32 ? reinterpret_cast<float*>(p.out) : nullptr,
+                                                     p.out_f32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(p.out));
+        grove_count_launch();
+        GROVE_CHECK_LAUNCH();
+        return GROVE_OK;
+      }
+    }
+  }
   // straight-line epilogues for the two hot bf16-output forms (bias, optional GELU, nothing else)
   const bool plain_bf16 = !p.out_f32 && !p.resid && !p.gate_alpha && !p.out2 && !p.dact_pre && p.splits == 1 && p.conv != 2 && (p.act == 0 || p.act == 1) &&
                           !generic_epilogue_only();
   if (ctas == 2 && plain_bf16) return p.act == 1 ? launch_gemm<256, 2, 2>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 1>(p, ta, tb, max_ctas, st);
-  const bool resid_f32 = p.out_f32 && p.resid && p.resid_mod == 0 && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2_pre &&
+  const bool resid_f32 = p.out_f32 && p.resid && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2_pre &&
                          !generic_epilogue_only();
   if (ctas == 2 && resid_f32) {
     // Wave quantisation: 256x256 tiles on P = 74 CTA pairs.  With N = 768 and M = 32768 (proj, fc2, the Conv3d adapter) there are
@@ -722,7 +753,7 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
     const int full_waves = pairs > 0 ? tiles / pairs : 0, rem = pairs > 0 ? tiles % pairs : 0;
     // (measured: pays off for the K = 20736 adapter conv, 858 -> 778 us; LOSES on fc2 with K = 3072, 124 -> 134 us, where the two extra
     // launches and the partial-plane traffic outweigh 0.75 of a 20 us wave -- hence the k-block threshold)
-    if (workspace && full_waves >= 1 && rem > 0 && 2 * rem <= pairs && p.M % (BM * 2) == 0 && p.num_k_blocks >= 96 && !tail_split_disabled()) {
+    if (workspace && full_waves >= 1 && rem > 0 && 2 * rem <= pairs && p.M % (BM * 2) == 0 && p.num_k_blocks >= 96 && p.resid_mod == 0 && !tail_split_disabled()) {
       const int t = (rem + p.num_n_blocks - 1) / p.num_n_blocks;            // trailing m-blocks taken out of the main launch
       const int tail_tiles = t * p.num_n_blocks;
       int s = tail_tiles > 0 ? pairs / tail_tiles : 0;

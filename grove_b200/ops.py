@@ -43,7 +43,7 @@ def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, 
     e.out2_bf16 = None if out2 is None else _req(out2, BF16, "out2").data_ptr()
     e.max_ctas = int(max_ctas)
     e.force_ctas = int(force_ctas)
-    if out.dtype == F32 and resid is not None and splits == 1:      # residual-stream GEMM: scratch for the wave-quantisation tail split
+    if splits == 1:      # scratch for the wave-quantisation tail split (residual-stream GEMMs) and the few-tiles / long-K split
         ws = _gemm_workspace(out.device)
         e.workspace, e.workspace_bytes = ws.data_ptr(), ws.numel()
     return e

@@ -66,6 +66,21 @@ def test_gemm_epilogues(ops, force_ctas):
     assert _relerr(o3, ref3) < 2e-5
 
 
+def test_gemm_few_tiles_long_k_split(ops):
+    """The text projection's shapes (a handful of [DET] rows padded to 128, 4096 -> 4096 -> 256): few tiles and 64 k-blocks are spread
+    over the SMs as split-K planes + fix-up; bf16 output with ReLU and fp32 output with bias, against fp32 torch."""
+    M, K = 128, 4096
+    a = _rand((M, K), 51, dtype=torch.bfloat16)
+    w0, b0 = _rand((4096, K), 52, 1 / math.sqrt(K), dtype=torch.bfloat16), _rand((4096,), 53)
+    h = torch.empty(M, 4096, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w0, h, bias=b0, act="relu")
+    assert _relerr(h.float(), F.relu(a.float() @ w0.float().t() + b0)) < 6e-3
+    w2, b2 = _rand((256, K), 54, 1 / math.sqrt(K), dtype=torch.bfloat16), _rand((256,), 55)
+    o = torch.empty(M, 256, device="cuda", dtype=torch.float32)
+    ops.gemm(h, w2, o, bias=b2)
+    assert _relerr(o, h.float() @ w2.float().t() + b2) < 2e-5
+
+
 def test_gemm_tail_split(ops):
     """Wave-quantisation tail: with 12 CTA pairs, 6 m-blocks x 3 n-blocks = 18 tiles leave 6 for a second wave, so the last two
     m-blocks are computed as split-K partial planes + fix-up kernel (long-K problems only); the result must equal the plain schedule
