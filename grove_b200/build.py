@@ -23,20 +23,31 @@ def _stale(out, deps):
 def build(verbose: bool = False, force: bool = False) -> str:
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
     hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tmem_ldst.cuh"), os.path.join(CSRC, "mma_sync.cuh"), os.path.join(ROOT, "include", "grove_b200.h")]
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(HERE, "_build", src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [NVCC] + FLAGS + ["-c", s, "-o", o]
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            with open(o + ".log", "w") as f:
-                f.write(r.stdout + r.stderr)
+            jobs.append((src, [NVCC] + FLAGS + ["-c", s, "-o", o], o))
+
+    def compile_one(job):
+        src, cmd, o = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(o + ".log", "w") as f:
+            f.write(r.stdout + r.stderr)
+        return src, r
+
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:   # one nvcc per translation unit, in parallel
+            results = list(pool.map(compile_one, jobs))
+        for src, r in results:
             if verbose or r.returncode:
                 sys.stderr.write(r.stdout + r.stderr)
-            if r.returncode:
-                raise RuntimeError(f"nvcc failed on {src}")
+        failed = [src for src, r in results if r.returncode]
+        if failed:
+            raise RuntimeError(f"nvcc failed on {', '.join(failed)}")
     if force or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
