@@ -302,17 +302,24 @@ class GroundingBranch(nn.Module):
         dev = next(self.parameters()).device
         main = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
+        slots, slot_free = [None, None], [None, None]        # two persistent device staging sets: no allocator traffic in steady state
 
-        def upload(batch):
+        def upload(batch, k):
             with torch.cuda.stream(side):
-                t = tuple(x.to(dev, non_blocking=True) for x in batch)
+                if slot_free[k] is not None:
+                    side.wait_event(slot_free[k])            # the step that read this slot two batches ago has finished
+                cur = slots[k]
+                if cur is None or any(d.shape != x.shape or d.dtype != x.dtype for d, x in zip(cur, batch)):
+                    cur = slots[k] = tuple(torch.empty(x.shape, dtype=x.dtype, device=dev) for x in batch)
+                for d, x in zip(cur, batch):
+                    d.copy_(x, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(side)
-            return t, ev
+            return cur, ev
 
         it = iter(host_batches)
         try:
-            nxt = upload(next(it))
+            nxt = upload(next(it), 0)
         except StopIteration:
             return
         pending = None                                       # (pinned host result, event) of the previous batch
@@ -320,10 +327,9 @@ class GroundingBranch(nn.Module):
         while nxt is not None:
             (images, hidden, ids), ev = nxt
             main.wait_event(ev)
-            for x in (images, hidden, ids):
-                x.record_stream(main)
+            k = n_out & 1
             try:
-                nxt = upload(next(it))
+                nxt = upload(next(it), k ^ 1)
             except StopIteration:
                 nxt = None
             mask = self._create_det_token_mask(ids)
@@ -331,9 +337,11 @@ class GroundingBranch(nn.Module):
             b = torch.cat([x for v in boxes for x in v]).float()
             l = torch.cat([x for v in logits for x in v]).float()
             packed = torch.cat([b, l[:, None]], 1)
-            slot = pool[n_out & 1]                           # two pinned result buffers, alternated (cudaHostAlloc per step is slow)
-            if slot is None or slot.shape[0] < packed.shape[0]:
-                slot = pool[n_out & 1] = torch.empty((max(packed.shape[0], 1), 5 if not infer else packed.shape[1]), dtype=packed.dtype, pin_memory=True)
+            slot_free[k] = torch.cuda.Event()
+            slot_free[k].record(main)
+            slot = pool[k]                                   # two pinned result buffers, alternated (cudaHostAlloc per step is slow)
+            if slot is None or slot.shape[0] < packed.shape[0] or slot.shape[1] != packed.shape[1]:
+                slot = pool[k] = torch.empty((max(packed.shape[0], 1), packed.shape[1]), dtype=packed.dtype, pin_memory=True)
             host = slot[:packed.shape[0]]
             n_out += 1
             host.copy_(packed, non_blocking=True)
