@@ -90,6 +90,12 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;    // m-blocks of 128*CTAS rows
   const int num_tiles = tiles_mn * p.splits;
   const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
+  // Conv3d taps that look one frame before the first / after the last frame of an 8-frame group multiply by TMA's zero fill only:
+  // those k-blocks (a third of K for two frames in eight, 8 % of the adapter's MMA work and operand traffic) are skipped by the
+  // producer and the MMA issuer alike.  The first k-block of a range is always executed so that every accumulator is written.
+  // live k-blocks of a tile of frame-in-group ft: [lo, hi) (whole range unless ft is the first / last frame of its group)
+  auto conv_live_lo = [&](int ft) { return (p.conv == 1 && p.kt == 3 && ft == 0) ? 9 * p.kc_blocks : 0; };
+  auto conv_live_hi = [&](int ft) { return (p.conv == 1 && p.kt == 3 && ft == p.T - 1) ? 18 * p.kc_blocks : p.num_k_blocks; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -134,9 +140,12 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
           wtap = n_blk / p.cblocks_per_tap;
           wc0 = (n_blk % p.cblocks_per_tap) * BN + (int)cta_rank * Cfg::kBRows;
         }
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int live_lo = conv_live_lo(p.conv == 1 ? f % p.T : 1), live_hi = conv_live_hi(p.conv == 1 ? f % p.T : 1);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (kb != kb_begin && (kb < live_lo || kb >= live_hi)) continue;
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1u;
+          ++it;
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
@@ -203,9 +212,13 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
         const uint32_t d_tmem = tmem_base + acc * BN;
         const int sp = tile / tiles_mn;
         const int kb_begin = sp * p.kb_per_split, kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int ft = p.conv == 1 ? (((p.m_blk0 + (tile % tiles_mn) / p.num_n_blocks) * CTAS) / p.tiles_per_frame) % p.T : 1;
+        const int live_lo = conv_live_lo(ft), live_hi = conv_live_hi(ft);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (kb != kb_begin && (kb < live_lo || kb >= live_hi)) continue;
           const int s = it % Cfg::kStages;
           const uint32_t ph = (it / Cfg::kStages) & 1u;
+          ++it;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           if (elect_one()) {
@@ -218,16 +231,16 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
               if (CTAS == 2) tc_mma_f16_cg2(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0);
               else           tc_mma_f16(d_tmem, da, db, idesc, ((kb - kb_begin) | k) != 0);
             }
-            if (CTAS == 2) {
-              tc_commit_cg2(empty_bar(s), 3);                                   // frees the slot in both CTAs
-              if (kb == kb_end - 1) tc_commit_cg2(tfull_bar(acc), 3);   // accumulators complete in both CTAs
-            } else {
-              tc_commit(empty_bar(s));
-              if (kb == kb_end - 1) tc_commit(tfull_bar(acc));
-            }
+            if (CTAS == 2) tc_commit_cg2(empty_bar(s), 3);                      // frees the slot in both CTAs
+            else tc_commit(empty_bar(s));
           }
           __syncwarp();
         }
+        if (elect_one()) {                                                      // accumulators complete (in both CTAs)
+          if (CTAS == 2) tc_commit_cg2(tfull_bar(acc), 3);
+          else tc_commit(tfull_bar(acc));
+        }
+        __syncwarp();
       }
     }
   } else {
