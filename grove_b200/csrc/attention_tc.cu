@@ -144,9 +144,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
     // whole 128 B/clk shared-memory bandwidth of the SM and made Q.K^T run at half rate next to the TMA writes and the softmax's traffic.
     auto issue_s = [&](uint32_t b_smem, bool q_tmem) {
       const uint32_t sb = sit & 1u;
-#ifndef GROVE_ATT_NOFENCE
       tc_fence_after();
-#endif
       if (elect_one()) {
         if (q_tmem) {
 #pragma unroll
@@ -179,11 +177,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       PROBE(1000 + 3 * kit);
       mbar_wait2(bar(K_FULL + s), (kit / kKStages) & 1u, bar(S_EMPTY + (sit & 1u)), s_empty_par());
       PROBE(1001 + 3 * kit);
-#ifdef GROVE_ATT_QSS
-      issue_s(sK + s * TS, false);
-#else
       issue_s(sK + s * TS, true);
-#endif
       PROBE(4000 + 3 * kit);
       if (elect_one()) { tc_commit(bar(K_EMPTY + s)); PROBE(4001 + 3 * kit); tc_commit(bar(S_FULL + (sit & 1u))); PROBE(4002 + 3 * kit); }
       __syncwarp();
@@ -199,9 +193,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       PROBE(1300 + 3 * b);
       mbar_wait2(bar(V_FULL + v), (vit / kVStages) & 1u, bar(P_FULL + pb), (b >> 1) & 1u);
       PROBE(1301 + 3 * b);
-#ifndef GROVE_ATT_NOFENCE
       tc_fence_after();
-#endif
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
@@ -372,11 +364,8 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
           const float e0 = __uint_as_float(rr[cc][j]) + off;
           const float e1 = __uint_as_float(rr[cc][j + 1]) + off;
           asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
-#ifndef GROVE_ATT_NOPOLY
-          if (j & 2) p1 = ex2_fma(e1);
-          else
-#endif
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
+          if (j & 2) p1 = ex2_fma(e1);                    // one exponential in four on the FMA pipe
+          else asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
           lsum += p0 + p1;
           pk[j >> 1] = pack_bf16(p0, p1);
         }

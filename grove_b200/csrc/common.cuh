@@ -110,7 +110,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // Wait with a watchdog: a protocol bug must trap (launch error reported to the caller) instead of
 // hanging the GPU.  try_wait suspends in hardware, so the poll loop is cheap.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-#ifdef GROVE_MBAR_SPIN
+#ifdef GROVE_MBAR_SPIN   // A/B variant without the hardware-sleep hint: measured identical, kept for re-measurement
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
