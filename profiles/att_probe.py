@@ -1,3 +1,5 @@
+"""Timeline of one CTA of the global-attention kernel (build with GROVE_NVCC_EXTRA=-DGROVE_ATT_PROBE python -m grove_b200.build -f):
+clock64 at every hand-off of the issuing warp and of three softmax warps, per 128-key block."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
@@ -22,9 +24,6 @@ r = lambda x: int(x - t0)
 print("MMA qk [pre-wait, post-wait, issued] per kit:")
 for k in range(32):
     print("  ", k, [r(a[1000 + 3 * k + i]) for i in range(3)])
-print("MMA qk detail [mmas issued, commit0, commit1]:")
-for k in range(32):
-    print("  ", k, [r(a[4000 + 3 * k + i]) for i in range(3)])
 print("MMA pv [pre-wait, post-wait, issued]:")
 for b in range(32):
     print("  ", b, [r(a[1300 + 3 * b + i]) for i in range(3)])

@@ -1,3 +1,5 @@
+"""Timeline of one CTA of the window-attention kernel (build with GROVE_NVCC_EXTRA=-DGROVE_WIN_PROBE python -m grove_b200.build -f):
+clock64 at every hand-off of the issuing warp and of three softmax warps, last 8 units of the CTA."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
