@@ -27,8 +27,8 @@ VIDEOS = 1   # videos per GPU per step (config 3: 2)
 METRIC, UNIT = "grounding_path_frames_per_s", "frames/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch of the dominant kernel (qkv GEMM, M=32768 N=2304 K=768),
 # from the `ncu --set full` capture summarised in profiles/r1_ncu_full_summary.txt (algorithmic bytes of that launch: 205 MB)
-NCU_TRAFFIC_BYTES = 153403392
-NCU_TRAFFIC_NOTE = "qkv GEMM launch (M=32768,N=2304,K=768): 53.9 MB read + 99.5 MB written vs 205 MB algorithmic (profiles/r1_ncu_full_summary.txt)"
+NCU_TRAFFIC_BYTES = 152701696
+NCU_TRAFFIC_NOTE = "qkv GEMM launch (M=32768,N=2304,K=768): 53.9 MB read + 98.8 MB written vs 205 MB algorithmic (profiles/r1_ncu_full_summary.txt)"
 
 
 def useful_flops_per_frame(D, depth, n_glob, G):
