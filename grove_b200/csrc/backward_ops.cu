@@ -102,26 +102,28 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int split
 // XMODE 0: u = x (+ r), both fp32 [rows, D].   XMODE 1: u = bf16 keys[src_of[row / N] * N + row % N] + fp32 delta[row]  (norm4).
 // dx_out = (dx_in ? dx_in : 0) + dLN(dy);  optional bf16 copy;  optional d gamma / d beta accumulated with atomics.
 constexpr int kLnMaxV = 10;  // D <= 1280
-template <int XMODE, bool DY_F32>
+// NV = D / 128 and PG (d gamma / d beta wanted) are compile-time: with run-time bounds every array was sized for D = 1280 and the
+// parameter-gradient accumulators were always live -- 187 registers, one 8-warp CTA per SM, 280 us per call (~1 TB/s) on an HBM-bound op.
+template <int XMODE, bool DY_F32, int NV, bool PG>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ x, const float* __restrict__ r, const int* __restrict__ src_of, int N,
                                                             const float* __restrict__ gamma, const void* __restrict__ dy,
                                                             const float* __restrict__ dx_in, float* __restrict__ dx_out,
                                                             __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             long long rows, int D, float eps) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int nv = D / 128;
-  float4 ag[kLnMaxV], ab[kLnMaxV];
+  constexpr int nv = NV;
+  float4 ag[PG ? NV : 1], ab[PG ? NV : 1];
 #pragma unroll
-  for (int i = 0; i < kLnMaxV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < (PG ? NV : 1); ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = warp0; row < rows; row += nwarps) {
-    float4 u[kLnMaxV], g[kLnMaxV];
+    float4 u[NV], g[NV];
     float s = 0.f;
     size_t kbase = 0;
     if (XMODE == 1) kbase = ((size_t)(src_of ? src_of[row / N] : row / N) * N + row % N) * D;
 #pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i)
-      if (i < nv) {
+    for (int i = 0; i < NV; ++i)
+      {
         const int c4 = i * 32 + lane;
         if (XMODE == 0) {
           u[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + (size_t)row * D)[c4];
@@ -140,16 +142,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
     const float mean = warp_sum(s) / (float)D;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i)
-      if (i < nv) {
+    for (int i = 0; i < NV; ++i)
+      {
         u[i].x -= mean; u[i].y -= mean; u[i].z -= mean; u[i].w -= mean;
         q += u[i].x * u[i].x + u[i].y * u[i].y + u[i].z * u[i].z + u[i].w * u[i].w;
       }
     const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i)
-      if (i < nv) {
+    for (int i = 0; i < NV; ++i)
+      {
         const int c4 = i * 32 + lane;
         float4 d;
         if (DY_F32) {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
           d = make_float4(p0.x, p0.y, p1.x, p1.y);
         }
         u[i].x *= rstd; u[i].y *= rstd; u[i].z *= rstd; u[i].w *= rstd;   // xhat
-        if (dgamma) {
+        if (PG) {
           ag[i].x += d.x * u[i].x; ag[i].y += d.y * u[i].y; ag[i].z += d.z * u[i].z; ag[i].w += d.w * u[i].w;
           ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
         }
@@ -171,8 +173,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
       }
     const float mg = warp_sum(sg) / (float)D, mgx = warp_sum(sgx) / (float)D;
 #pragma unroll
-    for (int i = 0; i < kLnMaxV; ++i)
-      if (i < nv) {
+    for (int i = 0; i < NV; ++i)
+      {
         const int c4 = i * 32 + lane;
         float4 o = make_float4(rstd * (g[i].x - mg - u[i].x * mgx), rstd * (g[i].y - mg - u[i].y * mgx), rstd * (g[i].z - mg - u[i].z * mgx),
                                rstd * (g[i].w - mg - u[i].w * mgx));
@@ -184,13 +186,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
         if (dx_bf16) reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * D)[c4] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
       }
   }
-  if (dgamma) {
+  if (PG) {
     __shared__ float red[8][32 * 4];
-    for (int i = 0; i < nv; ++i) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
 #pragma unroll
-      for (int j = 0; j < kLnMaxV; ++j)
-        if (j == i) { a = ag[j]; b = ab[j]; }
+    for (int i = 0; i < (PG ? NV : 0); ++i) {
+      const float4 a = ag[i], b = ab[i];
       for (int pass = 0; pass < 2; ++pass) {
         const float4 v = pass ? b : a;
         __syncthreads();
@@ -489,12 +489,17 @@ extern "C" int grove_layernorm_bwd(const void* x, const float* r, const int* src
   GROVE_CHECK_ARG(x && gamma && dy && rows > 0 && D % 128 == 0 && D <= 128 * kLnMaxV);
   GROVE_CHECK_ARG((dx_out || dx_bf16) && ((dgamma == nullptr) == (dbeta == nullptr)));
   GROVE_CHECK_ARG(!x_is_keys_bf16 || (r && N > 0));
-  const int grid = bw_grid(rows * 32, 256, 4);
+  const int grid = bw_grid(rows * 32, 256, 8);
   auto* o16 = (__nv_bfloat16*)dx_bf16;
-#define LNB(XM, DF) layernorm_bwd_kernel<XM, DF><<<grid, 256, 0, stream>>>(x, r, src_of, N, gamma, dy, dx_in, dx_out, o16, dgamma, dbeta, rows, D, eps)
+#define LNB3(XM, DF, NVV, PGG) layernorm_bwd_kernel<XM, DF, NVV, PGG><<<grid, 256, 0, stream>>>(x, r, src_of, N, gamma, dy, dx_in, dx_out, o16, dgamma, dbeta, rows, D, eps)
+#define LNB2(XM, DF, NVV) do { if (dgamma) LNB3(XM, DF, NVV, true); else LNB3(XM, DF, NVV, false); } while (0)
+#define LNB(XM, DF) do { switch (D / 128) { case 2: LNB2(XM, DF, 2); break; case 6: LNB2(XM, DF, 6); break; case 8: LNB2(XM, DF, 8); break; \
+                                            case 10: LNB2(XM, DF, 10); break; default: grove_set_error("grove_layernorm_bwd: D = %d is not built (256, 768, 1024, 1280)", D); return GROVE_ERR_UNSUPPORTED; } } while (0)
   if (x_is_keys_bf16) { if (dy_is_f32) LNB(1, true); else LNB(1, false); }
   else { if (dy_is_f32) LNB(0, true); else LNB(0, false); }
 #undef LNB
+#undef LNB2
+#undef LNB3
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
