@@ -549,17 +549,30 @@ __global__ void __launch_bounds__(256) relpos_kernel(const bf16_t* __restrict__ 
   }
   __syncthreads();
   if (MODE == 0) {
-    for (int i = tid; i < 64 * 2 * S; i += 256) {
-      const int r = i / (2 * S), c = i % (2 * S);
+    // one thread = four bias columns (c, c + S/2, c + S, c + 3S/2) of one query: q[d] is read once for four dot products (the kernel is
+    // bound by shared-memory loads: 5 instead of 8 per four multiply-adds); neighbouring lanes keep neighbouring table rows (no conflicts)
+    static_assert((2 * S) % 4 == 0, "bias columns come in groups of four");
+    constexpr int CQ = 2 * S / 4;
+    for (int i = tid; i < 64 * CQ; i += 256) {
+      const int r = i / CQ, c0 = i % CQ;
       const int tok = (int)((row0 + r) % N), gy = tok / G, gx = tok % G;
       const int ly = WIN ? gy % S : gy, lx = WIN ? gx % S : gx;
-      const int idx = c < S ? (ly - c + S - 1) : TR + (lx - (c - S) + S - 1);
       const float* q = sX + r * HP;
-      const float* t = sT + idx * HP;
-      float a = 0.f;
+      const float* t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + j * CQ;
+        t[j] = sT + (c < S ? (ly - c + S - 1) : TR + (lx - (c - S) + S - 1)) * HP;
+      }
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
-      for (int d = 0; d < HD; ++d) a += q[d] * t[d];
-      rel[((size_t)(row0 + r) * heads + h) * (2 * S) + c] = a;
+      for (int d = 0; d < HD; ++d) {
+        const float qd = q[d];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] += qd * t[j][d];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rel[((size_t)(row0 + r) * heads + h) * (2 * S) + c0 + j * CQ] = a[j];
     }
   } else {
     for (int i = tid; i < 64 * HD; i += 256) {
