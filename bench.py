@@ -191,11 +191,11 @@ def run_reference(args, rank):
         s, _ = cpu_reference_step(sd, cfg, inputs)
         tot += s
     v = FRAMES * args.steps / tot
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    _emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                       "data": "synthetic", "config": workload_config(args.gpus),
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": SAMPLE_DESC},
-                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 def workload_config(n):
@@ -206,6 +206,25 @@ def workload_config(n):
             "image_size": IMG, "sharding": f"by video, {n} GPU(s), no data-path collective",
             "l2": "4 rotating input sets (220 MB) and a ~3 GB per-step activation working set, both larger than the 126 MB L2",
             "launch": "encoder block stack replayed as one CUDA graph (image_encoder.enable_cuda_graphs), decoder launched kernel by kernel"}
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route everything libraries write to fd 1 (NCCL prints its version banner there) to stderr: stdout carries the one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------ our arm
@@ -226,6 +245,7 @@ def main():
         args.no_cpu_baseline = True
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -370,7 +390,7 @@ def main():
             cpu_sd = {k: v.float() for k, v in sd.items()}
             sec, _ = cpu_reference_step(cpu_sd, cfg, tuple(t.clone() for t in host_sets[0]))
             line["cpu_baseline"] = {"value": FRAMES / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": SAMPLE_DESC}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
