@@ -48,12 +48,16 @@ SIGNATURES = {
     "grove_decoder_i2t_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_decoder_keys_add_ln": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "grove_small_linear_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "grove_decoder_heads_fwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_token_self_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_add_layernorm_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
     "grove_box_postprocess": [_P, _P, _P, _F, _P, _P, _I, _P],
     "grove_box_losses_fwd": [_P, _P, _P, _P, _P, _P, _I, _P],
     "grove_box_iou": [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P],
     "grove_greedy_match": [_P, _P, _D, _D, _P, _P, _I, _I, _P],
+    "grove_center_in_box": [_P, _P, _P, _I, _P],
+    "grove_viou_decisions": [_P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "grove_val_metrics": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "grove_resize_rows_u8": [_P, _P, _P, _P, _I, _LL, _I, _I, _P],
     "grove_frames_to_patches_u8": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P],
     # training step (backward pass)
@@ -93,7 +97,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if l.grove_abi_version() != 3:
+        if l.grove_abi_version() != 4:
             raise RuntimeError("libgrove_b200.so ABI version mismatch; rebuild")
         _lib = l
     return _lib

@@ -623,14 +623,13 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
   const int smem_q = 128 + 6 * TILEB + (2 * 64 * RS + 64 * 65) * 4 + 64 * 4;
   const int smem_qf = 128 + 6 * TILEB + 64 * (S + 1) * 4;
   const int smem_kv = 128 + 6 * TILEB + (2 * 64 * (GFAST ? S + 4 : RS) + 256) * 4 + 64 * 4;
-  static bool attr = false;
-  if (!attr) {
+  static GrovePerDeviceOnce attr;
+  if (attr.first_time()) {
     cudaFuncSetAttribute(relpos_kernel<S, HD, WIN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rel);
     cudaFuncSetAttribute(relpos_kernel<S, HD, WIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rel);
     cudaFuncSetAttribute(attn_bwd_q_kernel<S, HD, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_q);
     cudaFuncSetAttribute(attn_bwd_kv_kernel<S, HD, WIN, GFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv);
     if constexpr (GFAST) cudaFuncSetAttribute(attn_bwd_q_global_kernel<S, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_qf);
-    attr = true;
   }
   const dim3 grid_rel((unsigned)(M / 64), heads);
   relpos_kernel<S, HD, WIN, 0><<<grid_rel, 256, smem_rel, st>>>(qkv, Rh, Rw, rel, nullptr, nullptr, nullptr, G, heads);

@@ -124,7 +124,8 @@ __global__ void box_iou_kernel(const T* __restrict__ a, int lda, const T* __rest
 __global__ void greedy_match_kernel(double* iou, double* sim, double iou_thr, double sim_thr, int* pairs, int* count, int n, int m) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int c = 0;
-  while (n > 0 && m > 0) {
+  const int cap = n < m ? n : m;          // a match zeroes its row and column: at most min(n, m) pairs carry information
+  while (n > 0 && m > 0 && c < cap) {     // (the reference loops forever for thresholds <= 0; here the loop stops before writing pair cap)
     int best = 0;
     for (int k = 1; k < n * m; ++k)
       if (iou[k] > iou[best]) best = k;  // first maximum in row-major order, like np.argmax
@@ -133,9 +134,83 @@ __global__ void greedy_match_kernel(double* iou, double* sim, double iou_thr, do
     pairs[2 * c] = bi; pairs[2 * c + 1] = bj; ++c;
     for (int j = 0; j < m; ++j) { iou[bi * m + j] = 0; sim[bi * m + j] = 0; }
     for (int i = 0; i < n; ++i) { iou[i * m + bj] = 0; sim[i * m + bj] = 0; }
-    if (c >= (n < m ? n : m) + 1) break;  // cannot happen for thresholds > 0; guards thr <= 0
   }
   *count = c;
+}
+
+
+// ---------------------------------------------------------------- decision utilities of the eval / validation loops
+// centre-in-box (eval_youcookinteractions.py:43-48): cx = (x1 + x2) / 2, cy = (y1 + y2) / 2 in Python floats (double);
+// correct iff xtl <= cx <= xbr and ytl <= cy <= ybr (INCLUSIVE).  A NaN coordinate fails every comparison (the reference skips such rows).
+__global__ void center_in_box_kernel(const double* __restrict__ pred, const double* __restrict__ gt, uint8_t* __restrict__ correct, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double cx = __ddiv_rn(__dadd_rn(pred[4 * i], pred[4 * i + 2]), 2.0), cy = __ddiv_rn(__dadd_rn(pred[4 * i + 1], pred[4 * i + 3]), 2.0);
+  const double xtl = gt[4 * i], ytl = gt[4 * i + 1], xbr = gt[4 * i + 2], ybr = gt[4 * i + 3];
+  correct[i] = (xtl <= cx && cx <= xbr && ytl <= cy && cy <= ybr) ? 1 : 0;
+}
+
+// video IoU (eval_vidstg.py:157-178): per ground-truth frame iou = np_box_iou(pred, gt) if pred.any() else 0; gt_viou = (sum in frame
+// order, Python float) / max(n, 1); recall flag per threshold = gt_viou > thr (STRICT).  One thread: n is tens, the order is the contract.
+__global__ void viou_kernel(const double* __restrict__ pred, const double* __restrict__ gt, const double* __restrict__ thr, int n, int k,
+                            double* __restrict__ ious, double* __restrict__ viou, uint8_t* __restrict__ over) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double a0 = pred[4 * i], a1 = pred[4 * i + 1], a2 = pred[4 * i + 2], a3 = pred[4 * i + 3];
+    double iou = 0.0;
+    if (a0 != 0.0 || a1 != 0.0 || a2 != 0.0 || a3 != 0.0) {     // ndarray.any(): NaN counts as non-zero
+      const double b0 = gt[4 * i], b1 = gt[4 * i + 1], b2 = gt[4 * i + 2], b3 = gt[4 * i + 3];
+      const double area1 = __dmul_rn(__dsub_rn(a2, a0), __dsub_rn(a3, a1)), area2 = __dmul_rn(__dsub_rn(b2, b0), __dsub_rn(b3, b1));
+      const double w = tmax(__dsub_rn(tmin(a2, b2), tmax(a0, b0)), 0.0), h = tmax(__dsub_rn(tmin(a3, b3), tmax(a1, b1)), 0.0);
+      const double inter = __dmul_rn(w, h);
+      iou = __ddiv_rn(inter, __dsub_rn(__dadd_rn(area1, area2), inter));
+    }
+    ious[i] = iou;
+    acc = __dadd_rn(acc, iou);
+  }
+  const double v = __ddiv_rn(acc, (double)(n > 1 ? n : 1));
+  *viou = v;
+  for (int j = 0; j < k; ++j) over[j] = v > thr[j] ? 1 : 0;
+}
+
+// validation metrics (train.py:826-835): GIoU loss sum of the selected predictions against their ground truth ON THE COORDINATES AS GIVEN
+// (the reference feeds cxcywh predictions straight into torchvision's xyxy GIoU -- reproduced, not corrected) and the number of
+// instances whose thresholded objectness (sigmoid(logit) > 0.5) equals the integer label.
+__device__ __forceinline__ float giou_loss_xyxy(const float* p, const float* q) {
+  const float x1 = p[0], y1 = p[1], x2 = p[2], y2 = p[3], x1g = q[0], y1g = q[1], x2g = q[2], y2g = q[3];
+  const float xk1 = fmaxf(x1, x1g), yk1 = fmaxf(y1, y1g), xk2 = fminf(x2, x2g), yk2 = fminf(y2, y2g);
+  float inter = 0.f;
+  if (yk2 > yk1 && xk2 > xk1) inter = __fmul_rn(__fsub_rn(xk2, xk1), __fsub_rn(yk2, yk1));
+  const float uni = __fsub_rn(__fadd_rn(__fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1)), __fmul_rn(__fsub_rn(x2g, x1g), __fsub_rn(y2g, y1g))), inter);
+  const float iou = __fdiv_rn(inter, __fadd_rn(uni, 1e-7f));
+  const float xc1 = fminf(x1, x1g), yc1 = fminf(y1, y1g), xc2 = fmaxf(x2, x2g), yc2 = fmaxf(y2, y2g);
+  const float area_c = __fmul_rn(__fsub_rn(xc2, xc1), __fsub_rn(yc2, yc1));
+  const float miou = __fsub_rn(iou, __fdiv_rn(__fsub_rn(area_c, uni), __fadd_rn(area_c, 1e-7f)));
+  return __fsub_rn(1.f, miou);
+}
+
+__global__ void __launch_bounds__(256) val_metrics_kernel(const float* __restrict__ boxes, const float* __restrict__ logits, const float* __restrict__ gt,
+                                                          const uint8_t* __restrict__ sel, const int* __restrict__ labels, double* __restrict__ giou_sum,
+                                                          int* __restrict__ acc, float* __restrict__ giou_each, int B) {
+  __shared__ double red[256];
+  __shared__ int redi[256];
+  double g = 0.0;
+  int c = 0;
+  for (int i = threadIdx.x; i < B; i += 256) {
+    float gi = 0.f;
+    if (sel[i]) { gi = giou_loss_xyxy(boxes + 4 * i, gt + 4 * i); g += (double)gi; }
+    if (giou_each) giou_each[i] = gi;
+    const float sg = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-logits[i])));
+    c += ((sg > 0.5f ? 1 : 0) == labels[i]) ? 1 : 0;
+  }
+  red[threadIdx.x] = g; redi[threadIdx.x] = c;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { red[threadIdx.x] += red[threadIdx.x + s]; redi[threadIdx.x] += redi[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *giou_sum = red[0]; *acc = redi[0]; }
 }
 
 }  // namespace grove
@@ -180,6 +255,35 @@ extern "C" int grove_greedy_match(double* iou, double* sim, double iou_thr, doub
   GROVE_CHECK_ARG(count && n >= 0 && m >= 0);
   GROVE_CHECK_ARG((n == 0 || m == 0) || (iou && sim && pairs));
   greedy_match_kernel<<<1, 32, 0, stream>>>(iou, sim, iou_thr, sim_thr, pairs, count, n, m);
+  grove_count_launch();
+  GROVE_CHECK_LAUNCH();
+  return GROVE_OK;
+}
+
+extern "C" int grove_center_in_box(const double* pred, const double* gt, uint8_t* correct, int n, cudaStream_t stream) {
+  GROVE_CHECK_ARG(n >= 0);
+  if (n == 0) return GROVE_OK;
+  GROVE_CHECK_ARG(pred && gt && correct);
+  center_in_box_kernel<<<(n + 127) / 128, 128, 0, stream>>>(pred, gt, correct, n);
+  grove_count_launch();
+  GROVE_CHECK_LAUNCH();
+  return GROVE_OK;
+}
+
+extern "C" int grove_viou_decisions(const double* pred, const double* gt, const double* thr, int n, int k, double* ious, double* viou,
+                                    uint8_t* over, cudaStream_t stream) {
+  GROVE_CHECK_ARG(n >= 0 && k >= 0 && viou && (n == 0 || (pred && gt && ious)) && (k == 0 || (thr && over)));
+  viou_kernel<<<1, 32, 0, stream>>>(pred, gt, thr, n, k, ious, viou, over);
+  grove_count_launch();
+  GROVE_CHECK_LAUNCH();
+  return GROVE_OK;
+}
+
+extern "C" int grove_val_metrics(const float* boxes, const float* logits, const float* gt, const uint8_t* sel, const int* labels, double* giou_sum,
+                                 int* acc, float* giou_each, int B, cudaStream_t stream) {
+  GROVE_CHECK_ARG(giou_sum && acc && B >= 0);
+  GROVE_CHECK_ARG(B == 0 || (boxes && logits && gt && sel && labels));
+  val_metrics_kernel<<<1, 256, 0, stream>>>(boxes, logits, gt, sel, labels, giou_sum, acc, giou_each, B);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;

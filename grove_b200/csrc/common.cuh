@@ -29,6 +29,24 @@
 void grove_set_error(const char* fmt, ...);
 void grove_count_launch(int n = 1);
 
+// Function attributes (max dynamic shared memory) and the SM count belong to a DEVICE, not to the process: one flag bit per device
+// ordinal, set atomically, so the first launch on every GPU of a multi-device process configures that GPU's copy of the kernel.
+struct GrovePerDeviceOnce {
+  unsigned long long bits = 0;
+  bool first_time() {   // true exactly once per device (racing callers may both see true: setting an attribute twice is harmless)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    const unsigned long long prev = __atomic_fetch_or(&bits, bit, __ATOMIC_ACQ_REL);
+    return !(prev & bit);
+  }
+  void reset_current() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    __atomic_fetch_and(&bits, ~(1ull << (dev & 63)), __ATOMIC_ACQ_REL);
+  }
+};
+
 namespace grove {
 
 constexpr int kNumSMs = 148;

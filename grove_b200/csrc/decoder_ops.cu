@@ -325,6 +325,78 @@ __global__ void __launch_bounds__(256) add_layernorm_f32_kernel(const float* __r
   }
 }
 
+
+// ---------------------------------------------------------------- final out-proj + LayerNorm + heads for the prompt token -> packed record
+// One CTA (256 threads) per instance; only token `tok` (index 1 + num_mask_tokens) feeds the heads (mask_decoder.py:192):
+//   hs   = LN_final(queries[b,tok,:] + out_proj(att[b,tok,:]))        (transformer.py:99-104)
+//   box  = sigmoid(W2 relu(W0 hs + b0) + b2),  logit = Wt hs + bt      (mask_decoder.py:80-85, 198-203)
+//   rec[b, 0:4] = box (cx, cy, w, h),  rec[b, 4] = logit               (the record the config-5 all-gather ships)
+// A warp owns 32 consecutive outputs of each matrix-vector product; its lanes split K with float4 loads (coalesced weight rows).
+template <int K>
+__device__ __forceinline__ float warp_dot(const float* __restrict__ w, const float* __restrict__ xs, int lane) {
+  float a = 0.f;
+#pragma unroll
+  for (int kk = lane * 4; kk < K; kk += 128) {
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + kk));
+    const float4 xv = *reinterpret_cast<const float4*>(xs + kk);
+    a += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+  }
+  return warp_sum(a);
+}
+
+__global__ void __launch_bounds__(256) decoder_heads_kernel(const float* __restrict__ queries, const float* __restrict__ att, const float* __restrict__ Wo,
+                                                            const float* __restrict__ bo, const float* __restrict__ lg, const float* __restrict__ lb,
+                                                            float eps, const float* __restrict__ W0, const float* __restrict__ b0,
+                                                            const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ Wt,
+                                                            const float* __restrict__ bt, float* __restrict__ rec, float* __restrict__ hs_out, int T,
+                                                            int tok) {
+  constexpr int C = 256, CI = 128;
+  __shared__ __align__(16) float xs[C], hs[C], h1[C];
+  __shared__ float red[2][8];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t row = (size_t)b * T + tok;
+  if (tid < CI) xs[tid] = att[row * CI + tid];
+  __syncthreads();
+  for (int j = warp * 32; j < warp * 32 + 32; ++j) {
+    const float d = warp_dot<CI>(Wo + (size_t)j * CI, xs, lane);
+    if (lane == 0) h1[j] = d + bo[j] + queries[row * C + j];
+  }
+  __syncthreads();
+  // LayerNorm over the 256 channels (two-pass, like nn.LayerNorm)
+  const float v = h1[tid];
+  float s = warp_sum(v);
+  if (lane == 0) red[0][warp] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mean += red[0][i];
+  mean *= (1.f / C);
+  const float dv = v - mean;
+  s = warp_sum(dv * dv);
+  if (lane == 0) red[1][warp] = s;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) var += red[1][i];
+  const float y = dv * rsqrtf(var * (1.f / C) + eps) * lg[tid] + lb[tid];
+  hs[tid] = y;
+  if (hs_out) hs_out[(size_t)b * C + tid] = y;
+  __syncthreads();
+  for (int j = warp * 32; j < warp * 32 + 32; ++j) {
+    const float d = warp_dot<C>(W0 + (size_t)j * C, hs, lane);
+    if (lane == 0) xs[j] = fmaxf(d + b0[j], 0.f);     // xs is free again: CI <= C
+  }
+  __syncthreads();
+  if (warp < 4) {
+    const float d = warp_dot<C>(W2 + (size_t)warp * C, xs, lane);
+    if (lane == 0) rec[(size_t)b * 5 + warp] = 1.f / (1.f + expf(-(d + b2[warp])));
+  } else if (warp == 4) {
+    float d = 0.f;
+    if (Wt) d = warp_dot<C>(Wt, hs, lane) + bt[0];
+    if (lane == 0) rec[(size_t)b * 5 + 4] = d;
+  }
+}
+
 }  // namespace grove
 using namespace grove;
 
@@ -395,11 +467,9 @@ extern "C" int grove_small_linear_f32(const float* x, const float* W, const floa
                                       cudaStream_t stream) {
   GROVE_CHECK_ARG(x && W && y && R > 0 && N > 0 && K > 0 && K % 4 == 0 && K <= 4096 && act >= 0 && act <= 3);
   const int smem = 8 * K * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static GrovePerDeviceOnce attr;
+  if (attr.first_time())
     cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096 * (int)sizeof(float));
-    attr = true;
-  }
   small_linear_kernel<<<dim3((N + 15) / 16, (R + 7) / 8), 256, smem, stream>>>(x, W, b, resid, y, R, N, K, act);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
@@ -420,6 +490,18 @@ extern "C" int grove_add_layernorm_f32(const float* x, const float* r, const flo
   GROVE_CHECK_ARG(x && g && b && y && R > 0 && C % 32 == 0 && C <= 1024);
   GROVE_CHECK_ARG((y2 == nullptr) == (add2 == nullptr));
   add_layernorm_f32_kernel<<<(R + 7) / 8, 256, 0, stream>>>(x, r, g, b, y, add2, y2, R, C, eps);
+  grove_count_launch();
+  GROVE_CHECK_LAUNCH();
+  return GROVE_OK;
+}
+
+extern "C" int grove_decoder_heads_fwd(const float* queries, const float* att, const float* Wo, const float* bo, const float* ln_g, const float* ln_b,
+                                       float eps, const float* W0, const float* b0, const float* W2, const float* b2, const float* Wt, const float* bt,
+                                       float* records, float* hs_out, int B, int T, int tok, int C, int CI, cudaStream_t stream) {
+  GROVE_CHECK_ARG(queries && att && Wo && bo && ln_g && ln_b && W0 && b0 && W2 && b2 && records && B > 0 && T > 0 && tok >= 0 && tok < T);
+  GROVE_CHECK_ARG((Wt == nullptr) == (bt == nullptr));
+  if (C != 256 || CI != 128) { grove_set_error("decoder heads are built for transformer_dim 256 / cross-attention width 128 (got %d / %d)", C, CI); return GROVE_ERR_UNSUPPORTED; }
+  decoder_heads_kernel<<<B, 256, 0, stream>>>(queries, att, Wo, bo, ln_g, ln_b, eps, W0, b0, W2, b2, Wt, bt, records, hs_out, T, tok);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;

@@ -609,25 +609,30 @@ int make_tmap_bf16_nd(CUtensorMap* m, const void* base, int rank, const uint64_t
   return make_tmap_bf16(m, base, rank, dims, box, box[0] == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-static int g_num_sms = 0;
+static int g_num_sms[64] = {0};   // per device ordinal
 static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = kNumSMs;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = g_num_sms[dev & 63];
+  if (!n) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n = v > 0 ? v : kNumSMs;
   }
-  return g_num_sms;
+  return n;
 }
 
 template <int BN, int CTAS, int EPI = 0>
 static int launch_gemm(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb, int max_ctas, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static GrovePerDeviceOnce attr_set;
+  if (attr_set.first_time()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, CTAS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-    attr_set = true;
+    if (e != cudaSuccess) {
+      attr_set.reset_current();
+      grove_set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return GROVE_ERR_CUDA;
+    }
   }
   int grid = p.num_m_blocks * p.num_n_blocks * p.splits * CTAS;
   int cap = max_ctas > 0 ? max_ctas : num_sms();

@@ -6,6 +6,7 @@ the whole forward onto the CUDA library.  Calling one of them on its own is a ca
 """
 from __future__ import annotations
 
+import functools
 from typing import Type
 
 import torch
@@ -61,3 +62,36 @@ def f32(t):
 
 def bf16(t):
     return t.detach().to(torch.bfloat16).contiguous()
+
+
+_WARNED_NO_AUTOGRAD = set()
+
+
+def warn_no_autograd(what: str, params, *inputs) -> None:
+    """The forward entry points run the CUDA library under no_grad and return tensors without a grad_fn.  The reference trains the adapters,
+    the mask decoder and text_hidden_fcs THROUGH these calls (GROVE.py:134-136, train.py:279-296), so a trainer that only swaps the import
+    would silently lose those gradients: say so (once per entry point) whenever autograd is recording and something here wants a gradient."""
+    import warnings
+    if what in _WARNED_NO_AUTOGRAD or not torch.is_grad_enabled():
+        return
+    if any(getattr(t, "requires_grad", False) for t in inputs) or any(p.requires_grad for p in params):
+        _WARNED_NO_AUTOGRAD.add(what)
+        warnings.warn(f"grove_b200: {what} does not record an autograd graph — its outputs carry no gradient to the trainable grounding "
+                      "parameters or inputs.  For training call GroundingBranch.grounding_loss(...) (forward + the library's own backward pass, "
+                      "delivers .grad to adapters / mask decoder / text_hidden_fcs and to last_hidden_state); for inference wrap the call in "
+                      "torch.no_grad().", stacklevel=3)
+
+
+def no_grad_entry(what: str, params_of):
+    """@torch.no_grad() for a forward entry point, with the autograd check done BEFORE gradients are switched off"""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(self, *a, **k):
+            if torch.is_grad_enabled():
+                tensors = [x for x in list(a) + list(k.values()) if isinstance(x, torch.Tensor)]
+                tensors += [y for x in list(a) + list(k.values()) if isinstance(x, (list, tuple)) for y in x if isinstance(y, torch.Tensor)]
+                warn_no_autograd(what, list(params_of(self)), *tensors)
+            with torch.no_grad():
+                return fn(self, *a, **k)
+        return wrapper
+    return deco

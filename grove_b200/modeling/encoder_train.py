@@ -24,7 +24,7 @@ from .decoder_train import GradStore, _wants
 
 def encode_train(enc, x: torch.Tensor):
     """[V,3,T,H,W] -> (token-major embeddings [V*T, G*G, out_chans] bf16, tape)"""
-    from .image_encoder import SpatioTemporalConvAdapter, _resize_rel_pos
+    from .image_encoder import _resize_rel_pos, is_conv_adapter
     if x.dim() != 5 or x.shape[1] != 3 or not x.is_cuda:
         raise ValueError("expected CUDA images of shape [V,3,T,H,W]")
     V, _, T, H, W = x.shape
@@ -35,7 +35,7 @@ def encode_train(enc, x: torch.Tensor):
     dev = x.device
     M = Fr * N
     gi = list(enc.global_attn_indexes)
-    convs = [isinstance(a, SpatioTemporalConvAdapter) for a in enc.adapters]
+    convs = [is_conv_adapter(a) for a in enc.adapters]
     trainable = [c and any(p.requires_grad for p in a.parameters()) for c, a in zip(convs, enc.adapters)]
     first = next((gi[k] for k in range(len(gi)) if trainable[k]), None)      # block index followed by the first trainable adapter
     tape = {"Fr": Fr, "G": G, "N": N, "M": M, "blocks": {}, "adapters": {}, "first": first}
@@ -89,7 +89,7 @@ def encode_train(enc, x: torch.Tensor):
         ops.gemm(h, w1, hid, bias=bb1, act="gelu", out2=pre, out2_pre_act=1 if keep else 0)
         w2, bb2 = enc._linear(k + ".l2", blk.mlp.lin2)
         adapter = enc.adapters[gi.index(i)] if i in gi else None
-        conv = isinstance(adapter, SpatioTemporalConvAdapter)
+        conv = is_conv_adapter(adapter)
         x2 = torch.empty(M, D, device=dev, dtype=torch.float32) if keep else x1
         ops.gemm(hid, w2, x2, bias=bb2, resid=x1, out2=xb if (conv or i == last) else None)
         if keep:

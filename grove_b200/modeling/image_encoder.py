@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .common import LayerNorm2d, MLPBlock, PackCache, _ContainerOnly, bf16, f32
+from .common import LayerNorm2d, MLPBlock, PackCache, _ContainerOnly, bf16, f32, no_grad_entry
 
 
 class SpatioTemporalConvAdapter(_ContainerOnly):
@@ -74,6 +74,12 @@ class Block(_ContainerOnly):
         self.norm2 = norm_layer(dim)
         self.mlp = MLPBlock(embedding_dim=dim, mlp_dim=int(dim * mlp_ratio), act=act_layer)
         self.window_size = window_size
+
+
+def is_conv_adapter(m) -> bool:
+    """Any module exposing `.conv3d` (an nn.Conv3d) and `.alpha` is run as the spatio-temporal Conv3d adapter: train.py:170-176
+    replaces `adapters` with fresh instances of the REFERENCE's own class, so the check is structural, not by type."""
+    return isinstance(getattr(m, "conv3d", None), nn.Conv3d) and isinstance(getattr(m, "alpha", None), torch.Tensor)
 
 
 def _resize_rel_pos(rel_pos: torch.Tensor, size: int) -> torch.Tensor:
@@ -170,7 +176,7 @@ class ImageEncoderViT(nn.Module):
         return static_out.clone()
 
     # ------------------------------------------------------------------ forward
-    @torch.no_grad()
+    @no_grad_entry("ImageEncoderViT.forward", lambda self: self.adapters.parameters())
     def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
         """[V,3,T,H,W] -> token-major embeddings [V*T, G*G, out_chans] bf16"""
         if x.dim() != 5 or x.shape[1] != 3:
@@ -180,10 +186,11 @@ class ImageEncoderViT(nn.Module):
         V, _, T, H, W = x.shape
         if H != W or H % 16:
             raise ValueError("square inputs with side a multiple of 16 are required")
-        img = x.to(torch.bfloat16).contiguous()
-        patches = torch.empty(V * T * (H // 16) ** 2, 768, device=x.device, dtype=torch.bfloat16)
-        ops.im2col_patch16(img, patches)
-        return self._encode_patches_cached(patches, V * T, H // 16)
+        with ops.device_of(x):
+            img = x.to(torch.bfloat16).contiguous()
+            patches = torch.empty(V * T * (H // 16) ** 2, 768, device=x.device, dtype=torch.bfloat16)
+            ops.im2col_patch16(img, patches)
+            return self._encode_patches_cached(patches, V * T, H // 16)
 
     @torch.no_grad()
     def forward_frames(self, frames: torch.Tensor, transform=None) -> torch.Tensor:
@@ -197,9 +204,10 @@ class ImageEncoderViT(nn.Module):
             raise RuntimeError("grove_b200.ImageEncoderViT runs on CUDA only (no CPU fallback)")
         V, T, h, w, _ = frames.shape
         tr = transform if transform is not None else ResizeLongestSide(self.img_size)
-        patches = tr.patches(frames.reshape(V * T, h, w, 3).contiguous(), self.img_size)
         G = self.img_size // 16
-        tok = self._encode_patches_cached(patches, V * T, G)
+        with ops.device_of(frames):
+            patches = tr.patches(frames.reshape(V * T, h, w, 3).contiguous(), self.img_size)
+            tok = self._encode_patches_cached(patches, V * T, G)
         out = tok.view(V * T, G, G, self.out_chans).permute(0, 3, 1, 2)
         want = self.pos_embed.dtype if self.pos_embed is not None else torch.bfloat16
         return out if want == torch.bfloat16 else out.to(want)
@@ -208,7 +216,7 @@ class ImageEncoderViT(nn.Module):
         """patches bf16 [Fr*G*G, 768] (k = c*256 + py*16 + px) -> token-major embeddings [Fr, G*G, out_chans] bf16"""
         D, heads = self.embed_dim, self.num_heads
         hd, N = D // heads, G * G
-        has_conv = any(isinstance(a, SpatioTemporalConvAdapter) for a in self.adapters)
+        has_conv = any(is_conv_adapter(a) for a in self.adapters)
         if has_conv and Fr % 8:
             raise ValueError("the spatio-temporal adapter groups frames by 8 (image_encoder.py:52): V*T must be a multiple of 8")
         dev = patches.device
@@ -256,7 +264,7 @@ class ImageEncoderViT(nn.Module):
             ops.gemm(h, w1, hid, bias=bb1, act="gelu")
             w2, bb2 = self._linear(k + ".l2", blk.mlp.lin2)
             adapter = self.adapters[self.global_attn_indexes.index(i)] if i in self.global_attn_indexes else None
-            conv = isinstance(adapter, SpatioTemporalConvAdapter)
+            conv = is_conv_adapter(adapter)
             if adapter is not None and not conv and not isinstance(adapter, nn.Identity):
                 raise NotImplementedError(f"unsupported adapter module {type(adapter).__name__}")
             ops.gemm(hid, w2, xs, bias=bb2, resid=xs, out2=xb if (conv or i == last) else None)

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .common import LayerNorm2d, PackCache, _ContainerOnly, bf16, f32
+from .common import LayerNorm2d, PackCache, _ContainerOnly, bf16, f32, no_grad_entry
 
 
 class MLP(_ContainerOnly):
@@ -59,6 +59,7 @@ class MaskDecoder(nn.Module):
             self.use_temp_objectness = False
         self._pack = PackCache()
         self._pew = {}
+        self._idx_cache = {}
         self.max_instances_per_pass = 256  # bounds the per-instance key buffers (N x 256 bf16 + fp32 delta)
 
     # ------------------------------------------------------------------ helpers
@@ -93,7 +94,7 @@ class MaskDecoder(nn.Module):
                                            dense_prompt_embeddings=dense_prompt_embeddings, reps=reps)
         return (boxes, logits) if self.use_temp_objectness else boxes
 
-    @torch.no_grad()
+    @no_grad_entry("MaskDecoder.forward", lambda self: self.parameters())
     def predict_masks(self, image_embeddings, image_pe, sparse_prompt_embeddings, dense_prompt_embeddings, reps: List[int]):
         """mask_decoder.py:155-205 (query path)."""
         if not image_embeddings.is_cuda:
@@ -106,34 +107,59 @@ class MaskDecoder(nn.Module):
         if sparse_prompt_embeddings.shape[1] != 1:
             raise NotImplementedError("one text token per prompt (GROVE.py:272)")
         d = dense_prompt_embeddings
-        if d.dim() != 4 or (d.shape[0] > 0 and (d.stride(0) != 0 or d.stride(2) != 0 or d.stride(3) != 0)):
+        # a broadcast view of one embedding: expand() keeps the stride of size-1 dims (B == 1 has stride(0) == C, a G == 1 grid non-zero spatial strides)
+        if d.dim() != 4 or (d.shape[0] > 0 and any(d.shape[k] > 1 and d.stride(k) != 0 for k in (0, 2, 3))):
             raise NotImplementedError("dense prompts other than the broadcast no-mask embedding are out of scope (prompt_encoder.py:182-184)")
         out_dtype = sparse_prompt_embeddings.dtype
         dev = image_embeddings.device
         if B == 0:
             return torch.zeros(0, 4, device=dev, dtype=out_dtype), torch.zeros(0, device=dev, dtype=out_dtype)
         no_mask = d[0, :, 0, 0].to(torch.float32).contiguous()
-        N = G * G
         emb = self._tokens_of(image_embeddings, torch.bfloat16)                       # [F,N,C]
+        text = sparse_prompt_embeddings.reshape(B, C).to(torch.float32)
+        with ops.device_of(emb):
+            rec = self.decode_records(emb, image_pe, text, no_mask, reps)
+        return rec[:, :4].to(out_dtype), rec[:, 4].to(out_dtype)
+
+    def _frame_index(self, reps, dev) -> torch.Tensor:
+        """int32 [B] on `dev`: the frame every (frame, phrase) instance reads (the reference's index_select, mask_decoder.py:178-185).
+        Cached per `reps`, so a steady-state step (and a CUDA-graph capture) does no host->device copy for it."""
+        key = (tuple(reps), dev)
+        hit = self._idx_cache.get(key)
+        if hit is None:
+            if len(self._idx_cache) > 64:
+                self._idx_cache.clear()
+            hit = torch.repeat_interleave(torch.arange(len(reps)), torch.tensor(reps)).to(torch.int32).to(dev)
+            self._idx_cache[key] = hit
+        return hit
+
+    @torch.no_grad()
+    def decode_records(self, emb_tokens: torch.Tensor, image_pe: torch.Tensor, text: torch.Tensor, no_mask: torch.Tensor, reps: List[int],
+                       records: torch.Tensor = None) -> torch.Tensor:
+        """The box decoder on token-major inputs: emb_tokens bf16 [F, N, C] (encoder output), image_pe [1,C,G,G], text fp32 [B, C] (one prompt
+        token per instance), no_mask fp32 [C] -> packed fp32 records [B, 5] = (cx, cy, w, h, objectness logit), written by the heads kernel
+        (into `records` when given, e.g. a slice of the all-gather buffer of parallel.ground_sharded_clip).  No host synchronisation."""
+        Fr, N, C = emb_tokens.shape
+        B = text.shape[0]
+        dev = emb_tokens.device
+        if records is None:
+            records = torch.empty(B, 5, device=dev, dtype=torch.float32)
+        if B == 0:
+            return records
         pe = self._tokens_of(image_pe, torch.float32).reshape(N, C)                   # [N,C] (a view of the caller's tensor when possible)
         if not pe.is_contiguous():
             pe = pe.contiguous()
         keys0 = torch.empty(Fr * N, C, device=dev, dtype=torch.bfloat16)
-        ops.add_rowvec_bf16(emb.reshape(Fr * N, C), no_mask, keys0)
-        text = sparse_prompt_embeddings.reshape(B, C).to(torch.float32)
+        ops.add_rowvec_bf16(emb_tokens.reshape(Fr * N, C), no_mask, keys0)
         out_tok = torch.cat([self.iou_token.weight, self.mask_tokens.weight], 0).to(torch.float32)
-        frame_of_all = torch.repeat_interleave(torch.arange(Fr), torch.tensor(reps)).to(torch.int32)
-        boxes = torch.empty(B, 4, device=dev, dtype=torch.float32)
-        logits = torch.empty(B, device=dev, dtype=torch.float32)
+        frame_of_all = self._frame_index(reps, dev)
         shared = self._layer0_shared(keys0, pe, N, C)
         step = self.max_instances_per_pass
         for s in range(0, B, step):
             e = min(B, s + step)
             tokens = torch.cat([out_tok.unsqueeze(0).expand(e - s, -1, -1), text[s:e].unsqueeze(1)], 1).contiguous()
-            b, l = self._decode(tokens, keys0, shared, pe, frame_of_all[s:e].to(dev), N, C)
-            boxes[s:e] = b
-            logits[s:e] = l
-        return boxes.to(out_dtype), logits.to(out_dtype)
+            self._decode(tokens, keys0, shared, pe, frame_of_all[s:e], N, C, records[s:e])
+        return records
 
     # ------------------------------------------------------------------ training step (forward with tape, backward)
     def predict_masks_train(self, emb_tokens: torch.Tensor, image_pe: torch.Tensor, text: torch.Tensor, no_mask: torch.Tensor, reps: List[int]):
@@ -204,7 +230,7 @@ class MaskDecoder(nn.Module):
         w, b = self._w32(key + ".o", attn.out_proj)
         return ops.small_linear(att, w, b, resid=resid)
 
-    def _decode(self, tokens, keys0, shared, pe, frame_of, N, C):
+    def _decode(self, tokens, keys0, shared, pe, frame_of, N, C, records):
         tr = self.transformer
         B, T, _ = tokens.shape
         H = tr.num_heads
@@ -266,16 +292,10 @@ class MaskDecoder(nn.Module):
         kp = self._image_proj("f.k", fa.k_proj, keys, pe, N)
         vp = self._image_proj("f.v", fa.v_proj, keys, None, N)
         att = ops.t2i_attention(q, kp, vp, src_of, B, T, N, H, fa.internal_dim // H).reshape(R, fa.internal_dim)
-        o = self._token_attn_out("f", fa, att)
+        # final out-proj + norm_final_attn + heads for token 1 + num_mask_tokens (mask_decoder.py:191-203) -> packed record
+        wo, bo = self._w32("f.o", fa.out_proj)
         g, b = self._ln("f.n", tr.norm_final_attn)
-        hs = ops.add_layernorm(queries, o, g, b, eps=tr.norm_final_attn.eps)
-        # heads (mask_decoder.py:191-203): token index 1 + num_mask_tokens
-        qo = hs.view(B, T, C)[:, 1 + self.num_mask_tokens, :].contiguous()
         w0, b0 = self._w32("h.0", self.bbox_prediction_head[0]); w2, b2 = self._w32("h.2", self.bbox_prediction_head[2])
-        boxes = ops.small_linear(ops.small_linear(qo, w0, b0, act="relu"), w2, b2, act="sigmoid")
-        if self.use_temp_objectness:
-            wt, bt = self._w32("h.t", self.temporal_objectness_head)
-            logits = ops.small_linear(qo, wt, bt).reshape(B)
-        else:
-            logits = torch.zeros(B, device=tok.device, dtype=torch.float32)
-        return boxes, logits
+        wt, bt = self._w32("h.t", self.temporal_objectness_head) if self.use_temp_objectness else (None, None)
+        return ops.decoder_heads(queries.view(B, T, C), att.view(B, T, fa.internal_dim), wo, bo, g, b, tr.norm_final_attn.eps, w0, b0, w2, b2,
+                                 wt, bt, records, tok=1 + self.num_mask_tokens)

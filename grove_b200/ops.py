@@ -17,7 +17,19 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def _stream(t: torch.Tensor):
+    """the launching stream = torch's current stream on the tensor's device.  The C ABI launches on the CURRENT device, so a tensor that
+    lives elsewhere is a caller error (the nn.Module entry points switch devices themselves, see `device_of`)."""
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"grove_b200: tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "wrap the call in `with torch.cuda.device(tensor.device):`")
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def device_of(t: torch.Tensor):
+    """context manager making `t`'s device current for the kernels launched inside (multi-GPU processes)"""
+    if not t.is_cuda:
+        raise RuntimeError("grove_b200 runs on CUDA tensors only (there is no CPU path)")
+    return torch.cuda.device(t.device)
 
 
 def _req(t: torch.Tensor, dtype, name: str):
@@ -223,6 +235,19 @@ def small_linear(x, w, b=None, *, act=None, resid=None):
     return y
 
 
+def decoder_heads(queries, att, wo, bo, ln_g, ln_b, eps, w0, b0, w2, b2, wt, bt, records, *, tok, hs_out=None):
+    """records[B,5] = (box cxcywh, objectness logit) of the prompt token: final out-proj + LayerNorm + both heads in one launch"""
+    B, T, Cc = queries.shape
+    CI = att.shape[-1]
+    assert att.shape[:2] == (B, T) and records.shape == (B, 5)
+    for t, n in ((queries, "queries"), (att, "att"), (wo, "wo"), (bo, "bo"), (ln_g, "ln_g"), (ln_b, "ln_b"), (w0, "w0"), (b0, "b0"), (w2, "w2"),
+                 (b2, "b2"), (records, "records")):
+        _req(t, F32, n)
+    check(lib().grove_decoder_heads_fwd(_p(queries), _p(att), _p(wo), _p(bo), _p(ln_g), _p(ln_b), float(eps), _p(w0), _p(b0), _p(w2), _p(b2),
+                                        _p(wt), _p(bt), _p(records), _p(hs_out), B, T, int(tok), Cc, CI, _stream(queries)), "grove_decoder_heads_fwd")
+    return records
+
+
 def token_self_attention(q, k, v, B, T, heads, dh):
     out = torch.empty_like(q)
     check(lib().grove_token_self_attention(_p(_req(q, F32, "q")), _p(_req(k, F32, "k")), _p(_req(v, F32, "v")), _p(out), B, T, heads, dh,
@@ -279,6 +304,34 @@ def greedy_match(iou, sim, iou_thr, sim_thr):
                                    _p(pairs), _p(count), n, m, _stream(iou)), "grove_greedy_match")
     c = int(count.item())
     return [tuple(int(v) for v in p) for p in pairs[:c].tolist()]
+
+
+def center_in_box(pred, gt):
+    n = pred.shape[0]
+    out = torch.empty(n, device=pred.device, dtype=torch.uint8)
+    check(lib().grove_center_in_box(_p(_req(pred, torch.float64, "pred")), _p(_req(gt, torch.float64, "gt")), _p(out), n, _stream(pred)),
+          "grove_center_in_box")
+    return out
+
+
+def viou_decisions(pred, gt, thr):
+    n, k = pred.shape[0], thr.numel()
+    ious = torch.empty(max(n, 1), device=pred.device, dtype=torch.float64)
+    viou = torch.empty(1, device=pred.device, dtype=torch.float64)
+    over = torch.empty(max(k, 1), device=pred.device, dtype=torch.uint8)
+    check(lib().grove_viou_decisions(_p(_req(pred, torch.float64, "pred")), _p(_req(gt, torch.float64, "gt")), _p(_req(thr, torch.float64, "thr")),
+                                     n, k, _p(ious), _p(viou), _p(over), _stream(thr)), "grove_viou_decisions")
+    return ious[:n], viou, over[:k]
+
+
+def val_metrics(boxes, logits, gt, sel, labels):
+    B = boxes.shape[0]
+    giou = torch.empty(1, device=boxes.device, dtype=torch.float64)
+    acc = torch.empty(1, device=boxes.device, dtype=torch.int32)
+    check(lib().grove_val_metrics(_p(_req(boxes, F32, "boxes")), _p(_req(logits, F32, "logits")), _p(_req(gt, F32, "gt")),
+                                  _p(_req(sel, torch.uint8, "sel")), _p(_req(labels, torch.int32, "labels")), _p(giou), _p(acc), None, B,
+                                  _stream(boxes)), "grove_val_metrics")
+    return float(giou.item()), int(acc.item())
 
 
 # ------------------------------------------------------------------ training step (backward pass)

@@ -41,49 +41,103 @@ def units_of_rank(num_units: int, world: int, rank: int) -> List[int]:
     return list(range(rank, num_units, world))
 
 
-def ground_sharded_clip(window_fn: Callable[[List[int]], torch.Tensor], num_frames: int, num_phrases: int, *,
-                        group: Optional[dist.ProcessGroup] = None, device=None) -> torch.Tensor:
-    """Ground one long clip whose 8-frame windows are split across the ranks of `group`.
+def ground_sharded_clip(window_fn: Callable[..., Optional[torch.Tensor]], num_frames: int, num_phrases: int, *,
+                        group: Optional[dist.ProcessGroup] = None, device=None, timings: Optional[dict] = None) -> torch.Tensor:
+    """Ground one long clip whose 8-frame windows are split across the ranks of `group` (window w -> rank w mod n).
 
-    `window_fn(frame_ids) -> [8, P, 5]` runs the per-window hot path (encoder + decoder) on THIS rank and returns packed
-    records.  Returns, on every rank, the records of all frames in temporal order: [num_frames, P, 5] fp32.
-    One all-gather of a pre-packed buffer; no other communication."""
-    if num_frames % 8:
-        raise NotImplementedError("clips whose length is not a multiple of 8 produce windows of fewer than 8 frames, which the "
-                                  "reference's adapter cannot run either (image_encoder.py:52 hard-codes t=8)")
+    `window_fn(frame_ids, out)` runs the per-window hot path (encoder + decoder) on THIS rank; `out` is the window's `[len(frame_ids), P, 5]`
+    fp32 slot INSIDE the all-gather send buffer — the heads kernel writes its packed records straight into it (window_fn returns None), or
+    window_fn returns a tensor of that shape which is copied in.  Returns, on every rank, the records of all frames in temporal order:
+    `[num_frames, P, 5]` fp32.  One all-gather of the pre-packed buffer on the compute stream; no other communication.
+
+    Any clip length works: the reference's schedule (infer_iground.py:110-148) always emits 8-frame windows — for lengths that are not
+    a multiple of 8 the remainder windows re-visit frames already produced, and the first-seen masks drop the repeats (:264-266).
+    `timings` (optional dict) receives CUDA events around the collective: {"allgather": (start, end)}."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     windows, masks = sliding_segment_with_mask(num_frames, 8)
+    wlen = 8
+    if any(len(w) != wlen for w in windows):
+        raise ValueError("the sliding-window schedule produced a window that is not 8 frames long")
     mine = units_of_rank(len(windows), world, rank)
     per_rank = (len(windows) + world - 1) // world
     buf = None
     for slot, w in enumerate(mine):
-        rec = window_fn(windows[w])
-        if rec.shape != (8, num_phrases, 5):
-            raise ValueError(f"window_fn must return [8, {num_phrases}, 5], got {tuple(rec.shape)}")
         if buf is None:
-            buf = torch.zeros(per_rank, 8, num_phrases, 5, dtype=torch.float32, device=rec.device)
-        buf[slot] = rec.float()
+            dev0 = device if device is not None else _device_of_fn(window_fn)
+            buf = torch.zeros(per_rank, wlen, num_phrases, 5, dtype=torch.float32, device=dev0)
+        rec = window_fn(windows[w], buf[slot])
+        if rec is not None and rec.data_ptr() != buf[slot].data_ptr():
+            if tuple(rec.shape) != (wlen, num_phrases, 5):
+                raise ValueError(f"window_fn must return [{wlen}, {num_phrases}, 5], got {tuple(rec.shape)}")
+            if rec.device != buf.device:         # the first window tells where the path runs
+                buf = buf.to(rec.device)
+            buf[slot].copy_(rec)
     if buf is None:
-        buf = torch.zeros(per_rank, 8, num_phrases, 5, dtype=torch.float32, device=device or "cpu")
+        buf = torch.zeros(per_rank, wlen, num_phrases, 5, dtype=torch.float32, device=device or "cpu")
     if world > 1:
-        gathered = torch.empty(world * per_rank, 8, num_phrases, 5, dtype=torch.float32, device=buf.device)
-        dist.all_gather_into_tensor(gathered, buf, group=group)
+        gathered = torch.empty(world * per_rank, wlen, num_phrases, 5, dtype=torch.float32, device=buf.device)
+        if timings is not None and buf.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_gather_into_tensor(gathered, buf, group=group)
+            e1.record()
+            timings["allgather"] = (e0, e1)
+        else:
+            dist.all_gather_into_tensor(gathered, buf, group=group)
     else:
         gathered = buf
-    out = torch.zeros(num_frames, num_phrases, 5, dtype=torch.float32, device=buf.device)
+    # temporal re-assembly (the reference sorts by first-seen frame index, infer_iground.py:282-288): one gather with a host-built index
+    src_rows, dst_rows = [], []
     for w, (idx, msk) in enumerate(zip(windows, masks)):
-        src = gathered[(w % world) * per_rank + w // world]
-        keep = [i for i, mk in enumerate(msk) if mk]
-        if keep:
-            out[[idx[i] for i in keep]] = src[keep]
+        base = ((w % world) * per_rank + w // world) * wlen
+        for i, mk in enumerate(msk):
+            if mk:
+                src_rows.append(base + i)
+                dst_rows.append(idx[i])
+    out = torch.zeros(num_frames, num_phrases, 5, dtype=torch.float32, device=buf.device)
+    if src_rows:
+        src_t = torch.tensor(src_rows, dtype=torch.long).to(buf.device)
+        dst_t = torch.tensor(dst_rows, dtype=torch.long).to(buf.device)
+        out[dst_t] = gathered.view(-1, num_phrases, 5)[src_t]
     return out
 
 
+def _device_of_fn(fn):
+    return getattr(fn, "device", None) or "cpu"
+
+
+def ground_long_clip(branch, clip_images: torch.Tensor, last_hidden_state: torch.Tensor, det_token_mask: torch.Tensor, *,
+                     group: Optional[dist.ProcessGroup] = None, timings: Optional[dict] = None) -> torch.Tensor:
+    """BASELINE config 5 end to end: one long clip `[1, 3, F, H, W]` with P phrases, its 8-frame windows split across the ranks of `group`,
+    every window through `GroundingBranch.ground_records` (encoder + text projection + box decoder + heads), records written into the
+    all-gather buffer, one NCCL all-gather, temporal re-assembly.  Returns `[F, P, 5]` fp32 on every rank — the tensor that replaces the
+    reference's per-window Python dict merge + pickled `all_gather_object` (infer_iground.py:245-293)."""
+    if clip_images.dim() != 5 or clip_images.shape[0] != 1:
+        raise ValueError(f"expected one clip [1, 3, F, H, W], got {tuple(clip_images.shape)}")
+    num_frames = clip_images.shape[2]
+    idx, counts = branch._det_rows(det_token_mask)
+    P = counts[0]
+    dev = next(branch.parameters()).device
+    host_mask = det_token_mask.cpu()         # one read-back for the whole clip; every window reuses the host copy
+
+    def window_fn(frame_ids, out):
+        images = clip_images[:, :, frame_ids]
+        if images.is_cuda:
+            images = images.contiguous()
+        branch.ground_records(images, last_hidden_state, host_mask, records_out=out.view(-1, 5), copy_out=False)
+        return None
+    window_fn.device = dev
+    return ground_sharded_clip(window_fn, num_frames, P, group=group, device=dev, timings=timings)
+
+
 def pack_records(boxes_nested, logits_nested) -> torch.Tensor:
-    """nested [V][T] lists of [P,4] boxes / [P] logits (the return value of _generate_and_postprocess_masks, GROVE.py:297-331)
-    for ONE video -> packed [T, P, 5]"""
+    """nested [V][T] lists of [P,4] boxes / [P] logits (the return value of _generate_and_postprocess_masks with infer=False,
+    GROVE.py:297-331) for ONE video -> packed [T, P, 5].  With infer=True the reference drops boxes per frame (ragged): use
+    GroundingBranch.ground_records / ground_host_stream, whose records keep every row plus a keep flag."""
     fb, fl = boxes_nested[0], logits_nested[0]
+    if any(b.shape[0] != l.shape[0] for b, l in zip(fb, fl)):
+        raise ValueError("pack_records needs unfiltered per-frame outputs (infer=False): boxes and logits differ in length")
     return torch.stack([torch.cat([b.float(), l.float()[:, None]], 1) for b, l in zip(fb, fl)])
 
 

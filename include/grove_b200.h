@@ -25,7 +25,7 @@ typedef cudaStream_t grove_stream_t;
 typedef void* grove_stream_t;
 #endif
 
-#define GROVE_B200_ABI_VERSION 3
+#define GROVE_B200_ABI_VERSION 4
 
 /* ---- library ---------------------------------------------------------------------------------- */
 int grove_abi_version(void);
@@ -140,6 +140,15 @@ int grove_decoder_i2t_attention(const void* qi, const float* kt, const float* vt
 /* keys_out[b,n,:] = bf16(LayerNorm(keys_in[src_of[b],n,:] + delta[b,n,:]))  (norm4, transformer.py:180), C = 256. */
 int grove_decoder_keys_add_ln(const void* keys_in, const int* src_of, const float* delta, const float* g, const float* b, void* keys_out,
                               int B, int N, int C, float eps, grove_stream_t stream);
+/* The last step of the box decoder for the prompt token `tok` (= 1 + num_mask_tokens) of every instance, one launch:
+ *   hs = LayerNorm_final(queries[b,tok,:] + out_proj(att[b,tok,:]))   (final_attn_token_to_image + norm_final_attn, transformer.py:99-104)
+ *   records[b] = (sigmoid(W2 relu(W0 hs + b0) + b2), Wt hs + bt)      (bbox_prediction_head / temporal_objectness_head, mask_decoder.py:80-85,191-203)
+ * queries fp32 [B,T,C], att fp32 [B,T,CI] (grove_decoder_t2i_attention output), records fp32 [B,5] = (cx, cy, w, h, objectness logit) --
+ * the packed per-(frame, phrase) record that replaces the reference's pickled all_gather_object (infer_iground.py:290-293).
+ * Wt/bt NULL (use_temp_objectness=False) writes logit 0.  hs_out (optional, fp32 [B,C]) keeps the head input.  C = 256, CI = 128. */
+int grove_decoder_heads_fwd(const float* queries, const float* att, const float* Wo, const float* bo, const float* ln_g, const float* ln_b,
+                            float eps, const float* W0, const float* b0, const float* W2, const float* b2, const float* Wt, const float* bt,
+                            float* records, float* hs_out, int B, int T, int tok, int C, int CI, grove_stream_t stream);
 /* Token-side dense layer, all fp32: y[R,N] = act(x[R,K] . W[N,K]^T + b) (+ resid).  act: 0 none, 1 GELU, 2 ReLU, 3 sigmoid.
  * (6-token projections / MLP of transformer.py:151-182, heads mask_decoder.py:80-85,198-203, PE.W products.) */
 int grove_small_linear_f32(const float* x, const float* W, const float* b, const float* resid, float* y, int R, int N, int K, int act,
@@ -171,6 +180,19 @@ int grove_box_iou(const void* a, int lda, const void* b, int ldb, const uint8_t*
 /* Greedy one-to-one matching (eval_iground.py:85-96): iou, sim fp64 [n,m] (clobbered); pairs int32 [min(n,m),2]; count int32[1]. */
 int grove_greedy_match(double* iou, double* sim, double iou_thr, double sim_thr, int* pairs, int* count, int n, int m,
                        grove_stream_t stream);
+/* Centre-in-box decision (eval_youcookinteractions.py:43-48): pred, gt fp64 [n,4] xyxy; correct[i] = 1 iff the centre of pred[i]
+ * (Python-float arithmetic, (x1+x2)/2) lies inside gt[i] with INCLUSIVE bounds. */
+int grove_center_in_box(const double* pred, const double* gt, uint8_t* correct, int n, grove_stream_t stream);
+/* Video IoU and recall decisions of one video (eval_vidstg.py:157-178): pred, gt fp64 [n,4] (one row per ground-truth frame, in frame
+ * order); ious[i] = np_box_iou (mode 0) or 0 when pred[i] is all zeros; viou[0] = (sum in frame order) / max(n,1);
+ * over[j] = viou > thr[j] (strict) for the k thresholds. */
+int grove_viou_decisions(const double* pred, const double* gt, const double* thr, int n, int k, double* ious, double* viou, uint8_t* over,
+                         grove_stream_t stream);
+/* Validation metrics (train.py:826-835): giou_sum[0] = sum over rows with sel[i] of torchvision's GIoU loss of boxes[i] vs gt[i] ON THE
+ * COORDINATES AS GIVEN (fp32; the reference passes cxcywh there -- reproduced); acc[0] = #{i : (sigmoid(logits[i]) > 0.5) == labels[i]}.
+ * giou_each (optional, fp32 [B]) receives the per-row loss (0 where not selected). */
+int grove_val_metrics(const float* boxes, const float* logits, const float* gt, const uint8_t* sel, const int* labels, double* giou_sum, int* acc,
+                      float* giou_each, int B, grove_stream_t stream);
 
 
 /* ==== frame pre-processing fused into the patch embed's operand ===============================

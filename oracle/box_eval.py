@@ -20,9 +20,72 @@ def np_box_iou(b1: np.ndarray, b2: np.ndarray) -> np.ndarray:
 
 
 def viou_recalls(ious, n_gt_frames: int, thresholds):
-    """eval_vidstg.py:174-178: mean IoU over GT frames, strict '>' against each threshold."""
-    v = float(np.sum(ious)) / max(n_gt_frames, 1)
+    """eval_vidstg.py:157-178: IoUs accumulated in frame order (`gt_viou += iou`, Python floats), divided by max(n, 1),
+    strict '>' against each threshold."""
+    acc = 0
+    for v in ious:
+        acc += float(v)
+    v = acc / max(n_gt_frames, 1)
     return v, [1 if v > t else 0 for t in thresholds]
+
+
+def video_viou(pred_boxes, gt_boxes, thresholds):
+    """eval_vidstg.py:157-178 for one video: pred_boxes / gt_boxes [n,4] xyxy aligned per ground-truth frame; a prediction that is all
+    zeros scores 0 without an IoU (`pred_box.any()`)."""
+    ious = []
+    for p, g in zip(np.asarray(pred_boxes, dtype=np.float64), np.asarray(gt_boxes, dtype=np.float64)):
+        ious.append(float(np_box_iou(p[None], g[None])[0][0]) if p.any() else 0)
+    v, over = viou_recalls(ious, len(ious), thresholds)
+    return v, over, ious
+
+
+def localization_accuracy(pred_boxes, gt_boxes, kinds=None):
+    """eval_youcookinteractions.py:8-51 on flat arrays: kinds 0 normal, 1 empty ground truth (skipped), 2 missing prediction, 3 NaN
+    prediction (both valid-but-wrong).  Returns (accuracy %, correct, valid, per-pair flags)."""
+    n = len(pred_boxes)
+    kinds = np.zeros(n, dtype=np.int64) if kinds is None else kinds
+    correct = valid = 0
+    flags = np.zeros(n, dtype=np.uint8)
+    for i in range(n):
+        if kinds[i] == 1:
+            continue
+        valid += 1
+        if kinds[i] == 2 or np.any(np.isnan(pred_boxes[i])):
+            continue
+        if center_in_box([float(v) for v in pred_boxes[i]], [float(v) for v in gt_boxes[i]]):
+            correct += 1
+            flags[i] = 1
+    return ((correct / valid) * 100 if valid else 0.0), correct, valid, flags
+
+
+def giou_loss_xyxy(b1: np.ndarray, b2: np.ndarray) -> np.ndarray:
+    """torchvision.ops.generalized_box_iou_loss per row, fp32, on the coordinates as given (eps 1e-7)."""
+    b1, b2 = b1.astype(np.float32), b2.astype(np.float32)
+    x1, y1, x2, y2 = b1.T
+    x1g, y1g, x2g, y2g = b2.T
+    xk1, yk1, xk2, yk2 = np.maximum(x1, x1g), np.maximum(y1, y1g), np.minimum(x2, x2g), np.minimum(y2, y2g)
+    inter = np.where((yk2 > yk1) & (xk2 > xk1), (xk2 - xk1) * (yk2 - yk1), np.float32(0))
+    union = (x2 - x1) * (y2 - y1) + (x2g - x1g) * (y2g - y1g) - inter
+    iou = inter / (union + np.float32(1e-7))
+    ac = (np.maximum(x2, x2g) - np.minimum(x1, x1g)) * (np.maximum(y2, y2g) - np.minimum(y1, y1g))
+    return np.float32(1) - (iou - (ac - union) / (ac + np.float32(1e-7)))
+
+
+def val_giou_and_objectness_accuracy(pred_bboxes, logits, gt_bboxes, gt_obj):
+    """train.py:821-840: nested [V][T] lists; GIoU loss of pred[gt_obj] vs gt ON THE COORDINATES AS GIVEN (the reference passes cxcywh),
+    accumulated per frame in fp32; objectness hits = ((sigmoid(logit) > 0.5) == label).  Returns (giou_sum, hits, num_bboxes, num_max)."""
+    giou, hits, nb, nmax = np.float32(0), 0, 0, 0
+    for v in range(len(pred_bboxes)):
+        for f in range(len(pred_bboxes[v])):
+            pb, lg = np.asarray(pred_bboxes[v][f], dtype=np.float32), np.asarray(logits[v][f], dtype=np.float32)
+            go, gb = np.asarray(gt_obj[v][f]).astype(np.int64), np.asarray(gt_bboxes[v][f], dtype=np.float32).reshape(-1, 4)
+            if gb.shape[0]:
+                giou = np.float32(giou + giou_loss_xyxy(pb[go.astype(bool)], gb).sum(dtype=np.float32))
+            sg = np.float32(1) / (np.float32(1) + np.exp(-lg, dtype=np.float32))
+            hits += int(((sg > 0.5).astype(np.int64) == go).sum())
+            nb += gb.shape[0]
+            nmax += pb.shape[0]
+    return float(giou), hits, nb, nmax
 
 
 def compute_iou_plus1(p, g) -> float:

@@ -341,6 +341,137 @@ def box_eval_case(name, seed):
     print(name, "iou", iou64.shape, "matches", matches)
 
 
+
+def decisions_case(name, seed):
+    """The three decision utilities the round-1 product lacked, each executed from the reference's own source:
+    centre-in-box accuracy (eval_youcookinteractions.py:8-51), video IoU + strict '>' recall flags (VidSTGiouEvaluator.evaluate,
+    eval_vidstg.py:118-186) and the validation GIoU / objectness-accuracy sums (the `if logits_temp_objectness is not None:` block of
+    validate_model_performance, train.py:821-840 -- the enclosing function cannot run (it references an undefined name), so the block
+    is located in the AST and executed with its free variables bound)."""
+    import importlib.util
+    from torchvision.ops import generalized_box_iou_loss
+    rng = np.random.Generator(np.random.PCG64([seed, 11]))
+    out = {}
+    # ---- centre-in-box
+    spec = importlib.util.spec_from_file_location("ref_eval_yc", os.path.join(REF, "eval_youcookinteractions.py"))
+    yc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(yc)
+    n = 24
+    gt = np.round(rng.uniform(0, 100, (n, 2)))
+    gt = np.concatenate([gt, gt + np.round(rng.uniform(5, 60, (n, 2)))], 1)
+    pred = gt + rng.uniform(-30, 30, (n, 4))
+    pred[0] = [gt[0, 0], gt[0, 1], gt[0, 0], gt[0, 1]]                     # centre exactly on the top-left corner: inclusive -> correct
+    pred[1] = [gt[1, 2] - 4, gt[1, 3] - 2, gt[1, 2] + 4, gt[1, 3] + 2]     # centre exactly on the bottom-right corner -> correct
+    pred[2] = [gt[2, 2], 0, gt[2, 2] + 2, 2 * gt[2, 1]]                    # centre one pixel right of xbr -> wrong
+    pred[3] = np.nan                                                        # NaN prediction: valid, not correct
+    kinds = np.zeros(n, dtype=np.int64)                                     # 0 normal, 1 empty gt (skipped), 2 pred None, 3 NaN pred
+    kinds[3] = 3; kinds[5] = 1; kinds[9] = 2; kinds[17] = 1
+    gt_data, pred_dict = [], {}
+    for c in range(3):                                                      # three clips of eight frames
+        sl = slice(8 * c, 8 * c + 8)
+        gt_boxes = [[] if k == 1 else tuple(float(v) for v in g) for g, k in zip(gt[sl], kinds[sl])]
+        preds = [None if k == 2 else np.array([p]) for p, k in zip(pred[sl], kinds[sl])]
+        gt_data.append({"video_id": f"v{c}", "segment_youcook_idx": c, "segment_bboxes": gt_boxes})
+        pred_dict[f"v{c}_{c}"] = {"final_boxes": preds}
+    acc, correct, valid = yc.evaluate_dataset_localization(pred_dict, gt_data, "youcook")
+    flags = []
+    for i in range(n):                                                      # per-pair decisions through the same function
+        if kinds[i] in (1, 2):
+            flags.append(0)
+            continue
+        _, c1, _ = yc.evaluate_dataset_localization({"a_0": {"final_boxes": [np.array([pred[i]])]}},
+                                                    [{"video_id": "a", "segment_youcook_idx": 0, "segment_bboxes": [tuple(float(v) for v in gt[i])]}], "youcook")
+        flags.append(c1)
+    out.update(cib_pred=pred, cib_gt=gt, cib_kinds=kinds, cib_flags=np.array(flags, dtype=np.uint8), cib_result=np.array([acc, correct, valid], dtype=np.float64))
+    # ---- video IoU
+    spec = importlib.util.spec_from_file_location("ref_eval_vidstg2", os.path.join(REF, "eval_vidstg.py"))
+    ev = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ev)
+    E = object.__new__(ev.VidSTGiouEvaluator)
+    E.iou_thresholds = [0.3, 0.5]
+    nf = 10
+    E.video_gt, preds = {}, {}
+    vg, vp = [], []
+    for v in range(5):
+        g = rng.uniform(0, 100, (nf, 2)); g = np.concatenate([g, g + rng.uniform(10, 80, (nf, 2))], 1)
+        jitter = [3, 12, 25, 60, 0][v]
+        p_ = g + rng.uniform(-jitter, jitter, (nf, 4)) if jitter else g.copy()
+        if v == 4:                                                          # every frame IoU exactly 0.5 -> vIoU == 0.5 -> '>' 0.5 is False
+            g = np.tile(np.array([0.0, 0.0, 2.0, 1.0]), (nf, 1)); p_ = np.tile(np.array([0.0, 0.0, 1.0, 1.0]), (nf, 1))
+        p_[2] = 0.0                                                         # all-zero prediction: IoU 0 without calling np_box_iou
+        if v == 4:
+            p_[2] = [0.0, 0.0, 1.0, 1.0]
+        vg.append(g); vp.append(p_)
+        E.video_gt[f"vid{v}"] = {"frame_ids": list(range(0, 2 * nf, 2)), "boxes": [list(map(float, r)) for r in g]}
+        order = list(rng.permutation(nf))                                   # predictions arrive in a different frame order
+        preds[f"vid{v}"] = {"qtype": "declarative", "frame_ids": [2 * int(i) for i in order], "boxes": [np.array([p_[int(i)]]) for i in order]}
+    vm = E.evaluate(preds)
+    out.update(viou_gt=np.stack(vg), viou_pred=np.stack(vp),
+               viou_value=np.array([vm[f"vid{v}"]["gt_viou"] for v in range(5)]),
+               viou_over=np.array([[vm[f"vid{v}"][f"gt_viou@{t}"] for t in E.iou_thresholds] for v in range(5)], dtype=np.uint8),
+               viou_frame=np.array([[vm[f"vid{v}"]["img_metrics"][f"vid{v}_{2 * f}"]["iou"] for f in range(nf)] for v in range(5)]))
+    # ---- validation sums: locate the block in train.py's AST and execute it
+    tree = ast.parse(open(os.path.join(REF, "train.py")).read())
+    fn = next(nd for nd in tree.body if isinstance(nd, ast.FunctionDef) and nd.name == "validate_model_performance")
+    block = next(nd for nd in ast.walk(fn) if isinstance(nd, ast.If) and isinstance(nd.test, ast.Compare)
+                 and isinstance(nd.test.left, ast.Name) and nd.test.left.id == "logits_temp_objectness")
+    code = compile(ast.Module([block], []), "train.py", "exec")
+    T, P = 8, 3
+    pb = torch.from_numpy(rng.uniform(0.05, 0.95, (2, T, P, 4))).float()
+    lg = torch.from_numpy(rng.normal(0, 2, (2, T, P))).float()
+    lg[0, 0, 0] = 0.0                                                       # sigmoid(0) = 0.5 is NOT '> 0.5'
+    go = torch.from_numpy((rng.uniform(size=(2, T, P)) < 0.5).astype(np.int32))
+    gtb = torch.from_numpy(rng.uniform(0.05, 0.95, (2, T, P, 4))).float()
+    for variant, gcast in (("f", lambda t: t), ("i", lambda t: t.int())):   # raw float ground truth, and the reference's own `.int()` cast
+        scope = {"torch": torch, "F": torch.nn.functional, "generalized_box_iou_loss": generalized_box_iou_loss,
+                 "pred_bboxes": [[pb[v, f] for f in range(T)] for v in range(2)],
+                 "logits_temp_objectness": [[lg[v, f] for f in range(T)] for v in range(2)],
+                 "gt_bboxes": [[gcast(gtb[v, f][go[v, f].bool()]) for f in range(T)] for v in range(2)],
+                 "gt_temp_objectness": [[go[v, f] for f in range(T)] for v in range(2)]}
+        exec(code, scope)
+        out[f"val_{variant}"] = np.array([float(scope["giou_sum"]), float(scope["temp_objectness_sum"]), scope["num_bboxes"], scope["num_max_bboxes"]],
+                                         dtype=np.float64)
+    out.update(val_boxes=pb.numpy(), val_logits=lg.numpy(), val_obj=go.numpy(), val_gt=gtb.numpy())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "cib", out["cib_result"], "viou", out["viou_value"], out["viou_over"].tolist(), "val", out["val_f"], out["val_i"])
+
+
+def infer_case(name, seed):
+    """GROVEForCausalLM._generate_and_postprocess_masks(infer=True) (GROVE.py:297-331) at the real decoder width (256 / 2048, 16x16 grid) so the
+    CUDA decoder can run the same case: un-normalise with orig_sizes, cxcywh -> xyxy, keep sigmoid(logit) > threshold.  The threshold is set to the
+    median objectness of the case so that the keep decisions straddle it (the stock 0.5 keeps nothing for these random weights)."""
+    _stub_mm()
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import model.GROVE as RG
+    C = RG.GROVEForCausalLM
+    dim, mlp, G, T = 256, 2048, 16, 8
+    reps = [3] * T + [2] * T
+    pe, md, sdict = decoder_case(name + "_dec", dim=dim, mlp=mlp, G=G, frames=2 * T, reps=reps, seed=seed)
+    os.remove(os.path.join(OUT, name + "_dec.npz"))
+    emb = synth.synth_tensor(name + "_dec.emb", (2 * T, dim, G, G), seed)
+    txt = synth.synth_tensor(name + "_dec.txt", (sum(reps), 1, dim), seed)
+    pred_list, s0 = [], 0
+    for r in reps:
+        pred_list.append(txt[s0:s0 + r, 0]); s0 += r
+    sizes = [(1280, 720), (640, 360)]
+    self = NS(model=NS(grounding_encoder=NS(prompt_encoder=pe, mask_decoder=md)),
+              config=NS(num_frames=T, use_temp_objectness=True, temp_objectness_threshold=0.5))
+    with torch.no_grad():
+        tb, tl = C._generate_and_postprocess_masks(self, pred_list, emb, sizes, pe.get_dense_pe(), infer=False)
+        logits = torch.cat([l for v in tl for l in v])
+        sg = torch.sigmoid(logits).sort().values
+        thr = float((sg[sg.numel() // 2 - 1] + sg[sg.numel() // 2]) / 2)      # midway between the two middle objectness values
+        self.config.temp_objectness_threshold = thr
+        ib, il = C._generate_and_postprocess_masks(self, pred_list, emb, sizes, pe.get_dense_pe(), infer=True)
+    counts = np.array([b.shape[0] for v in ib for b in v])
+    assert 0 < counts.sum() < sum(reps), counts
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=np.array([dim, mlp, G, T, seed]), reps=np.array(reps), thr=np.array(thr),
+                        sizes=np.array(sizes), train_boxes=torch.cat([b for v in tb for b in v]).numpy(), train_logits=logits.numpy(),
+                        infer_boxes=torch.cat([b for v in ib for b in v]).numpy(), infer_counts=counts,
+                        infer_logits=torch.cat([l for v in il for l in v]).numpy())
+    print(name, "threshold %.4f keeps %d of %d boxes" % (thr, counts.sum(), sum(reps)), "margin", float((torch.sigmoid(logits) - thr).abs().min()))
+
+
 def _classes_from_source(path, names, scope):
     """exec only the named top-level classes of a reference module (modeling_clip.py imports a transformers version that is not
     installed here); nothing is written to the repo."""
@@ -401,6 +532,8 @@ def main():
     preprocess_case("preprocess", seed=8)
     posembed_case("posembed", seed=9)
     clip_case("clip_adapters", seed=10)
+    decisions_case("decisions", seed=12)
+    infer_case("glue_infer", seed=13)
 
 
 if __name__ == "__main__":

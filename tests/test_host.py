@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(l, name), f"{name} is declared in include/grove_b200.h but not exported by libgrove_b200.so"
     assert declared == set(SIGNATURES), (declared ^ set(SIGNATURES))
-    assert l.grove_abi_version() == 3
+    assert l.grove_abi_version() == 4
 
 
 @pytest.mark.parametrize("vit", ["vit_b", "vit_l", "vit_h"])
@@ -84,3 +84,43 @@ def test_checkpoint_tooling_matches_reference_surgery():
     r = ck.load_sam_state_dict(sam, sd, fcs)
     assert r["skipped"] == ["model.layers.0.self_attn.q_proj.weight"] and not r["unexpected"]
     assert float(enc.pos_embed.abs().sum()) == 0.0 and float(fcs[0][0].bias.sum()) == 4096.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
+def test_reference_trainer_surgery_leaves_a_runnable_module():
+    """train.py:162-191 (initialize_custom_layers_in_model) and :561-576 (interpolate_positional_embeddings), executed FROM THE REFERENCE'S
+    SOURCE on a grove_b200 model: the trainer replaces `adapters` with instances of the reference's own SpatioTemporalConvAdapter class and
+    the heads with fresh nn.Linear stacks, and reassigns pos_embed / rel_pos / img_size.  The encoder must accept all of it."""
+    import ast
+    import sys
+    from types import SimpleNamespace as NS
+    import torch.nn as nn
+    from grove_b200.modeling.grounding import GroundingBranch
+    from grove_b200.modeling.image_encoder import is_conv_adapter
+    sys.path.insert(0, "/root/reference")
+    sys.dont_write_bytecode = True
+    try:
+        from model.SAM.modeling.image_encoder import SpatioTemporalConvAdapter as RefAdapter
+    finally:
+        sys.path.remove("/root/reference")
+    src = open("/root/reference/train.py").read()
+    scope = {"torch": torch, "nn": nn, "F": torch.nn.functional, "GroundingSpatioTemporalConvAdapter": RefAdapter}
+    want = {"initialize_custom_layers_in_model", "interpolate_positional_embeddings", "resize_abs_pos_embedding", "resize_rel_pos_embedding"}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in want:
+            exec(compile(ast.Module([node], []), "train.py", "exec"), scope)
+    with torch.device("meta"):
+        gb = GroundingBranch(vit="vit_h")                       # GROVE builds ViT-H at the SAM default 1024 (GROVE.py:55)
+    enc, dec = gb.grounding_encoder.image_encoder, gb.grounding_encoder.mask_decoder
+    scope["initialize_custom_layers_in_model"](NS(get_model=lambda: gb, config=gb.config))
+    assert len(enc.adapters) == 4 and all(type(a) is RefAdapter and is_conv_adapter(a) for a in enc.adapters)
+    assert isinstance(dec.bbox_prediction_head[2], nn.Linear) and dec.temporal_objectness_head.out_features == 1
+    scope["interpolate_positional_embeddings"](NS(model=gb))
+    assert enc.img_size == 512 and tuple(enc.pos_embed.shape) == (1, 32, 32, 1280)
+    assert tuple(enc.blocks[7].attn.rel_pos_h.shape) == (63, 80) and tuple(enc.blocks[0].attn.rel_pos_h.shape) == (27, 80)
+    # what train.py does next (:279-296): unfreeze by .parameters() of the replaced containers
+    n_train = sum(p.numel() for m in (enc.adapters, dec, gb.text_hidden_fcs) for p in m.parameters())
+    assert n_train > 4 * 27 * 1280 * 1280
+    # the encoder's own structural checks accept the replaced modules (the CUDA run of the same surgery is tests/test_gpu_model.py)
+    c3 = enc.adapters[0].conv3d
+    assert tuple(c3.kernel_size) == (3, 3, 3) and c3.in_channels == c3.out_channels == 1280

@@ -224,3 +224,46 @@ def test_clip_adapters_vs_reference_classes():
     for k, xp in pools.items():
         np.testing.assert_allclose(oc.adaptive_avgpool3d_tokens(xp.double()).numpy(), g[k + "64"], rtol=0, atol=1e-12)
         np.testing.assert_allclose(oc.adaptive_avgpool3d_tokens(xp).numpy(), g[k + "64"], rtol=0, atol=1e-6)
+
+
+def test_decision_utilities_vs_reference():
+    """centre-in-box (eval_youcookinteractions.py:8-51), video IoU with strict '>' recalls (eval_vidstg.py:157-186) and the validation
+    GIoU / objectness-accuracy sums (train.py:821-840) against the reference's own code (tests/golden/decisions.npz): decisions exact."""
+    g = _g("decisions")
+    acc, correct, valid, flags = box_eval.localization_accuracy(g["cib_pred"], g["cib_gt"], g["cib_kinds"])
+    assert [acc, correct, valid] == g["cib_result"].tolist()
+    assert np.array_equal(flags, g["cib_flags"])
+    for v in range(g["viou_gt"].shape[0]):
+        viou, over, ious = box_eval.video_viou(g["viou_pred"][v], g["viou_gt"][v], [0.3, 0.5])
+        assert viou == g["viou_value"][v] and over == g["viou_over"][v].tolist()          # bit-exact float64, exact flags
+        assert np.array_equal(np.array(ious, dtype=np.float64), g["viou_frame"][v])
+    assert g["viou_value"][4] == 0.5 and g["viou_over"][4].tolist() == [1, 0]             # the strictness case is really in the fixture
+    pb, lg, go, gt = g["val_boxes"], g["val_logits"], g["val_obj"], g["val_gt"]
+    V, T = pb.shape[:2]
+    for variant, cast in (("f", lambda a: a), ("i", lambda a: a.astype(np.int32))):
+        out = box_eval.val_giou_and_objectness_accuracy([[pb[v, f] for f in range(T)] for v in range(V)], [[lg[v, f] for f in range(T)] for v in range(V)],
+                                                         [[cast(gt[v, f][go[v, f].astype(bool)]) for f in range(T)] for v in range(V)],
+                                                         [[go[v, f] for f in range(T)] for v in range(V)])
+        ref = g[f"val_{variant}"]
+        assert list(out[1:]) == ref[1:].tolist()                                           # hits and counts: exact
+        np.testing.assert_allclose(out[0], ref[0], rtol=1e-6)
+
+
+def test_infer_postprocess_vs_reference():
+    """_generate_and_postprocess_masks(infer=True) at the real decoder width with a threshold that splits the predictions
+    (tests/golden/glue_infer.npz): un-normalise, xyxy, keep sigmoid(logit) > thr, ragged per-frame lists."""
+    g = _g("glue_infer")
+    dim, mlp, G, T, seed = [int(x) for x in g["meta"]]
+    reps = g["reps"].tolist()
+    sd = synth.synth_state_dict(synth.decoder_param_shapes(dim, mlp), seed)
+    emb = synth.synth_tensor("glue_infer_dec.emb", (2 * T, dim, G, G), seed)
+    txt = synth.synth_tensor("glue_infer_dec.txt", (sum(reps), 1, dim), seed)
+    with torch.no_grad():
+        pe = og.dense_pe(sd["prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"], G)
+        boxes, logits = og.box_decoder(emb.double(), pe.double(), txt.double(), reps, {k: v.double() for k, v in sd.items()})
+        sizes = [tuple(int(x) for x in s) for s in g["sizes"]]
+        ib, il = og.postprocess(boxes.float(), logits.float(), reps, T, sizes, infer=True, thr=float(g["thr"]))
+    assert 0 < g["infer_counts"].sum() < sum(reps)
+    assert [b.shape[0] for v in ib for b in v] == g["infer_counts"].tolist()
+    np.testing.assert_allclose(torch.cat([b for v in ib for b in v]).numpy(), g["infer_boxes"], atol=1e-3)
+    np.testing.assert_allclose(torch.cat([l for v in il for l in v]).numpy(), g["infer_logits"], atol=2e-5)

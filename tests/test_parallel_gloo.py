@@ -14,7 +14,7 @@ from oracle import box_eval
 
 def _fake_window_fn(P):
     # a deterministic stand-in for the per-window hot path: the record of frame t, phrase p is a function of (t, p)
-    def fn(frame_ids):
+    def fn(frame_ids, out=None):
         t = torch.tensor(frame_ids, dtype=torch.float32)[:, None, None]
         p = torch.arange(P, dtype=torch.float32)[None, :, None]
         k = torch.arange(5, dtype=torch.float32)[None, None, :]
@@ -40,7 +40,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,num_frames", [(2, 128), (2, 40), (3, 64)])
+@pytest.mark.parametrize("world,num_frames", [(2, 128), (2, 40), (3, 64), (2, 50), (3, 61)])
 def test_sharded_clip_allgather_matches_single_process(world, num_frames):
     P = 16 if num_frames == 128 else 3
     ref = parallel.ground_sharded_clip(_fake_window_fn(P), num_frames, P)       # world size 1 path
@@ -54,7 +54,7 @@ def test_sharded_clip_allgather_matches_single_process(world, num_frames):
 
 
 def test_window_schedule_matches_reference_port():
-    for n in (8, 48, 64, 128):
+    for n in (8, 48, 50, 61, 64, 128):
         assert parallel.sliding_segment_with_mask(n, 8) == box_eval.sliding_segment_with_mask(n, 8)
     assert parallel.units_of_rank(16, 8, 3) == [3, 11]
     assert sorted(sum((parallel.units_of_rank(5, 2, r) for r in range(2)), [])) == list(range(5))
