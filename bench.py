@@ -171,9 +171,26 @@ def cpu_reference_step(sd, cfg, inputs, dev="cpu"):
 
 SAMPLE_DESC = ("layer-sampled 8-frame 1024^2 clip per step: patch embed, 1 of 8 windowed blocks, 1 of 4 global blocks + Conv3d adapter, neck, "
                "text projection, full box decoder (8 frames x 4 phrases) executed in fp32 on the host cores; step time = sum of parts x block counts")
+FULL_DESC = ("ONE full, un-sampled pass of the oracle port over the whole workload (8 frames at 1024^2, all 12 blocks, 4 adapters, neck, text "
+             "projection, box decoder for 8 x 4 instances), fp32, all host threads")
+
+
+def cpu_reference_full_pass(sd, cfg, inputs):
+    """One complete fp32 pass of the reference algorithm (oracle port) over one clip on the host cores; returns seconds."""
+    from oracle import grounding as og
+    images, hidden, ids = inputs
+    mask = og.create_det_token_mask(ids, 32005)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        og.grounding_forward(images.float(), hidden.float(), mask, sd, depth=cfg["depth"], heads=cfg["heads"], global_idx=cfg["global_idx"],
+                             num_frames=FRAMES)
+    return time.perf_counter() - t0
 
 
 def run_reference(args, rank):
+    """The reference arm: the reference's algorithm for the path (oracle port; the reference is pure PyTorch and does not travel) on the host
+    cores.  `value` comes from ONE full un-sampled pass; the K timed steps are bounded layer-sampled passes (so the run ends within minutes)
+    whose real wall time is `ms_per_step`; their extrapolation to a full clip is a secondary field."""
     if rank != 0:
         return
     from oracle import synth
@@ -186,16 +203,24 @@ def run_reference(args, rank):
     inputs = synth_inputs(1)[0]
     for _ in range(args.warmup):
         cpu_reference_step(sd, cfg, inputs)
+    wall0 = time.perf_counter()
     tot = 0.0
     for _ in range(args.steps):
         s, _ = cpu_reference_step(sd, cfg, inputs)
         tot += s
-    v = FRAMES * args.steps / tot
+    wall = time.perf_counter() - wall0
+    full_s = cpu_reference_full_pass(sd, cfg, inputs)
+    v = FRAMES / full_s
     _emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                      "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                      "data": "synthetic", "config": workload_config(args.gpus),
-                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": SAMPLE_DESC},
-                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+           "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": workload_config(args.gpus),
+           "step_definition": "each of the K timed steps is a bounded layer-sampled pass (ms_per_step is its real wall time); `value` is measured on "
+                              "one full un-sampled pass run after them",
+           "full_pass_ms": 1e3 * full_s,
+           "sampled_extrapolation": {"value": FRAMES * args.steps / tot if tot > 0 else None, "unit": UNIT, "ms_per_full_step_extrapolated": 1e3 * tot / max(args.steps, 1),
+                                     "how": SAMPLE_DESC},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": FULL_DESC},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 def workload_config(n):
@@ -205,7 +230,8 @@ def workload_config(n):
                         f"{PHRASES} phrases per GPU ({cfgname})", "frames_per_step_per_gpu": FRAMES * VIDEOS, "phrases": PHRASES,
             "image_size": IMG, "sharding": f"by video, {n} GPU(s), no data-path collective",
             "l2": "4 rotating input sets (220 MB) and a ~3 GB per-step activation working set, both larger than the 126 MB L2",
-            "launch": "encoder block stack replayed as one CUDA graph (image_encoder.enable_cuda_graphs), decoder launched kernel by kernel"}
+            "launch": "the whole step (im2col, encoder, [DET] gather + text projection, box decoder, heads) replayed as ONE CUDA graph "
+                      "(GroundingBranch.enable_cuda_graphs); [DET] bookkeeping on the host before the launch, no host sync inside the step"}
 
 
 _REAL_STDOUT = None
@@ -235,7 +261,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="grove_b200", choices=["grove_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graphs", action="store_true", help="launch the encoder kernel by kernel instead of replaying its CUDA graph")
+    ap.add_argument("--no-graphs", action="store_true", help="launch kernel by kernel instead of replaying the whole-step CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary legs (config5: long clip + all-gather; config3: ViT-H share)")
     ap.add_argument("--vit", default="vit_b", choices=["vit_b", "vit_l", "vit_h"], help="non-default workloads are for profiling only")
     ap.add_argument("--videos", type=int, default=1, help="videos per GPU per step (BASELINE configs[2] = vit_h with 2)")
     args = ap.parse_args()
@@ -255,24 +282,24 @@ def main():
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner there)
         dist.init_process_group("nccl", device_id=dev)
-    from grove_b200 import ops
+    from grove_b200 import ops, parallel
     gb, sd, cfg = build_model(dev)
-    gb.grounding_encoder.image_encoder.enable_cuda_graphs(not args.no_graphs)   # serving mode (frozen weights): the block stack is one graph replay
+    gb.enable_cuda_graphs(not args.no_graphs)   # serving mode (frozen weights): the whole step is one graph replay
     host_sets = [tuple(t.pin_memory() for t in s) for s in synth_inputs(4, 100 + 10 * rank)]
-    dev_sets = [tuple(t.to(dev) for t in s) for s in host_sets]
+    dev_sets = [tuple(t.to(dev) for t in s[:2]) for s in host_sets]
 
     def step_resident(i):
-        images, hidden, ids = dev_sets[i % len(dev_sets)]
-        mask = gb._create_det_token_mask(ids)
+        # images and hidden states resident in HBM; input_ids are host-resident (they come from the tokenizer), so the [DET] mask is built on
+        # the host and nothing inside the step waits for the device
+        images, hidden = dev_sets[i % len(dev_sets)]
+        mask = gb._create_det_token_mask(host_sets[i % len(host_sets)][2])
         return gb.ground(images, hidden, mask, infer=False)
 
     def step_e2e(i):
-        images, hidden, ids = (t.to(dev, non_blocking=True) for t in host_sets[i % len(host_sets)])
+        images, hidden, ids = host_sets[i % len(host_sets)]                  # pinned host memory
         mask = gb._create_det_token_mask(ids)
-        _, (boxes, logits) = gb.ground(images, hidden, mask, infer=False)
-        b = torch.cat([x for v in boxes for x in v]).float()
-        l = torch.cat([x for v in logits for x in v]).float()
-        return torch.cat([b, l[:, None]], 1).cpu()      # device -> host read of the step's result (boxes + objectness)
+        _, rec, _ = gb.ground_records(images, hidden, mask, copy_out=False)  # uploads, grounds; records [B,5] = boxes + objectness logit
+        return rec.cpu()                                                    # device -> host read of the step's result (blocking)
 
     def loop_e2e(first, n):
         # the serving loop of the public API: pinned host batches in, packed host results out, uploads / read-backs overlapped
@@ -331,6 +358,16 @@ def main():
     ms_e2e_sync, _ = timed(step_e2e, args.steps, max(args.warmup, 3))       # one blocking call per step (no overlap)
     ms_e2e = timed_loop(loop_e2e, args.steps, max(args.warmup, 3))           # GroundingBranch.ground_host_stream
 
+    # ---- secondary legs: BASELINE configs[4] (long clip split by window + packed NCCL all-gather) and configs[2] (ViT-H, 2 videos per GPU)
+    extras = {}
+    if not args.no_extras and (VIT, VIDEOS) == ("vit_b", 1):
+        extras["config5"] = bench_config5(gb, dev_sets, dev, world, dist, parallel, ops)
+    if not args.no_extras and (VIT, VIDEOS) == ("vit_b", 1):
+        try:
+            extras["config3"] = bench_config3(dev, world, dist, ops)
+        except Exception as e:   # the secondary leg must never take the headline down
+            extras["config3"] = {"error": repr(e)[:200]}
+
     # ---- per-kernel device time of the tensor-core GEMM (the dominant kernel), CUDA events on the launching stream
     rec = []
     orig_gemm, orig_conv = ops.gemm, ops.conv_gemm
@@ -347,7 +384,8 @@ def main():
     g_w = wrap(orig_gemm, lambda a, w, out, **k: 2.0 * a.shape[0] * a.shape[1] * w.shape[0])
     c_w = wrap(orig_conv, lambda x, wp, out, **k: 2.0 * out.shape[0] * wp.shape[0] * wp.shape[1])
     ops.gemm, ops.conv_gemm = g_w, c_w
-    gb.grounding_encoder.image_encoder.enable_cuda_graphs(False)    # per-launch events need kernel-by-kernel launches
+    gb.enable_cuda_graphs(False)                                     # per-launch events need kernel-by-kernel launches
+    gb.grounding_encoder.image_encoder.enable_cuda_graphs(False)
     for i in range(2):
         rec.clear()
         step_resident(i)
@@ -367,15 +405,15 @@ def main():
     if rank == 0:
         value = world * TOT * args.steps / (ms * 1e-3)
         e2e_v = world * TOT * args.steps / (ms_e2e_sync * 1e-3)
-        h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
+        h2d = sum(t.numel() * t.element_size() for t in host_sets[0][:2]) + 4 * PHRASES * VIDEOS
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOT * PHRASES * 5 * 4,
-                        "api": "one GroundingBranch.ground() call per step on pinned host inputs: upload, ground, read the boxes back (blocking)",
+                        "api": "one GroundingBranch.ground_records() call per step on pinned host inputs: upload (images, hidden states, [DET] row "
+                               "indices), ground, read the packed boxes + objectness back (blocking)",
                         "pipelined_value": world * TOT * args.steps / (ms_e2e * 1e-3),
-                        "pipelined_api": "GroundingBranch.ground_host_stream (next upload / previous read-back overlap the current step); "
-                                         "measured 437-518 frames/s across pool boxes, so the blocking figure is the headline"},
+                        "pipelined_api": "GroundingBranch.ground_host_stream (next upload / previous read-back overlap the current step)"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                              "frac": achieved / pk["bf16_tflops_sustained"], "traffic": NCU_TRAFFIC_BYTES,
@@ -384,15 +422,109 @@ def main():
                                        % (len(rec), gemm_ms, gemm_flops / 1e12),
                              "peak_source": pk["src"] + " cuBLAS bf16 sustained (kernel timed inside a long step)",
                              "step_useful_tflops": step_tflops, "step_frac_of_peak": step_tflops / pk["bf16_tflops_sustained"],
+                             "step_frac_of_burst_peak": step_tflops / pk["bf16_tflops"], "step_frac_of_nominal_2250": step_tflops / 2250.0,
                              "gemm_share_of_step": gemm_ms / step_ms}}
+        line.update(extras)
         if not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
             cpu_sd = {k: v.float() for k, v in sd.items()}
-            sec, _ = cpu_reference_step(cpu_sd, cfg, tuple(t.clone() for t in host_sets[0]))
-            line["cpu_baseline"] = {"value": FRAMES / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": SAMPLE_DESC}
+            sec = cpu_reference_full_pass(cpu_sd, cfg, tuple(t.clone() for t in host_sets[0]))
+            line["cpu_baseline"] = {"value": FRAMES / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": FULL_DESC}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _max_over_ranks(x, dev, world, dist):
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_config5(gb, dev_sets, dev, world, dist, parallel, ops, frames=128, phrases=16, reps=3):
+    """BASELINE configs[4]: ONE long clip of 128 frames x 16 phrases (same ViT-B, 1024^2), its sixteen 8-frame windows split over the ranks
+    (window w -> rank w mod N), records written into the all-gather buffer, one NCCL all-gather of packed [frames/N * 16, 5] fp32, temporal
+    re-assembly.  Strong scaling (total work fixed).  Times the whole clip and the collective alone with CUDA events (max over ranks)."""
+    from oracle import synth
+    clip = torch.cat([d[0] for d in dev_sets], 2)                    # 32 distinct synthetic frames ...
+    clip = torch.cat([clip] * (frames // clip.shape[2]), 2)          # ... tiled to 128 (every rank builds the same clip)
+    hidden = dev_sets[0][1]
+    ids = torch.full((1, SEQ_L - 575), 7, dtype=torch.long)
+    for p in synth.det_positions(SEQ_L, phrases, 77):
+        ids[0, p - 575 + 1] = 32005
+    mask = gb._create_det_token_mask(ids)
+    parallel.ground_long_clip(gb, clip, hidden, mask)               # warm-up (captures the 16-phrase graph, creates the communicator's buffers)
+    clip_ms, ag_us = [], []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        tm = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = parallel.ground_long_clip(gb, clip, hidden, mask, timings=tm)
+        e1.record()
+        torch.cuda.synchronize()
+        clip_ms.append(_max_over_ranks(e0.elapsed_time(e1), dev, world, dist))
+        if "allgather" in tm:
+            ag_us.append(_max_over_ranks(1e3 * tm["allgather"][0].elapsed_time(tm["allgather"][1]), dev, world, dist))
+    best = min(clip_ms)
+    return {"workload": f"1 clip x {frames} frames x {phrases} phrases, ViT-B at {IMG}^2, {frames // 8} windows split over {world} GPU(s)",
+            "clip_ms": best, "frames_per_s": frames / (best * 1e-3), "allgather_us": (min(ag_us) if ag_us else None),
+            "allgather_bytes_per_rank": (frames // 8 + world - 1) // world * 8 * phrases * 5 * 4, "scaling": "strong",
+            "records_shape": list(out.shape), "collective": "dist.all_gather_into_tensor (NCCL) on the compute stream" if world > 1 else None}
+
+
+def bench_config3(dev, world, dist, ops, videos=2, steps=5, warmup=2):
+    """BASELINE configs[2], one GPU's share: SAM ViT-H (the model GROVE builds, GROVE.py:55) + box decoder on 2 videos x 8 frames at 1024^2 with
+    4 phrases each; random-init weights of that architecture (torch default init on the device, zero-initialised tables re-randomised)."""
+    from grove_b200.modeling.grounding import GroundingBranch
+    from oracle import synth
+    from oracle.grounding import VIT_CFG
+    cfg = VIT_CFG["vit_h"]
+    torch.manual_seed(1234)
+    gh = GroundingBranch(vit="vit_h", num_frames=FRAMES, image_size=IMG).to(dev)
+    enc = gh.grounding_encoder.image_encoder
+    with torch.no_grad():
+        enc.pos_embed.normal_(std=0.02)
+        for blk in enc.blocks:
+            blk.attn.rel_pos_h.normal_(std=0.02); blk.attn.rel_pos_w.normal_(std=0.02)
+        for a in enc.adapters:
+            a.alpha.fill_(0.5)
+    gh.enable_cuda_graphs(True)
+    g = torch.Generator(device=dev).manual_seed(5 + int(os.environ.get("RANK", 0)))
+    sets = []
+    for i in range(2):
+        images = torch.randn(videos, 3, FRAMES, IMG, IMG, device=dev, generator=g).to(torch.bfloat16)
+        hidden = torch.randn(videos, SEQ_L, 4096, device=dev, generator=g).to(torch.bfloat16)
+        ids = torch.full((videos, SEQ_L - 575), 7, dtype=torch.long)
+        for v in range(videos):
+            for p in synth.det_positions(SEQ_L, PHRASES, 300 + i + 10 * v):
+                ids[v, p - 575 + 1] = 32005
+        sets.append((images, hidden, gh._create_det_token_mask(ids)))
+    for i in range(warmup):
+        gh.ground(*sets[i % 2], infer=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        gh.ground(*sets[i % 2], infer=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world, dist) / steps
+    fl = videos * FRAMES * (useful_flops_per_frame(cfg["embed_dim"], cfg["depth"], len(cfg["global_idx"]), IMG // 16)
+                            + PHRASES * decoder_flops_per_instance((IMG // 16) ** 2))
+    pk = peaks()
+    del gh
+    torch.cuda.empty_cache()
+    return {"workload": f"SAM ViT-H + box decoder, {videos} videos x {FRAMES} frames at {IMG}^2 x {PHRASES} phrases per GPU (BASELINE configs[2] share)",
+            "ms_per_step": ms, "frames_per_s": world * videos * FRAMES / (ms * 1e-3), "steps": steps,
+            "step_useful_tflops": fl / (ms * 1e-3) / 1e12, "step_frac_of_peak": fl / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+            "scaling": "weak", "weights": "torch default random init (not the deterministic synth set: 818 M parameters)"}
 
 
 if __name__ == "__main__":

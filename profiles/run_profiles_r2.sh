@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round-2 measurement pass on one B200 (run under gpurun): GPU parity tests, default bench line, ncu launch list of one step.
+#   gpurun --timeout 1500 -- 'bash profiles/run_profiles_r2.sh [tag]'
+TAG=${1:-r2}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu.log
+tail -5 gpurun_out/${TAG}_pytest_gpu.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
+echo "bench rc=$?"; cat gpurun_out/${TAG}_bench_n1.json
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python profiles/profile_step.py > gpurun_out/${TAG}_launches.log 2>&1
+echo "ncu rc=$?"
+python profiles/summarize_launches.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.txt 2>&1
+tail -40 gpurun_out/${TAG}_launches_summary.txt

@@ -261,3 +261,54 @@ def test_box_utilities_bit_exact(ops):
         assert torch.equal(keep.bool(), torch.sigmoid(logits) > thr)
         ref = og.box_cxcywh_to_xyxy(og.unnormalize_bboxes(boxes, 1280.0, 720.0))
         assert torch.equal(xyxy, ref)
+
+
+def test_decision_utilities_bit_exact(ops):
+    """centre-in-box, video IoU + strict recall flags and the validation sums on the GPU against the REFERENCE's own code
+    (tests/golden/decisions.npz) and, on larger random problems, against the oracle port: decisions and float64 values bit-exact."""
+    from conftest import GOLDEN
+    import os
+    from grove_b200 import box_eval as be
+    from oracle import box_eval as ob
+    g = np.load(os.path.join(GOLDEN, "decisions.npz"))
+    # the reference-shaped call: dicts of clips, empty ground truth skipped, None / NaN predictions valid but wrong
+    pred, gt, kinds = g["cib_pred"], g["cib_gt"], g["cib_kinds"]
+    gt_data, pred_dict = [], {}
+    for c in range(3):
+        sl = slice(8 * c, 8 * c + 8)
+        gt_data.append({"video_id": f"v{c}", "segment_youcook_idx": c,
+                        "segment_bboxes": [[] if k == 1 else tuple(float(v) for v in b) for b, k in zip(gt[sl], kinds[sl])]})
+        pred_dict[f"v{c}_{c}"] = {"final_boxes": [None if k == 2 else np.array([p]) for p, k in zip(pred[sl], kinds[sl])]}
+    assert list(be.evaluate_dataset_localization(pred_dict, gt_data, "youcook")) == g["cib_result"].tolist()
+    ok = np.isin(kinds, (0, 3))
+    assert np.array_equal(be.center_in_box(pred[ok], gt[ok]), g["cib_flags"][ok])
+    for v in range(g["viou_gt"].shape[0]):
+        viou, over, ious = be.viou_over_threshold(g["viou_pred"][v], g["viou_gt"][v], (0.3, 0.5))
+        assert viou == g["viou_value"][v] and [over[0.3], over[0.5]] == g["viou_over"][v].tolist()
+        assert np.array_equal(ious, g["viou_frame"][v])
+    pb, lg, go, gtb = g["val_boxes"], g["val_logits"], g["val_obj"], g["val_gt"]
+    V, T = pb.shape[:2]
+    for variant, cast in (("f", lambda a: a), ("i", lambda a: a.astype(np.int32))):
+        out = be.val_giou_and_objectness_accuracy([[pb[v, f] for f in range(T)] for v in range(V)], [[lg[v, f] for f in range(T)] for v in range(V)],
+                                                   [[cast(gtb[v, f][go[v, f].astype(bool)]) for f in range(T)] for v in range(V)],
+                                                   [[go[v, f] for f in range(T)] for v in range(V)])
+        ref = g[f"val_{variant}"]
+        assert list(out[1:]) == ref[1:].tolist()
+        np.testing.assert_allclose(out[0], ref[0], rtol=1e-6)
+    # larger random problems vs the oracle port
+    rng = np.random.default_rng(1)
+    n = 5000
+    gt2 = np.round(rng.uniform(0, 100, (n, 2))); gt2 = np.concatenate([gt2, gt2 + np.round(rng.uniform(1, 50, (n, 2)))], 1)
+    pr2 = np.round(gt2 + rng.uniform(-40, 40, (n, 4)))          # integer coordinates: many centres land exactly on a box edge
+    flags = be.center_in_box(pr2, gt2)
+    want = np.array([ob.center_in_box(p, q) for p, q in zip(pr2.tolist(), gt2.tolist())], dtype=np.uint8)
+    assert np.array_equal(flags, want) and 0 < want.sum() < n
+    for trial in range(20):
+        m = int(rng.integers(1, 40))
+        q = rng.uniform(0, 100, (m, 2)); q = np.concatenate([q, q + rng.uniform(5, 60, (m, 2))], 1)
+        p_ = q + rng.uniform(-15, 15, (m, 4))
+        p_[rng.uniform(size=m) < 0.1] = 0.0
+        thr = (0.1, 0.3, 0.5, 0.7)
+        viou, over, ious = be.viou_over_threshold(p_, q, thr)
+        rv, rover, rious = ob.video_viou(p_, q, thr)
+        assert viou == rv and [over[t] for t in thr] == rover and np.array_equal(ious, np.array(rious, dtype=np.float64))

@@ -169,7 +169,7 @@ def _end_to_end(vit, img, V, P, seed):
     print(f"{vit}@{img} V={V}: max|dbox|={eb:.2e} max|dlogit|={el:.2e} min|ref logit|={float(rl.abs().min()):.3f}")
     assert reps == [P] * (8 * V)
     assert eb < BOX_TOL and el < LOGIT_TOL
-    safe = rl.abs() > LOGIT_TOL          # decisions are well-defined only outside the float tolerance band of the threshold
+    safe = rl.abs() > 3 * max(el, 1e-4)   # a decision can legitimately flip only where the logit is closer to the threshold than the drift (3x margin)
     assert torch.equal((torch.sigmoid(l) > 0.5)[safe], (torch.sigmoid(rl) > 0.5)[safe])
 
 
@@ -181,31 +181,6 @@ def test_end_to_end_config2():
 def test_end_to_end_config3_one_gpu_share():
     """BASELINE config 3 as seen by ONE of the 8 GPUs: ViT-H (head dim 80), 2 videos x 8 frames at 1024^2, 4 phrases each."""
     _end_to_end("vit_h", 1024, 2, 4, 22)
-
-
-def test_sharded_long_clip_single_rank():
-    """BASELINE config 5 on one rank: a 32-frame clip cut into the reference's strided 8-frame windows (infer_iground.py:110-148),
-    each grounded by the real pipeline, records re-assembled in temporal order; equals grounding the windows directly."""
-    from grove_b200 import parallel
-    from grove_b200.modeling.grounding import GroundingBranch
-    seed, img, L, P, Ftot = 23, 512, 640, 3, 32
-    gb = GroundingBranch(vit="vit_b", num_frames=8, image_size=img).cuda()
-    clip = synth.synth_tensor("clip.images", (1, 3, Ftot, img, img), seed).cuda().to(torch.bfloat16)
-    hid = synth.synth_tensor("clip.hidden", (1, L, 4096), seed).cuda().to(torch.bfloat16)
-    ids = torch.full((1, L - 575), 7, dtype=torch.long)
-    for p in synth.det_positions(L, P, seed):
-        ids[0, p - 575 + 1] = gb.det_token_idx
-    mask = gb._create_det_token_mask(ids.cuda())
-
-    def window_fn(frame_ids):
-        _, (b, l) = gb.ground(clip[:, :, frame_ids].contiguous(), hid, mask, infer=False)
-        return parallel.pack_records(b, l)
-    out = parallel.ground_sharded_clip(window_fn, Ftot, P)
-    assert out.shape == (Ftot, P, 5)
-    windows, _ = parallel.sliding_segment_with_mask(Ftot, 8)
-    rec = window_fn(windows[1])
-    assert torch.equal(out[windows[1]], rec.float())
-    assert torch.isfinite(out).all() and float(out[..., :4].min()) > 0 and float(out[..., :4].max()) < 1
 
 
 def test_serving_loop_graph_replay_and_host_stream():
@@ -246,8 +221,198 @@ def test_serving_loop_graph_replay_and_host_stream():
     assert len(streamed) == 3
     for a, b in zip(eager, streamed):
         assert torch.equal(a, b)
+    # infer=True: unfiltered pixel boxes + logit + keep flag, [sum P, 6] (the ragged per-frame lists of ground(infer=True) hold the same rows)
+    gb.config.temp_objectness_threshold = float(torch.sigmoid(eager[0][:, 4]).median())      # make the threshold bite
+    inf = list(gb.ground_host_stream(iter(batches), orig_sizes=[(1280, 720)], infer=True))
+    for i, rec in enumerate(inf):
+        assert rec.shape == (8 * P, 6) and torch.equal(rec[:, 4], eager[i][:, 4])
+        images, hid, ids = (t.cuda() for t in batches[i])
+        _, (ib, il) = gb.ground(images, hid, gb._create_det_token_mask(ids), orig_sizes=[(1280, 720)], infer=True)
+        kept = rec[rec[:, 5] > 0][:, :4]
+        assert 0 < kept.shape[0] < 8 * P
+        assert torch.allclose(kept, torch.cat([b for v in ib for b in v]).float().cpu(), atol=0.51)   # ground() rounds the boxes to bf16 (pixels)
+    # the whole-step graph of GroundingBranch (encoder + text projection + decoder + heads in one replay)
+    gb.enable_cuda_graphs(True)
+    whole = [direct(b) for b in batches]
+    gb.enable_cuda_graphs(False)
+    for a, b in zip(eager, whole):
+        assert torch.equal(a, b)
     with torch.no_grad():                            # in-place weight update -> new signature -> re-capture
         enc.blocks[0].mlp.lin1.bias.add_(0.25)
     changed = direct(batches[0])
     enc.enable_cuda_graphs(False)
     assert torch.equal(changed, direct(batches[0])) and not torch.equal(changed, eager[0])
+
+
+def _branch_with_weights(vit, img, seed, num_frames=8, **kw):
+    from grove_b200.modeling.grounding import GroundingBranch
+    from oracle.grounding import VIT_CFG
+    cfg = VIT_CFG[vit]
+    gb = GroundingBranch(vit=vit, num_frames=num_frames, image_size=img, **kw)
+    sd = synth.synth_state_dict({**synth.encoder_param_shapes(cfg["embed_dim"], cfg["depth"], cfg["heads"], cfg["global_idx"], img // 16),
+                                 **synth.decoder_param_shapes()}, seed)
+    fsd = synth.synth_state_dict(synth.text_fcs_shapes(), seed)
+    gb.grounding_encoder.load_state_dict(sd, strict=False)
+    gb.text_hidden_fcs.load_state_dict({k[len("text_hidden_fcs."):]: v for k, v in fsd.items()})
+    full = {**{k: v.cuda() for k, v in sd.items()}, **{k: v.cuda() for k, v in fsd.items()}}
+    return gb.cuda(), cfg, full
+
+
+def test_infer_postprocess_vs_reference_golden():
+    """_generate_and_postprocess_masks(infer=True) on the GPU against the REFERENCE's own method (tests/golden/glue_infer.npz: real decoder
+    width, threshold placed between the two middle objectness values so that half of the boxes are dropped): kept-box counts and the keep
+    decisions are exact outside 3x the measured logit drift, the surviving xyxy boxes within 1e-2 of the frame size; all P logits per frame
+    are returned (GROVE.py:297-331).  Also: ground_host_stream(infer=True) packs unfiltered rows + keep flag (no ragged concat)."""
+    g = np.load(os.path.join(GOLDEN, "glue_infer.npz"))
+    dim, mlp, G, T, seed = [int(x) for x in g["meta"]]
+    reps = g["reps"].tolist()
+    thr = float(g["thr"])
+    gb, _, _ = _branch_with_weights("vit_b", 16 * G, 3, temp_objectness_threshold=thr)
+    sd = synth.synth_state_dict(synth.decoder_param_shapes(dim, mlp), seed)
+    gb.grounding_encoder.load_state_dict({k: v for k, v in sd.items()}, strict=False)
+    gb = gb.cuda()
+    emb = synth.synth_tensor("glue_infer_dec.emb", (2 * T, dim, G, G), seed).cuda()
+    txt = synth.synth_tensor("glue_infer_dec.txt", (sum(reps), 1, dim), seed).cuda()
+    pred_list, s0 = [], 0
+    for r in reps:
+        pred_list.append(txt[s0:s0 + r, 0]); s0 += r
+    sizes = [tuple(int(x) for x in s) for s in g["sizes"]]
+    dense_pe = gb.grounding_encoder.prompt_encoder.get_dense_pe()
+    tb, tl = gb._generate_and_postprocess_masks(pred_list, emb, sizes, dense_pe, infer=False)
+    ib, il = gb._generate_and_postprocess_masks(pred_list, emb, sizes, dense_pe, infer=True)
+    torch.cuda.synchronize()
+    logits = torch.cat([l for v in il for l in v]).float().cpu().numpy()
+    drift = float(np.abs(logits - g["infer_logits"]).max())
+    eb = float(np.abs(torch.cat([b for v in tb for b in v]).float().cpu().numpy() - g["train_boxes"]).max())
+    print(f"infer post-process: logit drift {drift:.2e}, box drift {eb:.2e}")
+    assert drift < LOGIT_TOL and eb < BOX_TOL
+    assert [l.shape[0] for v in il for l in v] == reps                     # every logit of the frame, also where boxes were dropped
+    ref_keep = 1.0 / (1.0 + np.exp(-g["infer_logits"].astype(np.float64))) > thr
+    got_counts = [b.shape[0] for v in ib for b in v]
+    logit_thr = float(np.log(thr / (1 - thr)))
+    safe = np.abs(g["infer_logits"] - logit_thr) > 3 * max(drift, 1e-4)    # a logit closer to the threshold than the drift may legitimately flip
+    got_keep = (torch.sigmoid(torch.from_numpy(logits)) > thr).numpy()
+    assert (got_keep[safe] == ref_keep[safe]).all() and safe.sum() >= len(safe) - 2
+    if safe.all():
+        assert got_counts == g["infer_counts"].tolist()
+        # boxes of the kept rows, in pixels of the original frame
+        got = torch.cat([b for v in ib for b in v]).float().cpu().numpy()
+        scale = np.repeat(np.array([max(sizes[i // T]) for i in range(2 * T)]), g["infer_counts"])[:, None]
+        assert float((np.abs(got - g["infer_boxes"]) / scale).max()) < BOX_TOL
+    assert sum(got_counts) == int(got_keep.sum()) and 0 < sum(got_counts) < sum(reps)
+
+
+def test_foreign_adapter_class_is_accepted():
+    """train.py:170-176 replaces `image_encoder.adapters` with instances of the REFERENCE's adapter class.  Any module exposing `.conv3d`
+    and `.alpha` must run (structural check, not isinstance) and give the same output as the built-in container with the same weights."""
+    from helpers import encoder_with_weights
+
+    class ForeignAdapter(torch.nn.Module):                   # what the reference's class looks like from outside (image_encoder.py:40-46)
+        def __init__(self, cin, cout, ks):
+            super().__init__()
+            self.conv3d = torch.nn.Conv3d(cin, cout, ks, padding="same")
+            self.relu = torch.nn.ReLU()
+            self.alpha = torch.nn.Parameter(torch.zeros([1]))
+            self.tanh = torch.nn.Tanh()
+
+    sam, sd, cfg = encoder_with_weights("vit_b", 512, 17)
+    enc = sam.image_encoder
+    images = synth.synth_tensor("foreign.images", (1, 3, 8, 512, 512), 17).cuda().to(torch.bfloat16)
+    want = enc(images).float()
+    old = enc.adapters
+    c = old[0].conv3d
+    enc.adapters = torch.nn.ModuleList([ForeignAdapter(c.in_channels, c.out_channels, c.kernel_size) for _ in old]).cuda()
+    enc.adapters.load_state_dict(old.state_dict())
+    got = enc(images).float()
+    assert torch.equal(got, want)
+    # and through the training step (encoder_train takes the same structural check)
+    from grove_b200.modeling.encoder_train import encode_train
+    tok, tape = encode_train(enc, images)
+    assert tok.shape[0] == 8 and torch.isfinite(tok.float()).all()
+
+
+def _long_clip_case(gb, cfg, full, Ftot, P, img, seed):
+    L = 640
+    clip = synth.synth_tensor("clip5.images", (1, 3, Ftot, img, img), seed).to(torch.bfloat16).cuda()
+    hid = synth.synth_tensor("clip5.hidden", (1, L, 4096), seed).to(torch.bfloat16).cuda()
+    ids = torch.full((1, L - 575), 7, dtype=torch.long)
+    for p in synth.det_positions(L, P, seed):
+        ids[0, p - 575 + 1] = gb.det_token_idx
+    return clip, hid, gb._create_det_token_mask(ids)
+
+
+def _oracle_long_clip(cfg, full, clip, hid, mask, Ftot, P):
+    """per-window oracle.grounding_forward with the reference's schedule and first-seen masks (infer_iground.py:110-148, 245-288)"""
+    from grove_b200 import parallel
+    windows, masks = parallel.sliding_segment_with_mask(Ftot, 8)
+    ref = torch.zeros(Ftot, P, 5, device="cuda")
+    dmask = mask.cuda()
+    for idx, msk in zip(windows, masks):
+        with torch.no_grad():
+            _, rb, rl, reps = og.grounding_forward(clip[:, :, idx].float(), hid.float(), dmask, full, depth=cfg["depth"], heads=cfg["heads"],
+                                                   global_idx=cfg["global_idx"])
+        rec = torch.cat([rb.view(8, P, 4), rl.view(8, P, 1)], -1)
+        for i, (k, mk) in enumerate(zip(idx, msk)):
+            if mk:
+                ref[k] = rec[i]
+    return ref
+
+
+def test_config5_long_clip_vs_oracle():
+    """BASELINE config 5 at its stated size on one rank: 128 frames x 16 phrases (ViT-B at 512^2), cut into the reference's strided 8-frame
+    windows, every window through encoder + decoder + heads, records re-assembled in temporal order (parallel.ground_long_clip) — against
+    oracle.grounding_forward per window: boxes 1e-2, logits 2e-2, decisions exact outside 3x the measured drift.  The decoder is also run
+    in several passes (max_instances_per_pass 48 -> 3 passes of the 128 instances of a window), which must not change a bit."""
+    from grove_b200 import parallel
+    Ftot, P, img, seed = 128, 16, 512, 23
+    gb, cfg, full = _branch_with_weights("vit_b", img, seed)
+    clip, hid, mask = _long_clip_case(gb, cfg, full, Ftot, P, img, seed)
+    out = parallel.ground_long_clip(gb, clip, hid, mask)
+    assert out.shape == (Ftot, P, 5)
+    md = gb.grounding_encoder.mask_decoder
+    md.max_instances_per_pass = 48
+    out3 = parallel.ground_long_clip(gb, clip, hid, mask)
+    md.max_instances_per_pass = 256
+    assert torch.equal(out, out3)
+    gb.enable_cuda_graphs(True)                                  # the whole-step graph (one per window shape) must give the same records
+    outg = parallel.ground_long_clip(gb, clip, hid, mask)
+    gb.enable_cuda_graphs(False)
+    assert torch.equal(out, outg)
+    ref = _oracle_long_clip(cfg, full, clip, hid, mask, Ftot, P)
+    eb, el = float((out[..., :4] - ref[..., :4]).abs().max()), float((out[..., 4] - ref[..., 4]).abs().max())
+    print(f"config 5 (128 x 16): max|dbox|={eb:.2e} max|dlogit|={el:.2e}")
+    assert eb < BOX_TOL and el < LOGIT_TOL
+    safe = ref[..., 4].abs() > 3 * max(el, 1e-4)
+    assert torch.equal((out[..., 4] > 0)[safe], (ref[..., 4] > 0)[safe]) and int(safe.sum()) > 0.9 * safe.numel()
+
+
+def test_long_clip_length_not_multiple_of_eight():
+    """50-frame clip: the reference's schedule emits 6 + 2 windows of 8 frames (remainder windows re-visit frames; masks drop the repeats)"""
+    from grove_b200 import parallel
+    Ftot, P, img, seed = 50, 3, 512, 29
+    gb, cfg, full = _branch_with_weights("vit_b", img, seed)
+    clip, hid, mask = _long_clip_case(gb, cfg, full, Ftot, P, img, seed)
+    out = parallel.ground_long_clip(gb, clip, hid, mask)
+    ref = _oracle_long_clip(cfg, full, clip, hid, mask, Ftot, P)
+    eb, el = float((out[..., :4] - ref[..., :4]).abs().max()), float((out[..., 4] - ref[..., 4]).abs().max())
+    print(f"50-frame clip: max|dbox|={eb:.2e} max|dlogit|={el:.2e}")
+    assert out.shape == (Ftot, P, 5) and eb < BOX_TOL and el < LOGIT_TOL
+
+
+def test_loss_without_temporal_objectness():
+    """use_temp_objectness=False branch of _compute_loss_components_video (GROVE.py:382-408): GIoU + L1 only, vs the oracle's components"""
+    from types import SimpleNamespace as NS
+    gb, cfg, full = _branch_with_weights("vit_b", 512, 31)
+    gb.config.use_temp_objectness = False
+    g = torch.Generator().manual_seed(3)
+    T, P = 8, 3
+    pb = [[(torch.rand(P, 4, generator=g) * 0.5 + 0.2).cuda() for _ in range(T)]]
+    go = [[(torch.rand(P, generator=g) > 0.4).double() for _ in range(T)]]
+    gt = [[torch.cat([torch.rand(int(o.sum()), 2, generator=g) * 0.4 + 0.3, torch.rand(int(o.sum()), 2, generator=g) * 0.3 + 0.1], 1) for o in go[0]]]
+    loss = gb._compute_loss_components_video(pb, None, gt, go, NS(loss=torch.tensor(0.5, device="cuda")))
+    assert set(loss) == {"loss", "ce_loss", "giou_loss", "l1_loss"}
+    ref = og.loss_components(pb, [[torch.zeros(P, device="cuda") for _ in range(T)]], gt, [[o.float() for o in go[0]]],
+                             torch.tensor(0.5, device="cuda"), 1.0, 2.0, 2.0)
+    for k in ("giou_loss", "l1_loss"):
+        assert abs(float(loss[k]) - float(ref[k])) < 2e-5 * max(1.0, abs(float(ref[k]))), k
+    assert abs(float(loss["loss"]) - float(ref["ce_loss"] + ref["giou_loss"] + ref["l1_loss"])) < 1e-4

@@ -86,12 +86,14 @@ def _cmp(name, g, r, tol, worst):
     return rel, cos
 
 
-@pytest.mark.parametrize("vit,img,V,P,vjp", [("vit_b", 512, 1, 2, True), ("vit_b", 512, 1, 2, False), ("vit_b", 512, 2, 3, True),
-                                             ("vit_h", 512, 1, 2, True), ("vit_b", 1024, 1, 2, True)])
-def test_training_step_vs_oracle_autograd(vit, img, V, P, vjp):
+@pytest.mark.parametrize("vit,img,V,P,vjp,frames", [("vit_b", 512, 1, 2, True, 8), ("vit_b", 512, 1, 2, False, 8), ("vit_b", 512, 2, 3, True, 8),
+                                                    ("vit_h", 512, 1, 2, True, 8), ("vit_b", 1024, 1, 2, True, 8),
+                                                    ("vit_b", 512, 1, 4, True, 32), ("vit_b", 512, 1, 4, False, 32)])
+def test_training_step_vs_oracle_autograd(vit, img, V, P, vjp, frames):
     """vjp=True: a prescribed random cotangent of (boxes, logits) on both sides — isolates the backward pass from the forward's
-    bf16 drift (the loss' own cotangent contains sign(pred - gt) and GIoU case splits); vjp=False: the loss end to end."""
-    frames, seed = 8, 11
+    bf16 drift (the loss' own cotangent contains sign(pred - gt) and GIoU case splits); vjp=False: the loss end to end.
+    frames=32: BASELINE config 4's clip shape (config.num_frames = 32 -> four 8-frame adapter groups per clip, 4 phrases; train.py:761-782)."""
+    seed = 11
     gb, cfg, full, images, hidden, mask, gt_boxes, gt_obj = _setup(vit, img, V, frames, P, seed)
     B = V * frames * P
     cot = (synth.synth_tensor("train.dboxes", (B, 4), seed).cuda() * 0.1, synth.synth_tensor("train.dlogits", (B,), seed).cuda() * 0.1) if vjp else None
