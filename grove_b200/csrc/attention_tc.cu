@@ -43,6 +43,23 @@ __device__ __forceinline__ float ex2_fma(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// The same polynomial on two values at once with Blackwell's packed fp32 pipe (FFMA2 / FADD2): 10 issue slots per PAIR.  The softmax warps
+// are issue-bound (one instruction per clock per SM sub-partition), so everything per-element in the loops below is written on float2:
+// scale*S + rel_w is one FFMA2 per two scores, the running maximum one FMNMX3, the offset add and the row-sum one FADD2 each.
+__device__ __forceinline__ float2 ex2_fma2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 kMagic = make_float2(12582912.0f, 12582912.0f);
+  const float2 t = __fadd2_rn(x, kMagic);
+  const float2 u = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(u, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.0565415754f, 0.0565415754f), make_float2(0.242068237f, 0.242068237f));
+  p = __ffma2_rn(p, f, make_float2(0.692983806f, 0.692983806f));
+  p = __ffma2_rn(p, f, make_float2(0.999953968f, 0.999953968f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
 // warp 0 TMA, warp 1 MMA, then 4 * SPLIT softmax warps: SPLIT threads per query row (= TMEM lane), each owning 128 / SPLIT keys of a block
 template <int SPLIT> constexpr int att_threads() { return 64 + 128 * SPLIT; }
 constexpr int kVStages = 2;
@@ -248,7 +265,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(Q_TMEM));
     }
-    float relw[32];                                      // this thread's kw half (G=64) / the whole grid row (G=32)
+    float2 relw[16];                                     // this thread's kw half (G=64) / the whole grid row (G=32), as FFMA2 operand pairs
     const int kw0 = (G == 64) ? (hs & 1) * 32 : 0;       // chunk c covers kw = (c % 2) * 32 .. + 32 of a 64-wide grid row; SPLIT is even
     // ---- prologue: rel_w -> registers, rel_h -> smem (both x log2 e)
 #pragma unroll
@@ -272,16 +289,19 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       softmax_sync();                                    // both halves of every staging row are written
       if (which == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) relw[j] = stage_at(qw + (G - 1) - (kw0 + j)) * kL2e;
+        for (int j = 0; j < 32; j += 2)
+          relw[j >> 1] = make_float2(stage_at(qw + (G - 1) - (kw0 + j)) * kL2e, stage_at(qw + (G - 1) - (kw0 + j + 1)) * kL2e);
       } else {
         for (int kh = hs * (G / SPLIT); kh < (hs + 1) * (G / SPLIT); ++kh) relh_f[kh * 128 + row] = stage_at(qh + (G - 1) - kh) * kL2e;
       }
       softmax_sync();                                    // staging is rewritten by the next table / rel_h complete
     }
     const float c_scale = (HD == 64 ? 0.125f : 0.11180339887498949f) * kL2e;   // hd^-0.5 * log2(e)
+    const float2 c_scale2 = make_float2(c_scale, c_scale);
     // ---- main loop: lazy running max, probabilities, P.V
     auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(2 + quad), "n"(32 * SPLIT) : "memory"); };   // the SPLIT warps that share 32 rows
-    float m = -INFINITY, lsum = 0.f;
+    float m = -INFINITY;
+    float2 lsum2 = make_float2(0.f, 0.f);
     for (int b = 0; b < NB; ++b, ++sit) {
       const uint32_t sb = sit & 1u, pb = b & 1u;
       // S(b) complete, and P.V of block b-2 has finished reading this P buffer (both polls in flight together)
@@ -303,13 +323,13 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
         const int kh = (b * 128 + (SPLIT * cc + hs) * 32) / G;
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {                 // scale*S + rel_w is kept in place: the exponential pass adds only a per-chunk offset
-          const float e0 = fmaf(__uint_as_float(rr[cc][j]), c_scale, relw[j]);
-          const float e1 = fmaf(__uint_as_float(rr[cc][j + 1]), c_scale, relw[j + 1]);
-          rr[cc][j] = __float_as_uint(e0);
-          rr[cc][j + 1] = __float_as_uint(e1);
-          mx0 = fmaxf(mx0, e0);
-          mx1 = fmaxf(mx1, e1);
+        for (int j = 0; j < 32; j += 4) {                 // scale*S + rel_w is kept in place: the exponential pass adds only a per-chunk offset
+          const float2 e0 = __ffma2_rn(make_float2(__uint_as_float(rr[cc][j]), __uint_as_float(rr[cc][j + 1])), c_scale2, relw[j >> 1]);
+          const float2 e1 = __ffma2_rn(make_float2(__uint_as_float(rr[cc][j + 2]), __uint_as_float(rr[cc][j + 3])), c_scale2, relw[(j >> 1) + 1]);
+          rr[cc][j] = __float_as_uint(e0.x); rr[cc][j + 1] = __float_as_uint(e0.y);
+          rr[cc][j + 2] = __float_as_uint(e1.x); rr[cc][j + 3] = __float_as_uint(e1.y);
+          mx0 = fmaxf(mx0, fmaxf(e0.x, e0.y));            // FMNMX3
+          mx1 = fmaxf(mx1, fmaxf(e1.x, e1.y));
         }
         mb = fmaxf(mb, fmaxf(mx0, mx1) + relh_f[kh * 128 + row]);
       }
@@ -349,7 +369,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
           tmem_st_wait();
           tc_fence_before();
         }
-        lsum *= fac;
+        lsum2 = __fmul2_rn(lsum2, make_float2(fac, fac));
         m = m_new;
       }
 #pragma unroll
@@ -357,17 +377,22 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
         const int c = SPLIT * cc + hs;
         const int kh = (b * 128 + c * 32) / G;
         const float off = relh_f[kh * 128 + row] - m;
+        const float2 off2 = make_float2(off, off);
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float p0, p1;
-          const float e0 = __uint_as_float(rr[cc][j]) + off;
-          const float e1 = __uint_as_float(rr[cc][j + 1]) + off;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e0));
-          if (j & 2) p1 = ex2_fma(e1);                    // one exponential in four on the FMA pipe
-          else asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e1));
-          lsum += p0 + p1;
-          pk[j >> 1] = pack_bf16(p0, p1);
+          const float2 e = __fadd2_rn(make_float2(__uint_as_float(rr[cc][j]), __uint_as_float(rr[cc][j + 1])), off2);
+          float2 p;
+          // 3 pairs in 8 take the packed FMA-pipe polynomial (10 issue slots per pair), the rest the MUFU (2 slots, 16 XU clocks per pair):
+          // balances the sub-partition's issue port against its 4-lane-per-clock exponential unit
+          if (((j >> 1) & 7) == 1 || ((j >> 1) & 7) == 4 || ((j >> 1) & 7) == 6) {
+            p = ex2_fma2(e);
+          } else {
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p.x) : "f"(e.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p.y) : "f"(e.y));
+          }
+          lsum2 = __fadd2_rn(lsum2, p);
+          pk[j >> 1] = pack_bf16(p.x, p.y);
         }
         // keys [c*32, c*32+32) of the block -> 16 packed bf16x2 columns of the P buffer in tensor memory (the A operand of P.V)
         tmem_st_32x32b_x16(tP0 + pb * 64 + c * 16 + tlane, pk);
@@ -380,6 +405,7 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       PROBE(2103 + (warp - 2) * 400 + 4 * b);
     }
     // ---- epilogue: O / l -> bf16 -> global (each thread of a row stores 64 / SPLIT of the first 64 head dims)
+    float lsum = lsum2.x + lsum2.y;
     xch_f[2 * SPLIT * 128 + hs * 128 + row] = lsum;
     softmax_sync();
 #pragma unroll

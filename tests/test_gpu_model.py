@@ -207,10 +207,14 @@ def test_serving_loop_graph_replay_and_host_stream():
 
     def direct(batch):
         images, hid, ids = (t.cuda() for t in batch)
-        _, (boxes, logits) = gb.ground(images, hid, gb._create_det_token_mask(ids), infer=False)
-        b = torch.cat([x for v in boxes for x in v]).float()
-        l = torch.cat([x for v in logits for x in v]).float()
-        return torch.cat([b, l[:, None]], 1).cpu()
+        mask = gb._create_det_token_mask(ids)
+        _, rec, reps = gb.ground_records(images, hid, mask)
+        # ground() returns the same records in the reference's nested format, rounded to the hidden-state dtype (bf16 in production)
+        _, (boxes, logits) = gb.ground(images, hid, mask, infer=False)
+        b = torch.cat([x for v in boxes for x in v])
+        l = torch.cat([x for v in logits for x in v])
+        assert reps == [P] * 8 and torch.equal(b, rec[:, :4].to(hid.dtype)) and torch.equal(l, rec[:, 4].to(hid.dtype))
+        return rec.cpu()
 
     eager = [direct(b) for b in batches]
     enc.enable_cuda_graphs(True)
