@@ -134,12 +134,13 @@ class GroundingBranch(nn.Module):
         with ops.device_of(bbox_preds):
             return ops.box_postprocess(bbox_preds.float().contiguous(), lg, size_wh, self.config.temp_objectness_threshold)
 
-    def _nested_outputs(self, bbox_preds, logits, reps, orig_sizes, infer):
-        """the slicing loop of GROVE.py:297-331: nested [V][T] lists of views into the flat [B,4] / [B] outputs"""
+    def _nested_outputs(self, bbox_preds, logits, reps, orig_sizes, infer, post=None):
+        """the slicing loop of GROVE.py:297-331: nested [V][T] lists of views into the flat [B,4] / [B] outputs.  `post` = (xyxy, keep)
+        when the caller already ran the post-process (ground() thresholds the fp32 records, not their bf16 rounding)."""
         T = self.config.num_frames
         bs = len(reps)
         if infer:
-            xyxy, keep = self._postprocess(bbox_preds, logits, reps, orig_sizes)
+            xyxy, keep = post if post is not None else self._postprocess(bbox_preds, logits, reps, orig_sizes)
             xyxy = xyxy.to(bbox_preds.dtype)
             keep = keep.bool()
         bbox_pred_list, logit_list, s = [], [], 0
@@ -445,7 +446,8 @@ class GroundingBranch(nn.Module):
         out_dtype = last_hidden_state.dtype
         boxes = rec[:, :4].to(out_dtype)
         logits = rec[:, 4].to(out_dtype) if self.config.use_temp_objectness else None
-        return emb, self._nested_outputs(boxes, logits, reps, orig_sizes, infer)
+        post = self._postprocess(rec[:, :4], rec[:, 4] if logits is not None else None, reps, orig_sizes) if infer else None
+        return emb, self._nested_outputs(boxes, logits, reps, orig_sizes, infer, post)
 
     @torch.no_grad()
     def ground_host_stream(self, host_batches, orig_sizes=None, infer=False):
