@@ -19,6 +19,20 @@ class GemmEpilogue(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
 
 
+class TwoWayAParams(C.Structure):
+    """mirror of `struct grove_twoway_a_params`"""
+    _fields_ = [(n, C.c_void_p) for n in ("wq_t", "bq", "wk_t", "bk", "wv_t", "bv", "wo_t", "bo", "ln_g", "ln_b")] + [("ln_eps", C.c_float)] + \
+               [("wq2_t", C.c_void_p), ("bq2", C.c_void_p), ("skip_pe", C.c_int)]
+
+
+class TwoWayBParams(C.Structure):
+    """mirror of `struct grove_twoway_b_params`"""
+    _fields_ = [("wo_t", C.c_void_p), ("bo", C.c_void_p), ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p), ("ln2_eps", C.c_float),
+                ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p), ("b2", C.c_void_p), ("mlp_dim", C.c_int),
+                ("ln3_g", C.c_void_p), ("ln3_b", C.c_void_p), ("ln3_eps", C.c_float),
+                ("wk_t", C.c_void_p), ("bk", C.c_void_p), ("wv_t", C.c_void_p), ("bv", C.c_void_p), ("wqf_t", C.c_void_p), ("bqf", C.c_void_p)]
+
+
 _P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES); the stream is always last
@@ -48,6 +62,9 @@ SIGNATURES = {
     "grove_decoder_i2t_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_decoder_keys_add_ln": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "grove_small_linear_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "grove_twoway_block_tokens_a_fwd": [_P, _P, C.POINTER(TwoWayAParams), _P, _P, _I, _I, _I, _P],
+    "grove_twoway_block_tokens_b_fwd": [_P, _P, _P, C.POINTER(TwoWayBParams), _P, _P, _P, _P, _I, _I, _I, _P],
+    "grove_decoder_t2i_attention_wide": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_decoder_heads_fwd": [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_token_self_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_add_layernorm_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P],

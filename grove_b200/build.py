@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgrove_b200.so")
-SOURCES = ["lib.cu", "gemm_tcgen05.cu", "encoder_ops.cu", "attention.cu", "attention_tc.cu", "attention_win_tc.cu", "decoder_ops.cu", "box_ops.cu",
+SOURCES = ["lib.cu", "gemm_tcgen05.cu", "encoder_ops.cu", "attention.cu", "attention_tc.cu", "attention_win_tc.cu", "decoder_ops.cu", "decoder_fused.cu", "box_ops.cu",
            "backward_ops.cu", "attention_bwd.cu", "decoder_bwd.cu", "preprocess.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

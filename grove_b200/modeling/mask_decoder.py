@@ -230,7 +230,90 @@ class MaskDecoder(nn.Module):
         w, b = self._w32(key + ".o", attn.out_proj)
         return ops.small_linear(att, w, b, resid=resid)
 
+    def _wt32(self, key, lin):
+        """(W^T [in, out] fp32, bias fp32): the layout of the fused token kernels"""
+        return self._pack.get(key + ".wT32", [lin.weight], lambda w: f32(w.t())), self._pack.get(key + ".b32", [lin.bias], f32)
+
+    def _fused_ok(self) -> bool:
+        tr = self.transformer
+        return (self.transformer_dim == 256 and tr.num_heads == 8 and tr.mlp_dim == 2048 and self.num_mask_tokens == 4
+                and all(l.cross_attn_token_to_image.internal_dim == 128 and l.self_attn.internal_dim == 256 for l in tr.layers))
+
     def _decode(self, tokens, keys0, shared, pe, frame_of, N, C, records):
+        """One pass of the two-way transformer + heads over <= max_instances_per_pass instances.  Token side: two fused kernels per layer
+        around the token->image attention (csrc/decoder_fused.cu); image side: tcgen05 GEMMs + the two attention kernels + norm4."""
+        if not self._fused_ok():
+            return self._decode_unfused(tokens, keys0, shared, pe, frame_of, N, C, records)
+        tr = self.transformer
+        B, T, _ = tokens.shape
+        H = tr.num_heads
+        queries = tokens
+        keys, src_of = keys0, frame_of       # layer 0 reads the per-frame keys through the index
+        qf = None
+        last = len(tr.layers) - 1
+        for li, layer in enumerate(tr.layers):
+            k = f"l{li}"
+            if layer.skip_first_layer_pe and li != 0:
+                raise NotImplementedError("skip_first_layer_pe is only meaningful on layer 0 (transformer.py:45-55)")
+            sa, ca, ia = layer.self_attn, layer.cross_attn_token_to_image, layer.cross_attn_image_to_token
+            pa = {}
+            for nm, lin in (("q", sa.q_proj), ("k", sa.k_proj), ("v", sa.v_proj), ("o", sa.out_proj)):
+                pa[f"w{nm}_t"], pa[f"b{nm}"] = self._wt32(f"{k}.sa.{nm}", lin)
+            pa["ln_g"], pa["ln_b"] = self._ln(k + ".n1", layer.norm1)
+            pa["ln_eps"] = float(layer.norm1.eps)
+            pa["wq2_t"], pa["bq2"] = self._wt32(k + ".t2i.q", ca.q_proj)
+            pa["skip_pe"] = 1 if layer.skip_first_layer_pe else 0
+            queries, qt = ops.twoway_tokens_a(queries, tokens, pa)
+            # token -> image cross attention (:164-169)
+            dh = ca.internal_dim // H
+            if li == 0:
+                kp, vp = shared["k"], shared["v"]
+            else:
+                kp = self._image_proj(k + ".t2i.k", ca.k_proj, keys, pe, N)
+                vp = self._image_proj(k + ".t2i.v", ca.v_proj, keys, None, N)
+            att = ops.t2i_attention_wide(qt, kp, vp, src_of, B, T, N, H, dh)
+            pb = {}
+            pb["wo_t"], pb["bo"] = self._wt32(k + ".t2i.o", ca.out_proj)
+            pb["ln2_g"], pb["ln2_b"] = self._ln(k + ".n2", layer.norm2)
+            pb["ln2_eps"] = float(layer.norm2.eps)
+            pb["w1_t"], pb["b1"] = self._wt32(k + ".m1", layer.mlp.lin1)
+            pb["w2_t"], pb["b2"] = self._wt32(k + ".m2", layer.mlp.lin2)
+            pb["mlp_dim"] = int(tr.mlp_dim)
+            pb["ln3_g"], pb["ln3_b"] = self._ln(k + ".n3", layer.norm3)
+            pb["ln3_eps"] = float(layer.norm3.eps)
+            pb["wk_t"], pb["bk"] = self._wt32(k + ".i2t.k", ia.k_proj)
+            pb["wv_t"], pb["bv"] = self._wt32(k + ".i2t.v", ia.v_proj)
+            fa = tr.final_attn_token_to_image
+            if li == last:
+                pb["wqf_t"], pb["bqf"] = self._wt32("f.q", fa.q_proj)
+            else:
+                pb["wqf_t"], pb["bqf"] = None, None
+            queries, kt, vt, qf = ops.twoway_tokens_b(queries, att, tokens, pb, want_qf=(li == last))
+            # image -> token cross attention, updates the keys (:175-180)
+            qi = shared["qi"] if li == 0 else self._image_proj(k + ".i2t.q", ia.q_proj, keys, pe, N)
+            ai = torch.empty(B * N, ia.internal_dim, device=tokens.device, dtype=torch.bfloat16)
+            ops.i2t_attention(qi, kt, vt, src_of, ai, B, T, N, H, ia.internal_dim // H)
+            wo, bo = self._w16(k + ".i2t.o", ia.out_proj)
+            delta = torch.empty(B * N, C, device=tokens.device, dtype=torch.float32)
+            ops.gemm(ai, wo, delta, bias=bo)
+            g, b = self._ln(k + ".n4", layer.norm4)
+            new_keys = torch.empty(B * N, C, device=tokens.device, dtype=torch.bfloat16)
+            ops.keys_add_ln(keys, src_of, delta, g, b, new_keys, B, N, C, eps=layer.norm4.eps)
+            keys, src_of = new_keys, None
+            del delta, ai
+        # final token -> image attention (transformer.py:99-104) + norm_final_attn + heads (mask_decoder.py:191-203) -> packed record
+        fa = tr.final_attn_token_to_image
+        kp = self._image_proj("f.k", fa.k_proj, keys, pe, N)
+        vp = self._image_proj("f.v", fa.v_proj, keys, None, N)
+        att = ops.t2i_attention_wide(qf, kp, vp, src_of, B, T, N, H, fa.internal_dim // H)
+        wo, bo = self._w32("f.o", fa.out_proj)
+        g, b = self._ln("f.n", tr.norm_final_attn)
+        w0, b0 = self._w32("h.0", self.bbox_prediction_head[0]); w2, b2 = self._w32("h.2", self.bbox_prediction_head[2])
+        wt, bt = self._w32("h.t", self.temporal_objectness_head) if self.use_temp_objectness else (None, None)
+        return ops.decoder_heads(queries, att, wo, bo, g, b, tr.norm_final_attn.eps, w0, b0, w2, b2, wt, bt, records, tok=1 + self.num_mask_tokens)
+
+    def _decode_unfused(self, tokens, keys0, shared, pe, frame_of, N, C, records):
+        """the same pass on the per-op kernels of decoder_ops.cu (other widths than 256 / 128 / 2048; cross-check of the fused path)"""
         tr = self.transformer
         B, T, _ = tokens.shape
         H = tr.num_heads

@@ -6,7 +6,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import GemmEpilogue, check, lib
+from ._lib import GemmEpilogue, TwoWayAParams, TwoWayBParams, check, lib
 
 BF16, F32 = torch.bfloat16, torch.float32
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "sigmoid": 3}
@@ -233,6 +233,55 @@ def small_linear(x, w, b=None, *, act=None, resid=None):
     if R:
         check(lib().grove_small_linear_f32(_p(x), _p(w), _p(b), _p(resid), _p(y), R, N, K, ACT[act], _stream(x)), "grove_small_linear_f32")
     return y
+
+
+def _struct_of(cls, fields: dict):
+    """ctypes parameter block from {field: fp32 CUDA tensor | number | None}; returns (struct, tensors kept alive)"""
+    st, keep = cls(), []
+    for k, v in fields.items():
+        if isinstance(v, torch.Tensor):
+            _req(v, F32, k)
+            keep.append(v)
+            setattr(st, k, v.data_ptr())
+        elif v is None:
+            setattr(st, k, None)
+        else:
+            setattr(st, k, v)
+    return st, keep
+
+
+def twoway_tokens_a(queries, tokens, params: dict):
+    """part A of a two-way block on the token side (see grove_twoway_block_tokens_a_fwd): -> (queries_out [B,6,256], qt [B,6,128])"""
+    B, T, Cc = queries.shape
+    _req(queries, F32, "queries"); _req(tokens, F32, "tokens")
+    st, keep = _struct_of(TwoWayAParams, params)
+    q_out = torch.empty_like(queries)
+    qt = torch.empty(B, T, params["wq2_t"].shape[1], device=queries.device, dtype=F32)
+    check(lib().grove_twoway_block_tokens_a_fwd(_p(queries), _p(tokens), C.byref(st), _p(q_out), _p(qt), B, T, Cc, _stream(queries)),
+          "grove_twoway_block_tokens_a_fwd")
+    return q_out, qt
+
+
+def twoway_tokens_b(queries, att, tokens, params: dict, want_qf: bool):
+    """part B (see grove_twoway_block_tokens_b_fwd): -> (queries_out [B,6,256], kt, vt [B,6,128], qf [B,6,128] | None)"""
+    B, T, Cc = queries.shape
+    _req(queries, F32, "queries"); _req(att, F32, "att"); _req(tokens, F32, "tokens")
+    st, keep = _struct_of(TwoWayBParams, params)
+    CI = params["wk_t"].shape[1]
+    q_out = torch.empty_like(queries)
+    kt = torch.empty(B, T, CI, device=queries.device, dtype=F32)
+    vt = torch.empty_like(kt)
+    qf = torch.empty_like(kt) if want_qf else None
+    check(lib().grove_twoway_block_tokens_b_fwd(_p(queries), _p(att), _p(tokens), C.byref(st), _p(q_out), _p(kt), _p(vt), _p(qf), B, T, Cc,
+                                                _stream(queries)), "grove_twoway_block_tokens_b_fwd")
+    return q_out, kt, vt, qf
+
+
+def t2i_attention_wide(q, k, v, src_of, B, T, N, heads, dh, lse=None):
+    out = torch.empty(B, T, heads * dh, device=q.device, dtype=F32)
+    check(lib().grove_decoder_t2i_attention_wide(_p(_req(q, F32, "q")), _p(_req(k, BF16, "k")), _p(_req(v, BF16, "v")), _p(src_of), _p(out),
+                                                 _p(lse), B, T, N, heads, dh, _stream(q)), "grove_decoder_t2i_attention_wide")
+    return out
 
 
 def decoder_heads(queries, att, wo, bo, ln_g, ln_b, eps, w0, b0, w2, b2, wt, bt, records, *, tok, hs_out=None):

@@ -140,6 +140,41 @@ int grove_decoder_i2t_attention(const void* qi, const float* kt, const float* vt
 /* keys_out[b,n,:] = bf16(LayerNorm(keys_in[src_of[b],n,:] + delta[b,n,:]))  (norm4, transformer.py:180), C = 256. */
 int grove_decoder_keys_add_ln(const void* keys_in, const int* src_of, const float* delta, const float* g, const float* b, void* keys_out,
                               int B, int N, int C, float eps, grove_stream_t stream);
+/* ---- fused token side of a TwoWayAttentionBlock (transformer.py:151-182), ABI v4.  All weights fp32 and TRANSPOSED ([in][out]);
+ * 6 tokens x 256 channels per instance, cross-attention width 128, MLP width 2048. ---- */
+typedef struct grove_twoway_a_params {
+  const float *wq_t, *bq, *wk_t, *bk, *wv_t, *bv, *wo_t, *bo;   /* self_attn q/k/v/out_proj, [256][256] each */
+  const float *ln_g, *ln_b;                                      /* norm1 */
+  float ln_eps;
+  const float *wq2_t, *bq2;                                      /* cross_attn_token_to_image.q_proj, [256][128] */
+  int skip_pe;                                                   /* skip_first_layer_pe: no query_pe, no residual (layer 0) */
+} grove_twoway_a_params;
+typedef struct grove_twoway_b_params {
+  const float *wo_t, *bo;                                        /* cross_attn_token_to_image.out_proj, [128][256] */
+  const float *ln2_g, *ln2_b;                                    /* norm2 */
+  float ln2_eps;
+  const float *w1_t, *b1, *w2_t, *b2;                            /* mlp.lin1 [256][mlp_dim], mlp.lin2 [mlp_dim][256] */
+  int mlp_dim;
+  const float *ln3_g, *ln3_b;                                    /* norm3 */
+  float ln3_eps;
+  const float *wk_t, *bk, *wv_t, *bv;                            /* cross_attn_image_to_token.k_proj / v_proj, [256][128] */
+  const float *wqf_t, *bqf;                                      /* optional: q_proj of the NEXT token->image attention, [256][128] */
+} grove_twoway_b_params;
+/* Part A (one launch): queries fp32 [B,6,256], tokens (= query_pe) fp32 [B,6,256] ->
+ *   queries_out = norm1(self_attn(q = k = queries + pe, v = queries) (+ queries)),  qt_out [B,6,128] = q_proj(queries_out + pe)
+ * (transformer.py:155-164). */
+int grove_twoway_block_tokens_a_fwd(const float* queries, const float* tokens, const grove_twoway_a_params* p, float* queries_out, float* qt_out,
+                                    int B, int T, int C, grove_stream_t stream);
+/* Part B (one launch, a cluster of 8 CTAs per instance): queries = part A's output, att fp32 [B,6,128] = grove_decoder_t2i_attention output ->
+ *   x = norm2(queries + out_proj(att)); queries_out = norm3(x + lin2(relu(lin1(x))));
+ *   kt_out = k_proj(queries_out + pe), vt_out = v_proj(queries_out) [B,6,128] (image->token attention, transformer.py:164-177);
+ *   qf_out (optional) = wqf(queries_out + pe): the query projection of the following token->image attention (transformer.py:99-101). */
+int grove_twoway_block_tokens_b_fwd(const float* queries, const float* att, const float* tokens, const grove_twoway_b_params* p,
+                                    float* queries_out, float* kt_out, float* vt_out, float* qf_out, int B, int T, int C, grove_stream_t stream);
+/* grove_decoder_t2i_attention with 256 threads per (instance, head) and a shuffle-first merge (same arguments and results up to fp32
+ * summation order). */
+int grove_decoder_t2i_attention_wide(const float* q, const void* k, const void* v, const int* src_of, float* out, float* lse_out, int B, int T,
+                                     int N, int heads, int dh, grove_stream_t stream);
 /* The last step of the box decoder for the prompt token `tok` (= 1 + num_mask_tokens) of every instance, one launch:
  *   hs = LayerNorm_final(queries[b,tok,:] + out_proj(att[b,tok,:]))   (final_attn_token_to_image + norm_final_attn, transformer.py:99-104)
  *   records[b] = (sigmoid(W2 relu(W0 hs + b0) + b2), Wt hs + bt)      (bbox_prediction_head / temporal_objectness_head, mask_decoder.py:80-85,191-203)

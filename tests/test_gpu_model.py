@@ -420,3 +420,27 @@ def test_loss_without_temporal_objectness():
     for k in ("giou_loss", "l1_loss"):
         assert abs(float(loss[k]) - float(ref[k])) < 2e-5 * max(1.0, abs(float(ref[k]))), k
     assert abs(float(loss["loss"]) - float(ref["ce_loss"] + ref["giou_loss"] + ref["l1_loss"])) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["dec_cfg1_full", "dec_ragged"])
+def test_fused_token_kernels_match_per_op_path(name):
+    """The fused token-side kernels of the two-way transformer (csrc/decoder_fused.cu: part A, the 8-CTA-cluster part B, wide token->image
+    attention) against the per-op fp32 kernels of decoder_ops.cu on the reference golden cases: same boxes / logits up to fp32 summation order."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    dim, mlp, G, frames, seed = [int(x) for x in g["meta"]]
+    reps = [int(r) for r in g["reps"]]
+    pe, md, sd = _decoder_modules(dim, mlp, G, seed)
+    emb = synth.synth_tensor(name + ".emb", (frames, dim, G, G), seed).cuda()
+    txt = synth.synth_tensor(name + ".txt", (sum(reps), 1, dim), seed).cuda()
+    sparse, dense = pe(points=None, boxes=None, masks=None, text_embeds=txt)
+    with torch.no_grad():
+        assert md._fused_ok()
+        b1, l1 = md(image_embeddings=emb, image_pe=pe.get_dense_pe(), sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense,
+                    multimask_output=False, reps=reps)
+        md._fused_ok = lambda: False
+        b0, l0 = md(image_embeddings=emb, image_pe=pe.get_dense_pe(), sparse_prompt_embeddings=sparse, dense_prompt_embeddings=dense,
+                    multimask_output=False, reps=reps)
+    torch.cuda.synchronize()
+    eb, el = float((b1 - b0).abs().max()), float((l1 - l0).abs().max())
+    print(f"{name}: fused vs per-op max|dbox|={eb:.2e} max|dlogit|={el:.2e}")
+    assert eb < 2e-5 and el < 2e-4      # the image side in between is bf16: a last-bit change of a token value can move a bf16 rounding
