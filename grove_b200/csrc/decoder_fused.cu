@@ -24,19 +24,56 @@ constexpr int kC = 256;      // transformer_dim
 constexpr int kCI = 128;     // cross-attention internal width (attention_downsample_rate 2)
 constexpr int kHeads = 8;
 constexpr int kClu = 8;      // CTAs per instance in kernel B
+constexpr int kRingA = 3;    // cp.async ring depth of part A (one CTA per SM: 96 KB)
+constexpr int kRingB = 2;    // ... of part B (two CTAs of a cluster may share an SM: 64 KB each)
+constexpr int kRingTile = 32 * 256 * 4;
 
-// acc[r] += sum_k act[r][k] * wT[k*ldw + n] for r < 6, k < K: `act` in shared memory (row stride `lda` floats, broadcast float4 reads)
-template <int K>
-__device__ __forceinline__ void col_dot(const float* __restrict__ wT, int ldw, int n, const float* act, int lda, float (&acc)[kT]) {
-#pragma unroll 2
-  for (int k = 0; k < K; k += 4) {
-    const float w0 = __ldg(wT + (size_t)(k + 0) * ldw + n), w1 = __ldg(wT + (size_t)(k + 1) * ldw + n);
-    const float w2 = __ldg(wT + (size_t)(k + 2) * ldw + n), w3 = __ldg(wT + (size_t)(k + 3) * ldw + n);
-#pragma unroll
-    for (int r = 0; r < kT; ++r) {
-      const float4 a = *reinterpret_cast<const float4*>(act + r * lda + k);
-      acc[r] = fmaf(a.x, w0, fmaf(a.y, w1, fmaf(a.z, w2, fmaf(a.w, w3, acc[r]))));
+// acc[r] += sum_k act[r][k] * wT[k*ldw + col0 + tid] for r < 6, k < K, for the NC columns [col0, col0 + NC) (thread tid < NC owns one).
+// The weights stream through shared memory in [32 k][NC] tiles with cp.async (NS-deep ring, whole CTA cooperates): with one CTA per SM
+// the stream is pure latency, and register-staged loads (which ptxas interleaves with the FMAs whatever the source order) kept ~8 loads
+// per thread in flight -- a tenth of the L2 bandwidth an SM can pull (119 us for part A, measured).  `act` lives in shared memory
+// (row stride `lda` floats, broadcast float4 reads).  Ends with a __syncthreads(): the ring may be reused immediately.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int K, int NC, int NS>
+__device__ __forceinline__ void cta_cols_dot(const float* __restrict__ wT, int ldw, int col0, const float* act, int lda, float* ring,
+                                             float (&acc)[kT], int tid) {
+  constexpr int KT = 32, C16 = NC / 4, CH = KT * C16, NTILES = K / KT;
+  static_assert(K % KT == 0 && NC % 4 == 0 && NC <= 256, "");
+  auto issue = [&](int kt) {
+    if (kt < NTILES) {
+      float* dst = ring + (kt % NS) * (KT * NC);
+      for (int idx = tid; idx < CH; idx += 256) {
+        const int row = idx / C16, c = idx % C16;
+        cp_async16(dst + row * NC + c * 4, wT + (size_t)(kt * KT + row) * ldw + col0 + c * 4);
+      }
     }
+    cp_async_commit();               // always a group, so that the wait depth below is uniform
+  };
+#pragma unroll
+  for (int s = 0; s < NS - 1; ++s) issue(s);
+#pragma unroll 1
+  for (int kt = 0; kt < NTILES; ++kt) {
+    issue(kt + NS - 1);
+    cp_async_wait<NS - 1>();         // tile kt has landed (for this thread's copies; the barrier makes it true for everyone's)
+    __syncthreads();
+    if (tid < NC) {
+      const float* wb = ring + (kt % NS) * (KT * NC) + tid;
+#pragma unroll
+      for (int i = 0; i < KT; i += 4) {
+        const float w0 = wb[(i + 0) * NC], w1 = wb[(i + 1) * NC], w2 = wb[(i + 2) * NC], w3 = wb[(i + 3) * NC];
+#pragma unroll
+        for (int r = 0; r < kT; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(act + r * lda + kt * KT + i);
+          acc[r] = fmaf(a.x, w0, fmaf(a.y, w1, fmaf(a.z, w2, fmaf(a.w, w3, acc[r]))));
+        }
+      }
+    }
+    __syncthreads();                 // the slot is refilled NS-1 iterations later
   }
 }
 
@@ -62,6 +99,7 @@ __global__ void __launch_bounds__(256) twoway_tokens_a_kernel(const float* __res
   __shared__ __align__(16) float Ks[kT][kC];
   __shared__ __align__(16) float Vs[kT][kC];
   __shared__ __align__(16) float att[kT][kC];
+  extern __shared__ __align__(16) float ring[];   // cp.async weight ring: kRingA stages of [32][256] fp32
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* xq = queries + (size_t)b * kT * kC;
   const float* xt = tokens + (size_t)b * kT * kC;
@@ -77,9 +115,9 @@ __global__ void __launch_bounds__(256) twoway_tokens_a_kernel(const float* __res
     const float bq = p.bq[n], bk = p.bk[n], bv = p.bv[n];
 #pragma unroll
     for (int r = 0; r < kT; ++r) { aq[r] = bq; ak[r] = bk; av[r] = bv; }
-    col_dot<kC>(p.wq_t, kC, n, &qin[0][0], kC, aq);
-    col_dot<kC>(p.wk_t, kC, n, &qin[0][0], kC, ak);
-    col_dot<kC>(p.wv_t, kC, n, &xs[0][0], kC, av);
+    cta_cols_dot<kC, kC, kRingA>(p.wq_t, kC, 0, &qin[0][0], kC, ring, aq, tid);
+    cta_cols_dot<kC, kC, kRingA>(p.wk_t, kC, 0, &qin[0][0], kC, ring, ak, tid);
+    cta_cols_dot<kC, kC, kRingA>(p.wv_t, kC, 0, &xs[0][0], kC, ring, av, tid);
 #pragma unroll
     for (int r = 0; r < kT; ++r) { Qs[r][n] = aq[r]; Ks[r][n] = ak[r]; Vs[r][n] = av[r]; }
   }
@@ -114,7 +152,7 @@ __global__ void __launch_bounds__(256) twoway_tokens_a_kernel(const float* __res
     const float bo = p.bo[n];
 #pragma unroll
     for (int r = 0; r < kT; ++r) ao[r] = bo;
-    col_dot<kC>(p.wo_t, kC, n, &att[0][0], kC, ao);
+    cta_cols_dot<kC, kC, kRingA>(p.wo_t, kC, 0, &att[0][0], kC, ring, ao, tid);
 #pragma unroll
     for (int r = 0; r < kT; ++r) Qs[r][n] = ao[r] + (p.skip_pe ? 0.f : xs[r][n]);
   }
@@ -130,15 +168,17 @@ __global__ void __launch_bounds__(256) twoway_tokens_a_kernel(const float* __res
     }
   }
   __syncthreads();
-  if (tid < kCI) {
+  {
     const int n = tid;
     float a[kT];
-    const float bq2 = p.bq2[n];
+    const float bq2 = n < kCI ? p.bq2[n] : 0.f;
 #pragma unroll
     for (int r = 0; r < kT; ++r) a[r] = bq2;
-    col_dot<kC>(p.wq2_t, kCI, n, &qin[0][0], kC, a);
+    cta_cols_dot<kC, kCI, kRingA>(p.wq2_t, kCI, 0, &qin[0][0], kC, ring, a, tid);
+    if (n < kCI) {
 #pragma unroll
-    for (int r = 0; r < kT; ++r) qt_out[((size_t)b * kT + r) * kCI + n] = a[r];
+      for (int r = 0; r < kT; ++r) qt_out[((size_t)b * kT + r) * kCI + n] = a[r];
+    }
   }
 }
 
@@ -156,6 +196,7 @@ twoway_tokens_b_kernel(const float* __restrict__ queries, const float* __restric
   __shared__ float wsl[kT][32];                     // this CTA's 32-column slice of the norm3 output (read by the whole cluster)
   __shared__ float ssum[kT], ssq[kT];               // this CTA's slice statistics (read by the whole cluster)
   __shared__ float part[16][16][kT];
+  extern __shared__ __align__(16) float ring[];     // cp.async weight ring: kRingB stages of [32][256] fp32
   const int rk = (int)cluster.block_rank();
   const int b = blockIdx.x / kClu, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* xq = queries + (size_t)b * kT * kC;
@@ -168,7 +209,7 @@ twoway_tokens_b_kernel(const float* __restrict__ queries, const float* __restric
     const float bo = p.bo[n];
 #pragma unroll
     for (int r = 0; r < kT; ++r) ao[r] = bo;
-    col_dot<kCI>(p.wo_t, kC, n, &a2[0][0], kCI, ao);
+    cta_cols_dot<kCI, kC, kRingB>(p.wo_t, kC, 0, &a2[0][0], kCI, ring, ao, tid);
 #pragma unroll
     for (int r = 0; r < kT; ++r) mp[r][n] = ao[r] + xq[r * kC + n];
   }
@@ -186,7 +227,7 @@ twoway_tokens_b_kernel(const float* __restrict__ queries, const float* __restric
     const float b1 = p.b1[j];
 #pragma unroll
     for (int r = 0; r < kT; ++r) ah[r] = b1;
-    col_dot<kC>(p.w1_t, p.mlp_dim, j, &z[0][0], kC, ah);
+    cta_cols_dot<kC, 256, kRingB>(p.w1_t, p.mlp_dim, rk * 256, &z[0][0], kC, ring, ah, tid);
 #pragma unroll
     for (int r = 0; r < kT; ++r) hs[r][tid] = fmaxf(ah[r], 0.f);
   }
@@ -196,7 +237,7 @@ twoway_tokens_b_kernel(const float* __restrict__ queries, const float* __restric
     float am[kT];
 #pragma unroll
     for (int r = 0; r < kT; ++r) am[r] = 0.f;
-    col_dot<256>(p.w2_t + (size_t)rk * 256 * kC, kC, n, &hs[0][0], 256, am);
+    cta_cols_dot<256, kC, kRingB>(p.w2_t + (size_t)rk * 256 * kC, kC, 0, &hs[0][0], 256, ring, am, tid);
 #pragma unroll
     for (int r = 0; r < kT; ++r) mp[r][n] = am[r];
   }
@@ -369,7 +410,9 @@ extern "C" int grove_twoway_block_tokens_a_fwd(const float* queries, const float
   GROVE_CHECK_ARG(queries && tokens && p && queries_out && qt_out && B > 0);
   GROVE_CHECK_ARG(p->wq_t && p->bq && p->wk_t && p->bk && p->wv_t && p->bv && p->wo_t && p->bo && p->ln_g && p->ln_b && p->wq2_t && p->bq2);
   if (T != kT || C != kC) { grove_set_error("the fused two-way token kernels are built for 6 tokens x 256 channels (got %d x %d)", T, C); return GROVE_ERR_UNSUPPORTED; }
-  twoway_tokens_a_kernel<<<B, 256, 0, stream>>>(queries, tokens, *p, queries_out, qt_out);
+  static GrovePerDeviceOnce attr;
+  if (attr.first_time()) cudaFuncSetAttribute(twoway_tokens_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingA * kRingTile);
+  twoway_tokens_a_kernel<<<B, 256, kRingA * kRingTile, stream>>>(queries, tokens, *p, queries_out, qt_out);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
@@ -386,7 +429,9 @@ extern "C" int grove_twoway_block_tokens_b_fwd(const float* queries, const float
     grove_set_error("the fused two-way token kernels are built for 6 tokens x 256 channels, MLP width 2048 (got %d x %d, %d)", T, C, p->mlp_dim);
     return GROVE_ERR_UNSUPPORTED;
   }
-  twoway_tokens_b_kernel<<<B * kClu, 256, 0, stream>>>(queries, att, tokens, *p, queries_out, kt_out, vt_out, qf_out);
+  static GrovePerDeviceOnce attr;
+  if (attr.first_time()) cudaFuncSetAttribute(twoway_tokens_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingB * kRingTile);
+  twoway_tokens_b_kernel<<<B * kClu, 256, kRingB * kRingTile, stream>>>(queries, att, tokens, *p, queries_out, kt_out, vt_out, qf_out);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;

@@ -233,8 +233,8 @@ def test_serving_loop_graph_replay_and_host_stream():
         images, hid, ids = (t.cuda() for t in batches[i])
         _, (ib, il) = gb.ground(images, hid, gb._create_det_token_mask(ids), orig_sizes=[(1280, 720)], infer=True)
         kept = rec[rec[:, 5] > 0][:, :4]
-        assert 0 < kept.shape[0] < 8 * P
-        assert torch.allclose(kept, torch.cat([b for v in ib for b in v]).float().cpu(), atol=0.51)   # ground() rounds the boxes to bf16 (pixels)
+        assert i > 0 or 0 < kept.shape[0] < 8 * P      # the threshold is batch 0's median objectness
+        assert torch.allclose(kept, torch.cat([b for v in ib for b in v]).float().cpu(), rtol=8e-3, atol=0.1)   # ground() returns bf16 boxes (pixels: 8 mantissa bits)
     # the whole-step graph of GroundingBranch (encoder + text projection + decoder + heads in one replay)
     gb.enable_cuda_graphs(True)
     whole = [direct(b) for b in batches]
