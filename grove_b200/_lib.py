@@ -16,7 +16,7 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_row_mod", C.c_int), ("gate_alpha", C.c_void_p),
                 ("act", C.c_int), ("out_f32", C.c_int), ("out2_bf16", C.c_void_p), ("max_ctas", C.c_int), ("force_ctas", C.c_int),
                 ("out2_pre_act", C.c_int), ("dact_pre", C.c_void_p), ("dact", C.c_int), ("splits", C.c_int),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("resid_bf16", C.c_void_p)]
 
 
 class TwoWayAParams(C.Structure):
@@ -46,6 +46,7 @@ SIGNATURES = {
     "grove_conv_gemm_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(GemmEpilogue), _P],
     "grove_im2col_patch16": [_P, _P, _I, _I, _I, _I, _P],
     "grove_layernorm": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "grove_layernorm_bf16in": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "grove_attn_window_relpos_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_attn_window_relpos_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
@@ -114,7 +115,7 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, C.c_int)
-        if l.grove_abi_version() != 4:
+        if l.grove_abi_version() != 5:
             raise RuntimeError("libgrove_b200.so ABI version mismatch; rebuild")
         _lib = l
     return _lib

@@ -29,21 +29,26 @@ __global__ void im2col_patch16_kernel(const __nv_bfloat16* __restrict__ img, __n
 }
 
 // ---------------------------------------------------------------- LayerNorm, one warp per row
-template <bool OUT_F32>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+template <bool OUT_F32, bool IN_BF16 = false>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, void* __restrict__ y, int rows, int D, float eps) {
   constexpr int MAXV = 10;  // D <= 1280: 10 float4 per lane
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int nv = D / 128;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * D);
   float4 v[MAXV];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
     if (i < nv) {
-      v[i] = xr[i * 32 + lane];
+      if (IN_BF16) {       // bf16 residual stream: 4 values = 8 bytes per lane
+        const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)warp * D)[i * 32 + lane];
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        v[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        v[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + (size_t)warp * D)[i * 32 + lane];
+      }
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   const float mean = warp_sum(s) / (float)D;
@@ -120,6 +125,18 @@ extern "C" int grove_layernorm(const float* x, const float* gamma, const float* 
   const int blocks = (rows + 7) / 8;
   if (y_f32) layernorm_kernel<true><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, rows, D, eps);
   else       layernorm_kernel<false><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, rows, D, eps);
+  grove_count_launch();
+  GROVE_CHECK_LAUNCH();
+  return GROVE_OK;
+}
+
+extern "C" int grove_layernorm_bf16in(const void* x, const float* gamma, const float* beta, void* y, int y_f32, int rows, int D, float eps,
+                                      cudaStream_t stream) {
+  GROVE_CHECK_ARG(x && gamma && beta && y && rows > 0);
+  GROVE_CHECK_ARG(D % 128 == 0 && D <= 1280);
+  const int blocks = (rows + 7) / 8;
+  if (y_f32) layernorm_kernel<true, true><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, rows, D, eps);
+  else       layernorm_kernel<false, true><<<blocks, 256, 0, stream>>>(x, gamma, beta, y, rows, D, eps);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;

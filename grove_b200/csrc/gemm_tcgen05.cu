@@ -37,6 +37,7 @@ struct GemmParams {
   int dact;            // 1 exact-GELU derivative, 2 ReLU mask
   const float* bias;   // [N] or null
   const float* resid;  // fp32 [*,N] or null
+  const __nv_bfloat16* resid16;  // bf16 [M,N] or null: bf16 residual stream (EPI = 4 / general bf16-output epilogue)
   int resid_mod;       // >0: residual row = m % resid_mod (abs-pos embedding broadcast over frames)
   const float* gate_alpha;  // non-null: gate = tanh(*gate_alpha)   (adapter, image_encoder.py:54)
   int act;             // 0 none, 1 exact GELU, 2 ReLU
@@ -397,6 +398,82 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
           __syncwarp();                                    // staging is rewritten by the next pass
         }
       }
+    } else if constexpr (EPI == 4) {
+      // ---- bf16 output = bf16(resid_bf16 + gate * act(acc + bias)): the residual-stream GEMMs with the stream kept in bf16 (half the
+      // epilogue traffic of EPI = 3 and no separate bf16 copy for the next tensor-core operand).  Same structure: fp32 staging through the
+      // padded transpose buffer, residual rows fetched one pass ahead, sum formed in fp32 and rounded once.
+      const float relu_floor = p.act == 2 ? 0.f : -INFINITY;
+      __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+      const int c = (lane & 7) * 4;                        // lane -> (row 4i + lane/8, 4 columns at c)
+      auto res_ptr = [&](int tile_, int ps_, int i_) {
+        const int m_blk_ = (p.m_blk0 + tile_ / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk_ = tile_ % p.num_n_blocks;
+        const int row_ = m_blk_ * BM + quad * 32 + 4 * i_ + (lane >> 3);
+        const int rr_ = min(row_, p.M - 1);
+        return p.resid16 + (size_t)rr_ * p.N + n_blk_ * BN + half * (BN / 2) + ps_ * 32 + c;
+      };
+      uint2 res[8];
+      if (tile0 < num_tiles) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res[i] = *reinterpret_cast<const uint2*>(res_ptr(tile0, 0, i));
+      }
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
+        const int m_blk = (p.m_blk0 + tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
+        const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
+        const int row_base = m_blk * BM + quad * 32;
+        const int colw = n_blk * BN + half * (BN / 2);
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ps = 0; ps < kPasses; ++ps) {
+          const int col0 = colw + ps * 32 + c;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0));
+          {
+            uint32_t r0[32];
+            tmem_ld_32x32b_x32(tmem_base + acc * BN + half * (BN / 2) + ps * 32 + ((uint32_t)(quad * 32) << 16), r0);
+            tmem_ld_wait();
+            if (ps == kPasses - 1) {                       // accumulator drained
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CTAS == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+                else mbar_arrive(tempty_bar(acc));
+              }
+            }
+            const uint32_t wrow = stg + lane * (Cfg::kStageRowF * 4);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(wrow + j * 4), "r"(r0[j]), "r"(r0[j + 1]), "r"(r0[j + 2]), "r"(r0[j + 3]) : "memory");
+          }
+          __syncwarp();
+          // next pass's residual rows (next tile's first pass after the last one) go in flight before this pass is consumed
+          uint2 nres[8];
+          const bool last = ps == kPasses - 1;
+          const int ntile = last ? tile + tile_step : tile;
+          const bool more = ntile < num_tiles;
+          if (more) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) nres[i] = *reinterpret_cast<const uint2*>(res_ptr(ntile, last ? 0 : ps + 1, i));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + (lane >> 3);
+            const int row = row_base + rl;
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stg + (rl * Cfg::kStageRowF + c) * 4));
+            v.x = fmaxf(v.x + bias4.x, relu_floor); v.y = fmaxf(v.y + bias4.y, relu_floor);
+            v.z = fmaxf(v.z + bias4.z, relu_floor); v.w = fmaxf(v.w + bias4.w, relu_floor);
+            const float2 r01 = unpack_bf16(res[i].x), r23 = unpack_bf16(res[i].y);
+            v.x = fmaf(v.x, gate, r01.x); v.y = fmaf(v.y, gate, r01.y); v.z = fmaf(v.z, gate, r23.x); v.w = fmaf(v.w, gate, r23.y);
+            if (row < p.M) *reinterpret_cast<uint2*>(outp + (size_t)row * p.N + col0) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+          }
+          if (more) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = nres[i];
+          }
+          __syncwarp();                                    // staging is rewritten by the next pass
+        }
+      }
     } else
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
       const int sp = tile / tiles_mn, tmn = tile % tiles_mn;
@@ -469,6 +546,18 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
                 res[2 * i + 1] = *reinterpret_cast<const float4*>(rp + 4);
               }
             }
+          } else if (p.resid16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = row_base + 8 * i + (lane >> 2);
+              res[2 * i] = res[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < p.M) {
+                const uint4 u = *reinterpret_cast<const uint4*>(p.resid16 + (size_t)row * p.N + col0 + c);
+                const float2 a = unpack_bf16(u.x), b2 = unpack_bf16(u.y), c2 = unpack_bf16(u.z), d2 = unpack_bf16(u.w);
+                res[2 * i] = make_float4(a.x, a.y, b2.x, b2.y);
+                res[2 * i + 1] = make_float4(c2.x, c2.y, d2.x, d2.y);
+              }
+            }
           }
           uint4 pre[4];
           if (p.dact_pre) {
@@ -527,7 +616,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
                 else             { v[2 * j] = z.x > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = z.y > 0.f ? v[2 * j + 1] : 0.f; }
               }
             }
-            if (p.resid) {
+            if (p.resid || p.resid16) {
               v[0] += res[2 * i].x; v[1] += res[2 * i].y; v[2] += res[2 * i].z; v[3] += res[2 * i].w;
               v[4] += res[2 * i + 1].x; v[5] += res[2 * i + 1].y; v[6] += res[2 * i + 1].z; v[7] += res[2 * i + 1].w;
             }
@@ -672,7 +761,7 @@ static bool generic_epilogue_only() {   // GROVE_GEMM_GENERIC_EPI=1: route every
 // for the rows [row0, row1) whose tiles were computed as split-K partial planes (see dispatch_gemm).
 __global__ void __launch_bounds__(256) gemm_tail_fixup_kernel(const float* __restrict__ part, int splits, int plane_rows, int row0, int row1, int N,
                                                               const float* __restrict__ bias, const float* resid, const float* __restrict__ gate_alpha,
-                                                              int act, float* out, __nv_bfloat16* out2) {
+                                                              int act, float* out, __nv_bfloat16* out2, const __nv_bfloat16* resid16 = nullptr) {
   const float gate = gate_alpha ? tanhf(__ldg(gate_alpha)) : 1.0f;
   const float floor_v = act == 2 ? 0.f : -INFINITY;
   const int n4 = N / 4;
@@ -689,6 +778,11 @@ __global__ void __launch_bounds__(256) gemm_tail_fixup_kernel(const float* __res
     const size_t o = (size_t)(row0 + r) * N + c;
     float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (resid) rv = *reinterpret_cast<const float4*>(resid + o);
+    else if (resid16) {
+      const uint2 u = *reinterpret_cast<const uint2*>(resid16 + o);
+      const float2 r01 = unpack_bf16(u.x), r23 = unpack_bf16(u.y);
+      rv = make_float4(r01.x, r01.y, r23.x, r23.y);
+    }
     float4 v;
     v.x = fmaf(fmaxf(a.x + bv.x, floor_v), gate, rv.x); v.y = fmaf(fmaxf(a.y + bv.y, floor_v), gate, rv.y);
     v.z = fmaf(fmaxf(a.z + bv.z, floor_v), gate, rv.z); v.w = fmaf(fmaxf(a.w + bv.w, floor_v), gate, rv.w);
@@ -729,7 +823,7 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
   // through a single CTA at ~0.9 TB/s): spread K over the idle SMs as split-K partial planes and finish with the fix-up kernel.
   {
     const int tiles = p.num_m_blocks * p.num_n_blocks;
-    const bool simple = p.splits == 1 && p.conv == 0 && !p.resid && !p.gate_alpha && !p.dact_pre && !p.out2 && p.act != 1;
+    const bool simple = p.splits == 1 && p.conv == 0 && !p.resid && !p.resid16 && !p.gate_alpha && !p.dact_pre && !p.out2 && p.act != 1;
     if (simple && workspace && tiles * ctas * 2 <= num_sms() && p.num_k_blocks >= 32 && max_ctas == 0 && !tail_split_disabled()) {
       int s = num_sms() / (tiles * ctas);
       if (s > 16) s = 16;
@@ -756,12 +850,14 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
     }
   }
   // straight-line epilogues for the two hot bf16-output forms (bias, optional GELU, nothing else)
-  const bool plain_bf16 = !p.out_f32 && !p.resid && !p.gate_alpha && !p.out2 && !p.dact_pre && p.splits == 1 && p.conv != 2 && (p.act == 0 || p.act == 1) &&
+  const bool plain_bf16 = !p.out_f32 && !p.resid && !p.resid16 && !p.gate_alpha && !p.out2 && !p.dact_pre && p.splits == 1 && p.conv != 2 && (p.act == 0 || p.act == 1) &&
                           !generic_epilogue_only();
   if (ctas == 2 && plain_bf16) return p.act == 1 ? launch_gemm<256, 2, 2>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 1>(p, ta, tb, max_ctas, st);
-  const bool resid_f32 = p.out_f32 && p.resid && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2_pre &&
+  const bool resid_f32 = p.out_f32 && p.resid && !p.resid16 && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2_pre &&
                          !generic_epilogue_only();
-  if (ctas == 2 && resid_f32) {
+  const bool resid_b16 = !p.out_f32 && p.resid16 && !p.resid && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2 &&
+                         !generic_epilogue_only();
+  if (ctas == 2 && (resid_f32 || resid_b16)) {
     // Wave quantisation: 256x256 tiles on P = 74 CTA pairs.  With N = 768 and M = 32768 (proj, fc2, the Conv3d adapter) there are
     // 384 tiles = 5.19 waves, so the last wave runs 14 tiles on 74 pairs.  When the remainder is small the trailing m-blocks are
     // computed instead as split-K partial planes (t*nb tiles x s splits <= P units of K/s k-blocks each, one short wave) and a
@@ -781,7 +877,7 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
       if (s >= 2 && t < p.num_m_blocks && need <= workspace_bytes) {
         GemmParams pa = p;
         pa.num_m_blocks = p.num_m_blocks - t;
-        int rc = launch_gemm<256, 2, 3>(pa, ta, tb, max_ctas, st);
+        int rc = resid_b16 ? launch_gemm<256, 2, 4>(pa, ta, tb, max_ctas, st) : launch_gemm<256, 2, 3>(pa, ta, tb, max_ctas, st);
         if (rc) return rc;
         GemmParams pb = p;
         pb.m_blk0 = p.num_m_blocks - t; pb.num_m_blocks = t;
@@ -789,20 +885,24 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
         pb.splits = (p.num_k_blocks + pb.kb_per_split - 1) / pb.kb_per_split;
         pb.plane_rows = t * BM * 2;
         pb.out = workspace; pb.out_f32 = 1;
-        pb.bias = nullptr; pb.resid = nullptr; pb.gate_alpha = nullptr; pb.act = 0; pb.out2 = nullptr;
+        pb.bias = nullptr; pb.resid = nullptr; pb.resid16 = nullptr; pb.gate_alpha = nullptr; pb.act = 0; pb.out2 = nullptr;
         rc = launch_gemm<256, 2>(pb, ta, tb, max_ctas, st);
         if (rc) return rc;
         const int row0 = pb.m_blk0 * BM * 2;
         const long long n4 = (long long)(p.M - row0) * (p.N / 4);
         const int grid = (int)((n4 + 255) / 256 < 4 * num_sms() ? (n4 + 255) / 256 : 4 * num_sms());
-        gemm_tail_fixup_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), pb.splits, pb.plane_rows, row0, p.M, p.N, p.bias, p.resid,
-                                                     p.gate_alpha, p.act, reinterpret_cast<float*>(p.out), p.out2);
+        if (resid_b16)
+          gemm_tail_fixup_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), pb.splits, pb.plane_rows, row0, p.M, p.N, p.bias, nullptr,
+                                                       p.gate_alpha, p.act, nullptr, reinterpret_cast<__nv_bfloat16*>(p.out), p.resid16);
+        else
+          gemm_tail_fixup_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), pb.splits, pb.plane_rows, row0, p.M, p.N, p.bias, p.resid,
+                                                       p.gate_alpha, p.act, reinterpret_cast<float*>(p.out), p.out2);
         grove_count_launch();
         GROVE_CHECK_LAUNCH();
         return GROVE_OK;
       }
     }
-    return launch_gemm<256, 2, 3>(p, ta, tb, max_ctas, st);
+    return resid_b16 ? launch_gemm<256, 2, 4>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 3>(p, ta, tb, max_ctas, st);
   }
   if (ctas == 2) return launch_gemm<256, 2>(p, ta, tb, max_ctas, st);
   return BN == 256 ? launch_gemm<256, 1>(p, ta, tb, max_ctas, st) : launch_gemm<128, 1>(p, ta, tb, max_ctas, st);
@@ -815,6 +915,7 @@ using namespace grove;
 static int fill_epilogue(GemmParams& p, const grove_gemm_epilogue* e, int M, int N) {
   p.bias = e ? e->bias : nullptr;
   p.resid = e ? e->resid : nullptr;
+  p.resid16 = e ? reinterpret_cast<const __nv_bfloat16*>(e->resid_bf16) : nullptr;
   p.resid_mod = e ? e->resid_row_mod : 0;
   p.gate_alpha = e ? e->gate_alpha : nullptr;
   p.act = e ? e->act : 0;
@@ -828,7 +929,8 @@ static int fill_epilogue(GemmParams& p, const grove_gemm_epilogue* e, int M, int
   GROVE_CHECK_ARG(!p.dact_pre || ((p.dact == 1 || p.dact == 2) && !p.out_f32 && ((uintptr_t)p.dact_pre & 15) == 0));
   GROVE_CHECK_ARG(p.out2_pre == 0 || (p.out2_pre == 1 && !p.out_f32) || (p.out2_pre == 2 && p.out_f32));
   // split-K writes raw fp32 partial planes [splits, M, N]; reduce them with grove_reduce_partials_f32
-  GROVE_CHECK_ARG(p.splits == 1 || (p.out_f32 && !p.bias && !p.resid && !p.gate_alpha && !p.act && !p.out2));
+  GROVE_CHECK_ARG(p.splits == 1 || (p.out_f32 && !p.bias && !p.resid && !p.resid16 && !p.gate_alpha && !p.act && !p.out2));
+  GROVE_CHECK_ARG(!p.resid16 || (!p.resid && !p.out_f32 && p.resid_mod == 0 && ((uintptr_t)p.resid16 & 15) == 0));
   GROVE_CHECK_ARG(((uintptr_t)p.bias & 15) == 0 && ((uintptr_t)p.resid & 15) == 0 && ((uintptr_t)p.out2 & 15) == 0);
   (void)M; (void)N;
   return GROVE_OK;

@@ -129,6 +129,10 @@ class ImageEncoderViT(nn.Module):
         self._pack = PackCache()
         self._use_graphs = False
         self._graph = None          # (signature, CUDAGraph, static patches, static embeddings, kernels per replay)
+        # dtype of the residual stream between blocks.  fp32 (default) keeps 4-5x headroom under the 1e-2 / 2e-2 output tolerance; bfloat16
+        # halves the residual GEMMs' epilogue traffic and the LayerNorm reads (the reference itself runs the whole model in bf16,
+        # train.py:618) — sums are still formed in fp32 and rounded once per block half.  See DESIGN.md section 4 for the measured drift.
+        self.residual_dtype = torch.float32
 
     # ------------------------------------------------------------------ weight packing (cached)
     def _linear(self, key, lin: nn.Linear):
@@ -151,7 +155,7 @@ class ImageEncoderViT(nn.Module):
     def _encode_patches_cached(self, patches: torch.Tensor, Fr: int, G: int) -> torch.Tensor:
         if not self._use_graphs:
             return self._encode_patches(patches, Fr, G)
-        sig = (Fr, G, patches.device, tuple(patches.shape), tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        sig = (Fr, G, patches.device, tuple(patches.shape), self.residual_dtype, tuple((p.data_ptr(), p._version) for p in self.parameters()))
         if self._graph is None or self._graph[0] != sig:
             self._graph = None
             self._encode_patches(patches, Fr, G)            # warm-up: packs the weights, sets the kernels' shared-memory attributes
@@ -221,7 +225,10 @@ class ImageEncoderViT(nn.Module):
             raise ValueError("the spatio-temporal adapter groups frames by 8 (image_encoder.py:52): V*T must be a multiple of 8")
         dev = patches.device
         M = Fr * N
-        xs = torch.empty(M, D, device=dev, dtype=torch.float32)        # fp32 residual stream
+        lowp = self.residual_dtype == torch.bfloat16
+        if self.residual_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("residual_dtype must be torch.float32 or torch.bfloat16")
+        xs = torch.empty(M, D, device=dev, dtype=self.residual_dtype)   # residual stream
         wpe = self._pack.get("pe.w", [self.patch_embed.proj.weight], lambda w: bf16(w.reshape(w.shape[0], -1)))
         bpe = self._pack.get("pe.b", [self.patch_embed.proj.bias], f32)
         pos = None
@@ -237,7 +244,9 @@ class ImageEncoderViT(nn.Module):
         att = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
         mlp_dim = self.blocks[0].mlp.lin1.out_features
         hid = torch.empty(M, mlp_dim, device=dev, dtype=torch.bfloat16)
-        xb = torch.empty(M, D, device=dev, dtype=torch.bfloat16)       # bf16 copy of the stream for conv / neck operands
+        # fp32 stream: bf16 copies of it feed the conv / neck tensor-core operands; bf16 stream: the stream is its own operand and the
+        # adapter (which reads its neighbours' rows) writes into a second buffer
+        xb = None if lowp else torch.empty(M, D, device=dev, dtype=torch.bfloat16)
         xb2 = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
         last = len(self.blocks) - 1
         for i, blk in enumerate(self.blocks):
@@ -267,8 +276,17 @@ class ImageEncoderViT(nn.Module):
             conv = is_conv_adapter(adapter)
             if adapter is not None and not conv and not isinstance(adapter, nn.Identity):
                 raise NotImplementedError(f"unsupported adapter module {type(adapter).__name__}")
-            ops.gemm(hid, w2, xs, bias=bb2, resid=xs, out2=xb if (conv or i == last) else None)
-            if conv:
+            ops.gemm(hid, w2, xs, bias=bb2, resid=xs, out2=xb if ((conv or i == last) and not lowp) else None)
+            if conv and lowp:
+                c3 = adapter.conv3d
+                if tuple(c3.kernel_size) != (3, 3, 3) or c3.in_channels != D or c3.out_channels != D:
+                    raise NotImplementedError("adapter Conv3d must be DxDx3x3x3 (image_encoder.py:139-143)")
+                wc = self._pack.get(k + ".c3w", [c3.weight], lambda w: bf16(w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1)))
+                bc = self._pack.get(k + ".c3b", [c3.bias], f32)
+                al = self._pack.get(k + ".alpha", [adapter.alpha], f32)
+                ops.conv_gemm(xs, wc, xb2, V=Fr // 8, T=8, G=G, kt=3, bias=bc, act="relu", gate_alpha=al, resid=xs)
+                xs, xb2 = xb2, xs
+            elif conv:
                 c3 = adapter.conv3d
                 if tuple(c3.kernel_size) != (3, 3, 3) or c3.in_channels != D or c3.out_channels != D:
                     raise NotImplementedError("adapter Conv3d must be DxDx3x3x3 (image_encoder.py:139-143)")
@@ -283,7 +301,7 @@ class ImageEncoderViT(nn.Module):
         C = self.out_chans
         wn0 = self._pack.get("n0", [self.neck[0].weight], lambda w: bf16(w.reshape(w.shape[0], -1)))
         y0 = torch.empty(M, C, device=dev, dtype=torch.float32)
-        ops.gemm(xb, wn0, y0)
+        ops.gemm(xs if lowp else xb, wn0, y0)
         g, b = self._ln("n1", self.neck[1])
         y1 = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
         ops.layernorm(y0, g, b, y1, self.neck[1].eps)

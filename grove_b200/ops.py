@@ -47,7 +47,12 @@ def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, 
     e.dact = ACT[dact] if dact_pre is not None else 0
     e.splits = int(splits)
     e.bias = None if bias is None else _req(bias, F32, "bias").data_ptr()
-    e.resid = None if resid is None else _req(resid, F32, "resid").data_ptr()
+    if resid is not None and resid.dtype == BF16:      # bf16 residual stream (bf16 `out`, may alias it)
+        assert out.dtype == BF16 and resid_row_mod == 0 and out2 is None
+        e.resid, e.resid_bf16 = None, _req(resid, BF16, "resid").data_ptr()
+    else:
+        e.resid = None if resid is None else _req(resid, F32, "resid").data_ptr()
+        e.resid_bf16 = None
     e.resid_row_mod = int(resid_row_mod)
     e.gate_alpha = None if gate_alpha is None else _req(gate_alpha, F32, "gate_alpha").data_ptr()
     e.act = ACT[act]
@@ -107,11 +112,13 @@ def im2col_patch16(images, out):
 
 
 def layernorm(x, gamma, beta, out, eps):
-    _req(x, F32, "x"); _req(gamma, F32, "gamma"); _req(beta, F32, "beta")
+    """out = LayerNorm(x) over the last dim; x fp32 or bf16 (bf16 residual stream), statistics in fp32"""
+    assert x.is_cuda and x.is_contiguous() and x.dtype in (BF16, F32)
+    _req(gamma, F32, "gamma"); _req(beta, F32, "beta")
     rows, D = x.shape
     assert out.shape == x.shape and out.is_contiguous() and out.dtype in (BF16, F32)
-    check(lib().grove_layernorm(_p(x), _p(gamma), _p(beta), _p(out), 1 if out.dtype == F32 else 0, rows, D, float(eps), _stream(x)),
-          "grove_layernorm")
+    fn = lib().grove_layernorm if x.dtype == F32 else lib().grove_layernorm_bf16in
+    check(fn(_p(x), _p(gamma), _p(beta), _p(out), 1 if out.dtype == F32 else 0, rows, D, float(eps), _stream(x)), "grove_layernorm")
     return out
 
 

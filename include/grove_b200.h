@@ -25,7 +25,7 @@ typedef cudaStream_t grove_stream_t;
 typedef void* grove_stream_t;
 #endif
 
-#define GROVE_B200_ABI_VERSION 4
+#define GROVE_B200_ABI_VERSION 5
 
 /* ---- library ---------------------------------------------------------------------------------- */
 int grove_abi_version(void);
@@ -59,6 +59,9 @@ typedef struct grove_gemm_epilogue {
                               256x256 tiles would be mostly empty computes its trailing rows as split-K partial planes here and
                               finishes them with a fix-up kernel (needs splits * rows * N * 4 bytes, <= 32 MB for the encoder) */
   long long workspace_bytes;
+  /* ---- ABI v5 ---- */
+  const void* resid_bf16;  /* bf16 [M, N] or NULL (exclusive with `resid`; bf16 `out`, may alias it): the residual stream kept in bf16 —
+                              out = bf16(resid_bf16 + gate * act(acc + bias)), the sum formed in fp32 and rounded once */
 } grove_gemm_epilogue;
 
 /* out[M,N] = resid + gate * act(A[M,K] . W[N,K]^T + bias).  A, W bf16 row-major (nn.Linear layout).
@@ -81,6 +84,9 @@ int grove_conv_gemm_bf16(const void* X, const void* Wp, void* out, int V, int T,
 int grove_im2col_patch16(const void* images, void* patches, int V, int T, int H, int W, grove_stream_t stream);
 /* y = LayerNorm(x) over the last dim D (image_encoder.py:245,257 eps 1e-6; common.py:31-43 as token-major rows).
  * x fp32 [rows,D]; y bf16 or fp32 [rows,D]; gamma/beta fp32.  D % 128 == 0, D <= 1280. */
+/* the same with a bf16 input row (bf16 residual stream); statistics in fp32 */
+int grove_layernorm_bf16in(const void* x, const float* gamma, const float* beta, void* y, int y_f32, int rows, int D, float eps,
+                           grove_stream_t stream);
 int grove_layernorm(const float* x, const float* gamma, const float* beta, void* y, int y_f32, int rows, int D, float eps,
                     grove_stream_t stream);
 /* Windowed attention with decomposed rel-pos bias on the UNPARTITIONED token-major qkv[F,G,G,3,heads,hd]

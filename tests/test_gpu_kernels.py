@@ -312,3 +312,46 @@ def test_decision_utilities_bit_exact(ops):
         viou, over, ious = be.viou_over_threshold(p_, q, thr)
         rv, rover, rious = ob.video_viou(p_, q, thr)
         assert viou == rv and [over[t] for t in thr] == rover and np.array_equal(ious, np.array(rious, dtype=np.float64))
+
+
+@pytest.mark.parametrize("force_ctas", [1, 2])
+def test_gemm_bf16_residual_stream(ops, force_ctas):
+    """The residual-stream GEMMs with the stream kept in bf16 (EPI = 4 on CTA pairs, the general epilogue on single-CTA tiles, the
+    tail-split fix-up): out = bf16(resid_bf16 + gate * act(acc + bias)), sum in fp32, ONE rounding — equal to rounding the fp32-stream
+    result of the same kernel family, up to one bf16 ulp where the fp32 sums differ in the last bit."""
+    M, N, K = 1536, 768, 768
+    a, w = _rand((M, K), 3, dtype=torch.bfloat16), _rand((N, K), 4, 1 / math.sqrt(K), dtype=torch.bfloat16)
+    bias, resid = _rand((N,), 5), _rand((M, N), 6, dtype=torch.bfloat16)
+    ref = resid.float() + a.float() @ w.float().t() + bias
+    x = resid.clone()
+    ops.gemm(a, w, x, bias=bias, resid=x, force_ctas=force_ctas)           # in place
+    d = (x.float() - ref).abs()
+    assert float((d / (ref.abs() + 1e-3)).max()) < 8e-3 and float(d.mean()) < 3e-3       # bf16 rounding of an O(1) value
+    # ReLU + tanh gate (the adapter's epilogue) into a second buffer
+    alpha = torch.tensor([0.5], device="cuda")
+    y = torch.empty_like(resid)
+    ops.gemm(a, w, y, bias=bias, act="relu", gate_alpha=alpha, resid=resid, force_ctas=force_ctas)
+    ref2 = resid.float() + math.tanh(0.5) * F.relu(a.float() @ w.float().t() + bias)
+    assert float(((y.float() - ref2).abs() / (ref2.abs() + 1e-3)).max()) < 8e-3
+    # LayerNorm on a bf16 row equals LayerNorm on its fp32 widening
+    g, b = _rand((N,), 7) + 1.0, _rand((N,), 8)
+    h16, h32 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.layernorm(x, g, b, h16, 1e-6)
+    ops.layernorm(x.float().contiguous(), g, b, h32, 1e-6)
+    assert torch.equal(h16, h32)
+
+
+def test_conv_adapter_bf16_stream_tail_split(ops):
+    """The Conv3d adapter at its real size (8 frames x 64x64 x 768 -> 384 tiles on 74 CTA pairs: the trailing m-blocks go through the split-K
+    planes + fix-up kernel) with a bf16 stream: equals the fp32-stream result rounded to bf16 (<= 1 ulp)."""
+    V, T, G, C = 1, 8, 64, 768
+    x = _rand((V * T * G * G, C), 11, dtype=torch.bfloat16)
+    w = _rand((C, 27 * C), 12, 1 / math.sqrt(27 * C), dtype=torch.bfloat16)
+    bias, alpha = _rand((C,), 13), torch.tensor([0.5], device="cuda")
+    o32 = torch.empty(V * T * G * G, C, device="cuda", dtype=torch.float32)
+    ops.conv_gemm(x, w, o32, V=V, T=T, G=G, kt=3, bias=bias, act="relu", gate_alpha=alpha, resid=x.float().contiguous())
+    o16 = torch.empty_like(x)
+    ops.conv_gemm(x, w, o16, V=V, T=T, G=G, kt=3, bias=bias, act="relu", gate_alpha=alpha, resid=x)
+    d = (o16.float() - o32).abs()
+    assert float((d / (o32.abs() + 1e-3)).max()) < 8e-3 and float(d.mean()) < 3e-3
+    assert float((o16.float() - o32.to(torch.bfloat16).float()).abs().max()) < 0.04      # at most one bf16 ulp of an O(1..4) value

@@ -138,7 +138,7 @@ def test_image_encoder_vs_oracle(vit, img, frames):
     assert float(d.mean()) < 1e-2 and float(d.max()) < 0.15   # LayerNorm-ed outputs are O(1); output itself is bf16 (ulp 8e-3)
 
 
-def _end_to_end(vit, img, V, P, seed):
+def _end_to_end(vit, img, V, P, seed, residual_dtype=torch.float32):
     from grove_b200.modeling.grounding import GroundingBranch
     from oracle.grounding import VIT_CFG
     cfg = VIT_CFG[vit]
@@ -151,6 +151,7 @@ def _end_to_end(vit, img, V, P, seed):
     gb.grounding_encoder.load_state_dict(sd, strict=False)
     gb.text_hidden_fcs.load_state_dict({k[len("text_hidden_fcs."):]: v for k, v in fsd.items()})
     gb = gb.cuda()   # parameters stay fp32 masters; the pipeline picks bf16 operands / fp32 accumulation itself
+    gb.grounding_encoder.image_encoder.residual_dtype = residual_dtype
     images = synth.synth_tensor(f"e2e.{vit}.images", (V, 3, 8, img, img), seed).cuda().to(torch.bfloat16)
     hid = synth.synth_tensor(f"e2e.{vit}.hidden", (V, L, 4096), seed).cuda().to(torch.bfloat16)
     ids = torch.full((V, L - 575), 7, dtype=torch.long)
@@ -166,7 +167,7 @@ def _end_to_end(vit, img, V, P, seed):
         _, rb, rl, reps = og.grounding_forward(images.float(), hid.float(), mask, full, depth=cfg["depth"], heads=cfg["heads"],
                                                global_idx=cfg["global_idx"])
     eb, el = float((b - rb).abs().max()), float((l - rl).abs().max())
-    print(f"{vit}@{img} V={V}: max|dbox|={eb:.2e} max|dlogit|={el:.2e} min|ref logit|={float(rl.abs().min()):.3f}")
+    print(f"{vit}@{img} V={V} stream={residual_dtype}: max|dbox|={eb:.2e} max|dlogit|={el:.2e} min|ref logit|={float(rl.abs().min()):.3f}")
     assert reps == [P] * (8 * V)
     assert eb < BOX_TOL and el < LOGIT_TOL
     safe = rl.abs() > 3 * max(el, 1e-4)   # a decision can legitimately flip only where the logit is closer to the threshold than the drift (3x margin)
@@ -176,6 +177,12 @@ def _end_to_end(vit, img, V, P, seed):
 def test_end_to_end_config2():
     """BASELINE config 2: ViT-B encoder + box decoder, 1 video x 8 frames at 1024^2, 4 phrases, bf16 operands, vs the fp32 oracle."""
     _end_to_end("vit_b", 1024, 1, 4, 21)
+
+
+@pytest.mark.parametrize("vit,V", [("vit_b", 1), ("vit_h", 2)])
+def test_end_to_end_bf16_residual_stream(vit, V):
+    """configs 2 and 3 with the residual stream kept in bf16 (ImageEncoderViT.residual_dtype): same tolerance as the fp32 stream"""
+    _end_to_end(vit, 1024, V, 4, 21 if vit == "vit_b" else 22, residual_dtype=torch.bfloat16)
 
 
 def test_end_to_end_config3_one_gpu_share():

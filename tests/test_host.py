@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(l, name), f"{name} is declared in include/grove_b200.h but not exported by libgrove_b200.so"
     assert declared == set(SIGNATURES), (declared ^ set(SIGNATURES))
-    assert l.grove_abi_version() == 4
+    assert l.grove_abi_version() == 5
 
 
 @pytest.mark.parametrize("vit", ["vit_b", "vit_l", "vit_h"])
