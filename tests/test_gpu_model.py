@@ -160,8 +160,11 @@ def _end_to_end(vit, img, V, P, seed, residual_dtype=torch.float32):
             ids[v, p - 575 + 1] = gb.det_token_idx
     mask = gb._create_det_token_mask(ids.cuda())
     emb, (boxes, logits) = gb.ground(images, hid, mask, infer=False)
-    b = torch.cat([x for v in boxes for x in v]).float()
-    l = torch.cat([x for v in logits for x in v]).float()
+    _, rec, _ = gb.ground_records(images, hid, mask)
+    # the drift is measured on the fp32 records; ground() returns them rounded to the hidden-state dtype (bf16: half an ulp = 2e-3 at 0.5..1)
+    assert torch.equal(torch.cat([x for v in boxes for x in v]), rec[:, :4].to(hid.dtype))
+    assert torch.equal(torch.cat([x for v in logits for x in v]), rec[:, 4].to(hid.dtype))
+    b, l = rec[:, :4].clone(), rec[:, 4].clone()
     full = {**{k: v.cuda() for k, v in sd.items()}, **{k: v.cuda() for k, v in fsd.items()}}
     with torch.no_grad():
         _, rb, rl, reps = og.grounding_forward(images.float(), hid.float(), mask, full, depth=cfg["depth"], heads=cfg["heads"],
