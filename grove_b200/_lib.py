@@ -16,7 +16,8 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("resid", C.c_void_p), ("resid_row_mod", C.c_int), ("gate_alpha", C.c_void_p),
                 ("act", C.c_int), ("out_f32", C.c_int), ("out2_bf16", C.c_void_p), ("max_ctas", C.c_int), ("force_ctas", C.c_int),
                 ("out2_pre_act", C.c_int), ("dact_pre", C.c_void_p), ("dact", C.c_int), ("splits", C.c_int),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("resid_bf16", C.c_void_p)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("resid_bf16", C.c_void_p),
+                ("ln_stats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_parts", C.c_int), ("ln_eps", C.c_float)]
 
 
 class TwoWayAParams(C.Structure):

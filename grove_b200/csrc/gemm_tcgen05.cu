@@ -38,6 +38,14 @@ struct GemmParams {
   const float* bias;   // [N] or null
   const float* resid;  // fp32 [*,N] or null
   const __nv_bfloat16* resid16;  // bf16 [M,N] or null: bf16 residual stream (EPI = 4 / general bf16-output epilogue)
+  // LayerNorm folded into the GEMM that consumes the normalised rows (EPI = 5 / 6): A is the raw bf16 stream, W carries gamma, and
+  //   out[m, n] = rstd_m * (acc[m, n] - mu_m * ln_csum[n]) + bias[n]        (bias = b + W.beta, ln_csum[n] = sum_k (gamma*W)[n, k])
+  // with mu_m / rstd_m from the per-row partial sums (sum x, sum x^2) that the PRODUCING epilogue (EPI = 4, ln_stats_out) wrote.
+  const float* ln_stats;   // [M, ln_parts, 2] fp32 partial (sum, sum of squares) of row m of A, or null
+  const float* ln_csum;    // [N]
+  int ln_parts;
+  float ln_eps, ln_inv_k;  // 1 / (width of the normalised row)
+  float* ln_stats_out;     // EPI = 4: [M, 2 * num_n_blocks, 2] partial sums of the bf16 values written to `out`, or null
   int resid_mod;       // >0: residual row = m % resid_mod (abs-pos embedding broadcast over frames)
   const float* gate_alpha;  // non-null: gate = tanh(*gate_alpha)   (adapter, image_encoder.py:54)
   int act;             // 0 none, 1 exact GELU, 2 ReLU
@@ -256,11 +264,14 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     const uint32_t stg = epi_base + (warp - 2) * (32 * Cfg::kStageRowF * 4);
     constexpr int kPasses = BN / 2 / 32;
     uint32_t tile_it = 0;
-    if constexpr (EPI == 1 || EPI == 2) {
+    if constexpr (EPI == 1 || EPI == 2 || EPI == 5 || EPI == 6) {
+      constexpr bool kFold = EPI >= 5;                     // LayerNorm of the A rows folded in (see GemmParams::ln_stats)
+      constexpr bool kGelu = EPI == 2 || EPI == 6;
       // ---- bf16 output, bias, optional GELU.  Per warp and pass: one tcgen05.ld of 32 rows x 32 columns (lane = row), bias +
       // activation in registers, pack to bf16, stage 32 rows x 64 B through an XOR-swizzled (conflict-free both ways) private
       // buffer, then 8 rows x 64 B per store instruction.  The accumulator is released right after the last tcgen05.ld.
       const uint32_t bias_s = stg + 2048;                  // this warp's 128 bias values (fp32), 512 B behind the 2 KB staging
+      const uint32_t csum_s = stg + 2560;                  // kFold: this warp's 128 column sums of gamma*W
       __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(p.out);
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
         const int m_blk = (p.m_blk0 + tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
@@ -269,8 +280,21 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
         const int colw = n_blk * BN + half * (BN / 2);     // first output column of this warp
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + colw) + lane);
+        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kFold) cv = __ldg(reinterpret_cast<const float4*>(p.ln_csum + colw) + lane);
         __syncwarp();                                      // the previous tile's bias reads are done
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(bias_s + lane * 16), "f"(bv.x), "f"(bv.y), "f"(bv.z), "f"(bv.w) : "memory");
+        if (kFold) asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(csum_s + lane * 16), "f"(cv.x), "f"(cv.y), "f"(cv.z), "f"(cv.w) : "memory");
+        float rstd = 1.f, nmr = 0.f;                       // row statistics of this thread's row (TMEM lane = row): rstd and -mu * rstd
+        if (kFold) {
+          const int row = min(row_base + lane, p.M - 1);
+          const float2* sp2 = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)row * p.ln_parts;
+          float sx = 0.f, sq = 0.f;
+          for (int i = 0; i < p.ln_parts; ++i) { const float2 t2 = sp2[i]; sx += t2.x; sq += t2.y; }
+          const float mu = sx * p.ln_inv_k;
+          rstd = rsqrtf(fmaxf(sq * p.ln_inv_k - mu * mu, 0.f) + p.ln_eps);
+          nmr = -mu * rstd;
+        }
         __syncwarp();
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
@@ -292,9 +316,17 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
           for (int j = 0; j < 32; j += 4) {
             float4 b4;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_s + (ps * 32 + j) * 4));
-            float v0 = __uint_as_float(r0[j]) + b4.x, v1 = __uint_as_float(r0[j + 1]) + b4.y;
-            float v2 = __uint_as_float(r0[j + 2]) + b4.z, v3 = __uint_as_float(r0[j + 3]) + b4.w;
-            if (EPI == 2) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3); }
+            float v0, v1, v2, v3;
+            if (kFold) {
+              float4 c4;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(csum_s + (ps * 32 + j) * 4));
+              v0 = fmaf(__uint_as_float(r0[j]), rstd, fmaf(nmr, c4.x, b4.x)); v1 = fmaf(__uint_as_float(r0[j + 1]), rstd, fmaf(nmr, c4.y, b4.y));
+              v2 = fmaf(__uint_as_float(r0[j + 2]), rstd, fmaf(nmr, c4.z, b4.z)); v3 = fmaf(__uint_as_float(r0[j + 3]), rstd, fmaf(nmr, c4.w, b4.w));
+            } else {
+              v0 = __uint_as_float(r0[j]) + b4.x; v1 = __uint_as_float(r0[j + 1]) + b4.y;
+              v2 = __uint_as_float(r0[j + 2]) + b4.z; v3 = __uint_as_float(r0[j + 3]) + b4.w;
+            }
+            if (kGelu) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3); }
             pk[j >> 1] = pack_bf16(v0, v1);
             pk[(j >> 1) + 1] = pack_bf16(v2, v3);
           }
@@ -423,6 +455,9 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
         const int colw = n_blk * BN + half * (BN / 2);
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
+        float rs[8], rq[8];                                // ln_stats_out: sum / sum of squares of this thread's 8 rows (4 columns per pass)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
 #pragma unroll 1
         for (int ps = 0; ps < kPasses; ++ps) {
           const int col0 = colw + ps * 32 + c;
@@ -465,13 +500,29 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
             v.z = fmaxf(v.z + bias4.z, relu_floor); v.w = fmaxf(v.w + bias4.w, relu_floor);
             const float2 r01 = unpack_bf16(res[i].x), r23 = unpack_bf16(res[i].y);
             v.x = fmaf(v.x, gate, r01.x); v.y = fmaf(v.y, gate, r01.y); v.z = fmaf(v.z, gate, r23.x); v.w = fmaf(v.w, gate, r23.y);
-            if (row < p.M) *reinterpret_cast<uint2*>(outp + (size_t)row * p.N + col0) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            const uint2 pk2 = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            if (row < p.M) *reinterpret_cast<uint2*>(outp + (size_t)row * p.N + col0) = pk2;
+            if (p.ln_stats_out) {                          // statistics of the ROUNDED values: what the consuming GEMM reads
+              const float2 q01 = unpack_bf16(pk2.x), q23 = unpack_bf16(pk2.y);
+              rs[i] += (q01.x + q01.y) + (q23.x + q23.y);
+              rq[i] += (q01.x * q01.x + q01.y * q01.y) + (q23.x * q23.x + q23.y * q23.y);
+            }
           }
           if (more) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) res[i] = nres[i];
           }
           __syncwarp();                                    // staging is rewritten by the next pass
+        }
+        if (p.ln_stats_out) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o); rq[i] += __shfl_xor_sync(0xffffffffu, rq[i], o); }
+            const int row = row_base + 4 * i + (lane >> 3);
+            if ((lane & 7) == 0 && row < p.M)
+              reinterpret_cast<float2*>(p.ln_stats_out)[(size_t)row * (2 * p.num_n_blocks) + n_blk * 2 + half] = make_float2(rs[i], rq[i]);
+          }
         }
       }
     } else
@@ -852,11 +903,21 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
   // straight-line epilogues for the two hot bf16-output forms (bias, optional GELU, nothing else)
   const bool plain_bf16 = !p.out_f32 && !p.resid && !p.resid16 && !p.gate_alpha && !p.out2 && !p.dact_pre && p.splits == 1 && p.conv != 2 && (p.act == 0 || p.act == 1) &&
                           !generic_epilogue_only();
+  if (p.ln_stats && !(ctas == 2 && plain_bf16)) {
+    grove_set_error("the LayerNorm-folded epilogue needs a plain bf16-output GEMM on CTA-pair tiles (N %% 256 == 0, M >= 256)");
+    return GROVE_ERR_UNSUPPORTED;
+  }
+  if (ctas == 2 && plain_bf16 && p.ln_stats)
+    return p.act == 1 ? launch_gemm<256, 2, 6>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 5>(p, ta, tb, max_ctas, st);
   if (ctas == 2 && plain_bf16) return p.act == 1 ? launch_gemm<256, 2, 2>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 1>(p, ta, tb, max_ctas, st);
   const bool resid_f32 = p.out_f32 && p.resid && !p.resid16 && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2_pre &&
                          !generic_epilogue_only();
   const bool resid_b16 = !p.out_f32 && p.resid16 && !p.resid && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2 &&
                          !generic_epilogue_only();
+  if (p.ln_stats_out && !(ctas == 2 && resid_b16)) {
+    grove_set_error("row statistics are produced by the bf16 residual-stream epilogue on CTA-pair tiles only");
+    return GROVE_ERR_UNSUPPORTED;
+  }
   if (ctas == 2 && (resid_f32 || resid_b16)) {
     // Wave quantisation: 256x256 tiles on P = 74 CTA pairs.  With N = 768 and M = 32768 (proj, fc2, the Conv3d adapter) there are
     // 384 tiles = 5.19 waves, so the last wave runs 14 tiles on 74 pairs.  When the remainder is small the trailing m-blocks are
@@ -867,7 +928,7 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
     const int full_waves = pairs > 0 ? tiles / pairs : 0, rem = pairs > 0 ? tiles % pairs : 0;
     // (measured: pays off for the K = 20736 adapter conv, 858 -> 778 us; LOSES on fc2 with K = 3072, 124 -> 134 us, where the two extra
     // launches and the partial-plane traffic outweigh 0.75 of a 20 us wave -- hence the k-block threshold)
-    if (workspace && full_waves >= 1 && rem > 0 && 2 * rem <= pairs && p.M % (BM * 2) == 0 && p.num_k_blocks >= 96 && p.resid_mod == 0 && !tail_split_disabled()) {
+    if (workspace && full_waves >= 1 && rem > 0 && 2 * rem <= pairs && p.M % (BM * 2) == 0 && p.num_k_blocks >= 96 && p.resid_mod == 0 && !p.ln_stats_out && !tail_split_disabled()) {
       const int t = (rem + p.num_n_blocks - 1) / p.num_n_blocks;            // trailing m-blocks taken out of the main launch
       const int tail_tiles = t * p.num_n_blocks;
       int s = tail_tiles > 0 ? pairs / tail_tiles : 0;
@@ -916,6 +977,12 @@ static int fill_epilogue(GemmParams& p, const grove_gemm_epilogue* e, int M, int
   p.bias = e ? e->bias : nullptr;
   p.resid = e ? e->resid : nullptr;
   p.resid16 = e ? reinterpret_cast<const __nv_bfloat16*>(e->resid_bf16) : nullptr;
+  p.ln_stats = e ? e->ln_stats : nullptr;
+  p.ln_csum = e ? e->ln_colsum : nullptr;
+  p.ln_parts = e ? e->ln_parts : 0;
+  p.ln_eps = e ? e->ln_eps : 0.f;
+  p.ln_inv_k = 0.f;
+  p.ln_stats_out = e ? e->ln_stats_out : nullptr;
   p.resid_mod = e ? e->resid_row_mod : 0;
   p.gate_alpha = e ? e->gate_alpha : nullptr;
   p.act = e ? e->act : 0;
@@ -931,6 +998,8 @@ static int fill_epilogue(GemmParams& p, const grove_gemm_epilogue* e, int M, int
   // split-K writes raw fp32 partial planes [splits, M, N]; reduce them with grove_reduce_partials_f32
   GROVE_CHECK_ARG(p.splits == 1 || (p.out_f32 && !p.bias && !p.resid && !p.resid16 && !p.gate_alpha && !p.act && !p.out2));
   GROVE_CHECK_ARG(!p.resid16 || (!p.resid && !p.out_f32 && p.resid_mod == 0 && ((uintptr_t)p.resid16 & 15) == 0));
+  GROVE_CHECK_ARG(!p.ln_stats || (p.ln_csum && p.ln_parts > 0 && p.ln_parts <= 16 && ((uintptr_t)p.ln_stats & 7) == 0 && ((uintptr_t)p.ln_csum & 15) == 0));
+  GROVE_CHECK_ARG(!p.ln_stats_out || ((uintptr_t)p.ln_stats_out & 7) == 0);
   GROVE_CHECK_ARG(((uintptr_t)p.bias & 15) == 0 && ((uintptr_t)p.resid & 15) == 0 && ((uintptr_t)p.out2 & 15) == 0);
   (void)M; (void)N;
   return GROVE_OK;
@@ -948,6 +1017,7 @@ extern "C" int grove_gemm_bf16(const void* A, const void* W, void* out, int M, i
   p.out = out;
   int rc = fill_epilogue(p, epi, M, N);
   if (rc) return rc;
+  p.ln_inv_k = 1.0f / (float)K;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
   uint32_t ba[2] = {BK, BM};
   return dispatch_gemm(p, A, W, K, N, M, false, da, ba, 2, epi ? epi->max_ctas : 0, epi ? epi->force_ctas : 0, stream, nullptr,

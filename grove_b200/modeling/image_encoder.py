@@ -143,6 +143,17 @@ class ImageEncoderViT(nn.Module):
     def _ln(self, key, ln):
         return self._pack.get(key + ".g", [ln.weight], f32), self._pack.get(key + ".b", [ln.bias], f32)
 
+    def _ln_folded(self, key, ln: nn.LayerNorm, lin: nn.Linear):
+        """(W * gamma as bf16 [N, K], b + W.beta fp32 [N], column sums of the ROUNDED W * gamma fp32 [N]) for a LayerNorm -> Linear pair
+        whose normalisation runs inside the GEMM epilogue (grove_gemm_epilogue.ln_stats)."""
+        def build(w, b, g, be):
+            wg = (w.float() * g.float()[None, :]).to(torch.bfloat16).contiguous()
+            bias = (b.float() if b is not None else torch.zeros(w.shape[0], device=w.device)) + w.float() @ be.float()
+            return wg, bias.contiguous(), wg.float().sum(1).contiguous()
+        if lin.bias is None:
+            return self._pack.get(key + ".fold", [lin.weight, ln.weight, ln.bias], lambda w, g, be: build(w, None, g, be))
+        return self._pack.get(key + ".fold", [lin.weight, lin.bias, ln.weight, ln.bias], build)
+
     # ------------------------------------------------------------------ CUDA-graph replay of the block stack (serving)
     def enable_cuda_graphs(self, on: bool = True) -> None:
         """Serving mode: capture the ~100 launches from the patch-embed GEMM to the neck into one CUDA graph per input shape and
@@ -249,12 +260,20 @@ class ImageEncoderViT(nn.Module):
         xb = None if lowp else torch.empty(M, D, device=dev, dtype=torch.bfloat16)
         xb2 = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
         last = len(self.blocks) - 1
+        # bf16 stream: the residual GEMMs' epilogues emit per-row (sum, sum of squares) of what they write, and the LayerNorm that follows is
+        # folded into the GEMM that consumes it (A = the raw stream, W carries gamma) -- no LayerNorm pass, no normalised copy in HBM
+        stats = torch.empty(M, D // 128, 2, device=dev, dtype=torch.float32) if lowp else None
+        have_stats = False
         for i, blk in enumerate(self.blocks):
             k = f"b{i}"
-            g1, b1 = self._ln(k + ".n1", blk.norm1)
-            ops.layernorm(xs, g1, b1, h, blk.norm1.eps)
-            wq, bq = self._linear(k + ".qkv", blk.attn.qkv)
-            ops.gemm(h, wq, qkv, bias=bq)
+            if have_stats:
+                wq, bq, cq = self._ln_folded(k + ".qkv", blk.norm1, blk.attn.qkv)
+                ops.gemm(xs, wq, qkv, bias=bq, ln_fold=(stats, cq, blk.norm1.eps))
+            else:
+                g1, b1 = self._ln(k + ".n1", blk.norm1)
+                ops.layernorm(xs, g1, b1, h, blk.norm1.eps)
+                wq, bq = self._linear(k + ".qkv", blk.attn.qkv)
+                ops.gemm(h, wq, qkv, bias=bq)
             S = blk.window_size if blk.window_size > 0 else G
             if blk.window_size > 0:
                 bqb = self._pack.get(k + ".qkvb16", [blk.attn.qkv.bias], bf16)
@@ -266,17 +285,24 @@ class ImageEncoderViT(nn.Module):
                 rw = self._pack.get(k + ".rw", [blk.attn.rel_pos_w], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
                 ops.attn_global(qkv, rh, rw, att, F=Fr, G=G, heads=heads, hd=hd)
             wp, bp = self._linear(k + ".proj", blk.attn.proj)
-            ops.gemm(att, wp, xs, bias=bp, resid=xs)
-            g2, b2 = self._ln(k + ".n2", blk.norm2)
-            ops.layernorm(xs, g2, b2, h, blk.norm2.eps)
-            w1, bb1 = self._linear(k + ".l1", blk.mlp.lin1)
-            ops.gemm(h, w1, hid, bias=bb1, act="gelu")
+            if lowp:
+                ops.gemm(att, wp, xs, bias=bp, resid=xs, ln_stats_out=stats)
+                w1, bb1, c1 = self._ln_folded(k + ".l1", blk.norm2, blk.mlp.lin1)
+                ops.gemm(xs, w1, hid, bias=bb1, act="gelu", ln_fold=(stats, c1, blk.norm2.eps))
+            else:
+                ops.gemm(att, wp, xs, bias=bp, resid=xs)
+                g2, b2 = self._ln(k + ".n2", blk.norm2)
+                ops.layernorm(xs, g2, b2, h, blk.norm2.eps)
+                w1, bb1 = self._linear(k + ".l1", blk.mlp.lin1)
+                ops.gemm(h, w1, hid, bias=bb1, act="gelu")
             w2, bb2 = self._linear(k + ".l2", blk.mlp.lin2)
             adapter = self.adapters[self.global_attn_indexes.index(i)] if i in self.global_attn_indexes else None
             conv = is_conv_adapter(adapter)
             if adapter is not None and not conv and not isinstance(adapter, nn.Identity):
                 raise NotImplementedError(f"unsupported adapter module {type(adapter).__name__}")
-            ops.gemm(hid, w2, xs, bias=bb2, resid=xs, out2=xb if ((conv or i == last) and not lowp) else None)
+            have_stats = lowp and not conv and i != last       # the adapter rewrites the stream: the next norm1 runs as its own pass
+            ops.gemm(hid, w2, xs, bias=bb2, resid=xs, out2=xb if ((conv or i == last) and not lowp) else None,
+                     ln_stats_out=stats if have_stats else None)
             if conv and lowp:
                 c3 = adapter.conv3d
                 if tuple(c3.kernel_size) != (3, 3, 3) or c3.in_channels != D or c3.out_channels != D:

@@ -40,8 +40,16 @@ def _req(t: torch.Tensor, dtype, name: str):
     return t
 
 
-def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas=0, out2_pre_act=0, dact_pre=None, dact=None, splits=1):
+def _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas=0, out2_pre_act=0, dact_pre=None, dact=None, splits=1,
+              ln_stats_out=None, ln_fold=None):
     e = GemmEpilogue()
+    e.ln_stats_out = None if ln_stats_out is None else _req(ln_stats_out, F32, "ln_stats_out").data_ptr()
+    if ln_fold is not None:        # (row statistics [M, parts, 2], column sums of gamma*W [N], eps)
+        st, cs, eps = ln_fold
+        e.ln_stats, e.ln_colsum = _req(st, F32, "ln_stats").data_ptr(), _req(cs, F32, "ln_colsum").data_ptr()
+        e.ln_parts, e.ln_eps = int(st.shape[1]), float(eps)
+    else:
+        e.ln_stats, e.ln_colsum, e.ln_parts, e.ln_eps = None, None, 0, 0.0
     e.out2_pre_act = int(out2_pre_act)
     e.dact_pre = None if dact_pre is None else _req(dact_pre, BF16, "dact_pre").data_ptr()
     e.dact = ACT[dact] if dact_pre is not None else 0
@@ -77,15 +85,22 @@ def _gemm_workspace(device):
 
 
 def gemm(a, w, out, *, bias=None, resid=None, resid_row_mod=0, gate_alpha=None, act=None, out2=None, max_ctas=0, force_ctas=0,
-         out2_pre_act=0, dact_pre=None, dact=None, splits=1):
+         out2_pre_act=0, dact_pre=None, dact=None, splits=1, ln_stats_out=None, ln_fold=None):
     """out[M,N] = resid + tanh(gate_alpha) * act(a[M,K] @ w[N,K]^T + bias) * dact'(dact_pre)   (tcgen05 GEMM).
-    splits > 1: out is fp32 [splits, M, N] raw partial sums (finish with reduce_partials)."""
+    splits > 1: out is fp32 [splits, M, N] raw partial sums (finish with reduce_partials).
+    ln_stats_out (with a bf16 resid): fp32 [M, N/128, 2] receives per-row partial (sum, sum of squares) of the output.
+    ln_fold = (stats, colsum, eps): nn.LayerNorm of the rows of `a` folded into this GEMM (see grove_gemm_epilogue.ln_stats)."""
     _req(a, BF16, "a"); _req(w, BF16, "w")
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and out.is_contiguous() and out.dtype in (BF16, F32)
     assert out.shape == ((M, N) if splits == 1 else (splits, M, N))
-    e = _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas, out2_pre_act, dact_pre, dact, splits)
+    if ln_stats_out is not None:
+        assert ln_stats_out.shape == (M, N // 128, 2)
+    if ln_fold is not None:
+        assert ln_fold[0].shape[0] == M and ln_fold[0].shape[2] == 2 and ln_fold[1].shape == (N,)
+    e = _epilogue(bias, resid, resid_row_mod, gate_alpha, act, out, out2, max_ctas, force_ctas, out2_pre_act, dact_pre, dact, splits,
+                  ln_stats_out, ln_fold)
     check(lib().grove_gemm_bf16(_p(a), _p(w), _p(out), M, N, K, C.byref(e), _stream(a)), "grove_gemm_bf16")
     return out
 

@@ -62,6 +62,15 @@ typedef struct grove_gemm_epilogue {
   /* ---- ABI v5 ---- */
   const void* resid_bf16;  /* bf16 [M, N] or NULL (exclusive with `resid`; bf16 `out`, may alias it): the residual stream kept in bf16 —
                               out = bf16(resid_bf16 + gate * act(acc + bias)), the sum formed in fp32 and rounded once */
+  float* ln_stats_out;     /* with resid_bf16 (plain GEMM, N % 256 == 0): fp32 [M, N/128, 2] partial (sum, sum of squares) of every output
+                              row, one slot per 128-column slab — the LayerNorm statistics of the NEXT op, produced for free */
+  const float* ln_stats;   /* LayerNorm folded into this GEMM (nn.LayerNorm of the A rows, image_encoder.py:245,257): fp32
+                              [M, ln_parts, 2] partial sums of row m of A (= a producer's ln_stats_out); A is the RAW bf16 stream, W must
+                              carry gamma (W * gamma), bias must be b + W.beta, and ln_colsum[n] = sum_k (bf16(W*gamma))[n,k].
+                              out = rstd_m * (acc - mu_m * ln_colsum[n]) + bias[n], then the activation.  bf16 out, no residual. */
+  const float* ln_colsum;
+  int ln_parts;
+  float ln_eps;
 } grove_gemm_epilogue;
 
 /* out[M,N] = resid + gate * act(A[M,K] . W[N,K]^T + bias).  A, W bf16 row-major (nn.Linear layout).

@@ -355,3 +355,38 @@ def test_conv_adapter_bf16_stream_tail_split(ops):
     d = (o16.float() - o32).abs()
     assert float((d / (o32.abs() + 1e-3)).max()) < 8e-3 and float(d.mean()) < 3e-3
     assert float((o16.float() - o32.to(torch.bfloat16).float()).abs().max()) < 0.04      # at most one bf16 ulp of an O(1..4) value
+
+
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_gemm_layernorm_fold(ops, act):
+    """LayerNorm folded into the consuming GEMM: the residual GEMM's epilogue emits per-row (sum, sum of squares) partials of the bf16
+    stream it writes (ln_stats_out), the next GEMM takes the RAW stream as A, W * gamma as weights and applies
+    rstd * (acc - mu * colsum) + (b + W.beta) in its epilogue — against LayerNorm -> Linear (-> GELU) in fp32 on the same bf16 stream."""
+    M, D, N = 2048, 768, 2304 if act is None else 3072
+    a, w = _rand((M, D), 3, dtype=torch.bfloat16), _rand((D, D), 4, 1 / math.sqrt(D), dtype=torch.bfloat16)
+    bias = _rand((D,), 5)
+    resid = (_rand((M, D), 6) * 2.0 + _rand((1, D), 9) * 3.0).to(torch.bfloat16)      # per-channel offsets: a non-trivial row mean
+    stats = torch.empty(M, D // 128, 2, device="cuda", dtype=torch.float32)
+    xs = resid.clone()
+    ops.gemm(a, w, xs, bias=bias, resid=xs, ln_stats_out=stats)
+    x32 = xs.float()
+    np.testing.assert_allclose(stats[..., 0].sum(1).cpu().numpy(), x32.sum(1).cpu().numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(stats[..., 1].sum(1).cpu().numpy(), (x32 * x32).sum(1).cpu().numpy(), rtol=1e-4)
+    g, be = _rand((D,), 7) * 0.3 + 1.0, _rand((D,), 8) * 0.3
+    w2, b2 = _rand((N, D), 10, 1 / math.sqrt(D)), _rand((N,), 11)
+    wg = (w2 * g[None, :]).to(torch.bfloat16).contiguous()
+    bf = (b2 + w2 @ be).contiguous()
+    cs = wg.float().sum(1).contiguous()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(xs, wg, out, bias=bf, act=act, ln_fold=(stats, cs, 1e-6))
+    ref = F.layer_norm(x32, (D,), g, be, 1e-6) @ w2.t() + b2
+    if act == "gelu":
+        ref = F.gelu(ref)
+    # unfused path on the same stream: LayerNorm kernel -> bf16 -> GEMM
+    h = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    ops.layernorm(xs, g, be, h, 1e-6)
+    out_u = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(h, w2.to(torch.bfloat16).contiguous(), out_u, bias=b2, act=act)
+    e_f, e_u = _relerr(out.float(), ref), _relerr(out_u.float(), ref)
+    print(f"LN fold act={act}: rel err folded {e_f:.2e}, unfused {e_u:.2e}")
+    assert e_f < 6e-3 and e_f < 1.5 * e_u + 1e-3
