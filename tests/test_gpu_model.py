@@ -138,7 +138,7 @@ def test_image_encoder_vs_oracle(vit, img, frames):
     assert float(d.mean()) < 1e-2 and float(d.max()) < 0.15   # LayerNorm-ed outputs are O(1); output itself is bf16 (ulp 8e-3)
 
 
-def _end_to_end(vit, img, V, P, seed, residual_dtype=torch.float32):
+def _end_to_end(vit, img, V, P, seed, residual_dtype=torch.bfloat16):
     from grove_b200.modeling.grounding import GroundingBranch
     from oracle.grounding import VIT_CFG
     cfg = VIT_CFG[vit]
@@ -183,9 +183,10 @@ def test_end_to_end_config2():
 
 
 @pytest.mark.parametrize("vit,V", [("vit_b", 1), ("vit_h", 2)])
-def test_end_to_end_bf16_residual_stream(vit, V):
-    """configs 2 and 3 with the residual stream kept in bf16 (ImageEncoderViT.residual_dtype): same tolerance as the fp32 stream"""
-    _end_to_end(vit, 1024, V, 4, 21 if vit == "vit_b" else 22, residual_dtype=torch.bfloat16)
+def test_end_to_end_fp32_residual_stream(vit, V):
+    """configs 2 and 3 with the residual stream kept in fp32 (ImageEncoderViT.residual_dtype = torch.float32; the default is bfloat16
+    with the LayerNorms folded into the GEMMs): same tolerance, same measured drift"""
+    _end_to_end(vit, 1024, V, 4, 21 if vit == "vit_b" else 22, residual_dtype=torch.float32)
 
 
 def test_end_to_end_config3_one_gpu_share():
