@@ -388,6 +388,7 @@ def main():
     gb.grounding_encoder.image_encoder.enable_cuda_graphs(False)
     for i in range(2):
         rec.clear()
+        torch.cuda._sleep(int(4e7))      # ~20 ms of spin: the host queues the whole step behind it, so the events bracket GPU time only
         step_resident(i)
     torch.cuda.synchronize()
     ops.gemm, ops.conv_gemm = orig_gemm, orig_conv

