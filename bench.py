@@ -364,8 +364,8 @@ def main():
         extras["config5"] = bench_config5(gb, dev_sets, dev, world, dist, parallel, ops)
     if not args.no_extras and (VIT, VIDEOS) == ("vit_b", 1):
         try:
-            extras["config3"] = bench_config3(dev, world, dist, ops)
-        except Exception as e:   # the secondary leg must never take the headline down
+            extras["config3"], extras["config4"] = bench_config3_and_4(dev, world, dist, ops, parallel)
+        except Exception as e:   # the secondary legs must never take the headline down
             extras["config3"] = {"error": repr(e)[:200]}
 
     # ---- per-kernel device time of the tensor-core GEMM (the dominant kernel), CUDA events on the launching stream
@@ -478,9 +478,12 @@ def bench_config5(gb, dev_sets, dev, world, dist, parallel, ops, frames=128, phr
             "records_shape": list(out.shape), "collective": "dist.all_gather_into_tensor (NCCL) on the compute stream" if world > 1 else None}
 
 
-def bench_config3(dev, world, dist, ops, videos=2, steps=5, warmup=2):
+def bench_config3_and_4(dev, world, dist, ops, parallel, videos=2, steps=5, warmup=2):
     """BASELINE configs[2], one GPU's share: SAM ViT-H (the model GROVE builds, GROVE.py:55) + box decoder on 2 videos x 8 frames at 1024^2 with
-    4 phrases each; random-init weights of that architecture (torch default init on the device, zero-initialised tables re-randomised)."""
+    4 phrases each; random-init weights of that architecture (torch default init on the device, zero-initialised tables re-randomised).
+    Then BASELINE configs[3] on the same model: the training step of the grounding branch (forward + backward + L1/GIoU + objectness loss)
+    on one 32-frame clip per GPU at the reference's training resolution (512^2 after interpolate_positional_embeddings, train.py:52,561-576),
+    gradients of the trainable grounding parameters averaged over the ranks with the all-reduce overlapped with the backward pass."""
     from grove_b200.modeling.grounding import GroundingBranch
     from oracle import synth
     from oracle.grounding import VIT_CFG
@@ -520,12 +523,74 @@ def bench_config3(dev, world, dist, ops, videos=2, steps=5, warmup=2):
     fl = videos * FRAMES * (useful_flops_per_frame(cfg["embed_dim"], cfg["depth"], len(cfg["global_idx"]), IMG // 16)
                             + PHRASES * decoder_flops_per_instance((IMG // 16) ** 2))
     pk = peaks()
+    c3 = {"workload": f"SAM ViT-H + box decoder, {videos} videos x {FRAMES} frames at {IMG}^2 x {PHRASES} phrases per GPU (BASELINE configs[2] share)",
+          "ms_per_step": ms, "frames_per_s": world * videos * FRAMES / (ms * 1e-3), "steps": steps,
+          "step_useful_tflops": fl / (ms * 1e-3) / 1e12, "step_frac_of_peak": fl / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+          "scaling": "weak", "weights": "torch default random init (not the deterministic synth set: 818 M parameters)"}
+    try:
+        c4 = _bench_config4(gh, dev, world, dist, parallel, g)
+    except Exception as e:
+        c4 = {"error": repr(e)[:200]}
     del gh
     torch.cuda.empty_cache()
-    return {"workload": f"SAM ViT-H + box decoder, {videos} videos x {FRAMES} frames at {IMG}^2 x {PHRASES} phrases per GPU (BASELINE configs[2] share)",
-            "ms_per_step": ms, "frames_per_s": world * videos * FRAMES / (ms * 1e-3), "steps": steps,
-            "step_useful_tflops": fl / (ms * 1e-3) / 1e12, "step_frac_of_peak": fl / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
-            "scaling": "weak", "weights": "torch default random init (not the deterministic synth set: 818 M parameters)"}
+    return c3, c4
+
+
+def _bench_config4(gh, dev, world, dist, parallel, g, frames=32, img=512, steps=3, warmup=1):
+    from grove_b200 import checkpoint as ck
+    from oracle import synth
+    gh.enable_cuda_graphs(False)
+    gh._graphs = {}
+    torch.cuda.empty_cache()
+    enc = gh.grounding_encoder.image_encoder
+    ck.interpolate_positional_embeddings(enc, img)                 # train.py:561-576
+    gh.grounding_encoder.prompt_encoder.image_embedding_size = (img // 16, img // 16)     # the reference's factory value (build_sam.py:66-69)
+    gh.config.num_frames = frames
+    for p in gh.parameters():                                      # GROVE's freeze pattern (train.py:254-296)
+        p.requires_grad_(False)
+    for p in list(enc.adapters.parameters()) + list(gh.grounding_encoder.mask_decoder.parameters()) + list(gh.text_hidden_fcs.parameters()):
+        p.requires_grad_(True)
+    images = torch.randn(1, 3, frames, img, img, device=dev, generator=g).to(torch.bfloat16)
+    hidden = torch.randn(1, SEQ_L, 4096, device=dev, generator=g).to(torch.bfloat16)
+    ids = torch.full((1, SEQ_L - 575), 7, dtype=torch.long)
+    for p in synth.det_positions(SEQ_L, PHRASES, 400):
+        ids[0, p - 575 + 1] = 32005
+    mask = gh._create_det_token_mask(ids).to(dev)
+    cg = torch.Generator().manual_seed(9)
+    gt_b, gt_o = [[]], [[]]
+    for f in range(frames):
+        lab = (torch.rand(PHRASES, generator=cg) > 0.5).double()
+        if f == 0:
+            lab[0] = 1.0
+        nb = int(lab.sum())
+        gt_b[0].append(torch.cat([torch.rand(nb, 2, generator=cg) * 0.4 + 0.3, torch.rand(nb, 2, generator=cg) * 0.3 + 0.1], 1))
+        gt_o[0].append(lab)
+    red = None
+
+    def step():
+        nonlocal red
+        red = parallel.GradientReducer() if world > 1 else None
+        return gh.grounding_loss_and_grads(images, hidden, mask, gt_b, gt_o, apply=False, reducer=red)
+    for _ in range(warmup):
+        losses, _, _ = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses, _, grads = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1), dev, world, dist) / steps
+    trainable = sum(t.numel() for t in grads.g.values())
+    return {"workload": f"training step of the grounding branch (forward + backward, GIoU + L1 + objectness), SAM ViT-H, 1 clip x {frames} frames at "
+                        f"{img}^2 x {PHRASES} phrases per GPU (BASELINE configs[3]: data parallel over clips)",
+            "ms_per_step": ms, "frames_per_s": world * frames / (ms * 1e-3), "steps": steps, "loss": float(losses["loss"]),
+            "trainable_params": trainable, "scaling": "weak",
+            "gradient_allreduce": (f"{red.reduced_elems * 4 / 1e6:.0f} MB fp32 in {red.calls} groups on a side stream, overlapped with the backward pass "
+                                   "(parallel.GradientReducer, NCCL)") if red is not None else None,
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
 
 
 if __name__ == "__main__":

@@ -134,8 +134,10 @@ def encode_train(enc, x: torch.Tensor):
     return emb.view(Fr, N, C), tape
 
 
-def encode_backward(enc, tape, d_emb: torch.Tensor, grads: GradStore) -> None:
-    """d_emb: fp32 [M, out_chans] cotangent of the token-major embeddings.  Accumulates the adapters' gradients into `grads`."""
+def encode_backward(enc, tape, d_emb: torch.Tensor, grads: GradStore, on_ready=None) -> None:
+    """d_emb: fp32 [M, out_chans] cotangent of the token-major embeddings.  Accumulates the adapters' gradients into `grads`.
+    `on_ready(list of fp32 accumulators)` is called as soon as an adapter's gradients are final (its weight gradient is the last thing the
+    walk adds to them), so a data-parallel reducer can overlap their all-reduce with the rest of the walk."""
     from .image_encoder import _resize_rel_pos
     first = tape["first"]
     if first is None:
@@ -174,6 +176,8 @@ def encode_backward(enc, tape, d_emb: torch.Tensor, grads: GradStore) -> None:
             if _wants(c3.weight):
                 gw = grads.buf(c3.weight, shape=(D, 27 * D), unpack=lambda g, w=c3.weight: unpack_conv3d_grad(g, w))   # tap-major packed layout
                 ops.conv_wgrad(dyc, A["x_in"], gw, V=Fr // 8, T=8, G=G, kt=3)
+            if on_ready is not None:
+                on_ready([grads.g[p] for p in (c3.weight, c3.bias, ad.alpha) if p in grads.g])
             if i == first:
                 break                                               # nothing trainable precedes the first adapter
             wcf = enc._pack.get(k + ".c3w.flipT", [c3.weight], lambda w: bf16(w.flip(2, 3, 4).permute(1, 2, 3, 4, 0).reshape(w.shape[1], -1)))

@@ -221,7 +221,7 @@ class GroundingBranch(nn.Module):
 
     @torch.no_grad()
     def grounding_loss_and_grads(self, images, last_hidden_state, det_token_mask, gt_bboxes_list, gt_temp_objectness_list, ce_loss=None,
-                                 upstream: float = 1.0, apply: bool = True, _cotangent=None):
+                                 upstream: float = 1.0, apply: bool = True, _cotangent=None, reducer=None):
         """One training step of the grounding branch — model_forward's grounding half + _compute_loss_components_video + backward
         (GROVE.py:162-198, 339-381; train.py:761-770) — on the CUDA library, without autograd.
 
@@ -288,7 +288,10 @@ class GroundingBranch(nn.Module):
         # ---- backward: decoder -> encoder (adapters) and text projection
         d_emb, d_text = ge.mask_decoder.backward(dec_tape, dboxes, dlogits, grads)
         del dec_tape
-        encode_backward(ge.image_encoder, enc_tape, d_emb, grads)
+        on_ready = reducer.ready if reducer is not None else None
+        if on_ready is not None:
+            on_ready([grads.g[p] for p in ge.mask_decoder.parameters() if p in grads.g])     # the decoder's gradients are final
+        encode_backward(ge.image_encoder, enc_tape, d_emb, grads, on_ready=on_ready)
         del enc_tape
         onehot = torch.zeros(B, n, device=dev, dtype=torch.float32)
         onehot[torch.arange(B, device=dev), row_of_t] = 1.0
@@ -313,6 +316,9 @@ class GroundingBranch(nn.Module):
         d_hidden[idx.long()] = d_a[:n]
         if upstream != 1.0:
             d_hidden *= upstream
+        if reducer is not None:
+            reducer.ready([grads.g[p] for p in self.text_hidden_fcs.parameters() if p in grads.g])
+            reducer.finish()
         if apply:
             grads.apply(upstream)
         return losses, d_hidden.view(V, L, Hd), grads

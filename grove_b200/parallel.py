@@ -177,6 +177,49 @@ def allreduce_gradients(grads: Sequence[torch.Tensor], *, group: Optional[dist.P
     flush()
 
 
+class GradientReducer:
+    """Data-parallel gradient averaging OVERLAPPED with the backward pass (BASELINE config 4; the reference delegates this to DeepSpeed
+    ZeRO-2's overlap_comm, train.py:466-486).  The training step calls `ready(tensors)` as soon as a group of fp32 gradient accumulators is
+    final — the mask decoder right after its backward, each Conv3d adapter right after its weight gradient, text_hidden_fcs at the end —
+    and the group is all-reduced on a side stream while the encoder walk continues on the compute stream (a ViT-H adapter is 44 M fp32
+    values = 177 MB: its all-reduce hides under the ~8 frozen blocks the walk still has to cross).  `finish()` joins the streams.
+    Small tensors of a group share one flat bucket; on CPU tensors (gloo tests) everything runs synchronously."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, bucket_elems: int = 1 << 26, average: bool = True):
+        self.group, self.bucket_elems, self.average = group, bucket_elems, average
+        self._stream = None
+        self.reduced_elems = 0
+        self.calls = 0
+
+    def _active(self) -> bool:
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def ready(self, grads: Sequence[torch.Tensor]) -> None:
+        grads = [g for g in grads if g is not None]
+        if not grads or not self._active():
+            return
+        self.calls += 1
+        self.reduced_elems += sum(g.numel() for g in grads)
+        if not grads[0].is_cuda:
+            allreduce_gradients(grads, group=self.group, bucket_elems=self.bucket_elems, average=self.average)
+            return
+        dev = grads[0].device
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))            # the gradients are final at this point of the compute stream
+        self._stream.wait_event(ev)
+        with torch.cuda.stream(self._stream):
+            for g in grads:
+                g.record_stream(self._stream)
+            allreduce_gradients(grads, group=self.group, bucket_elems=self.bucket_elems, average=self.average)
+
+    def finish(self) -> None:
+        """the compute stream waits for every outstanding reduction (call before the optimizer step reads the gradients)"""
+        if self._stream is not None:
+            torch.cuda.current_stream(self._stream.device).wait_stream(self._stream)
+
+
 def allreduce_gradstore(store, parameters: Sequence[torch.Tensor], **kw) -> None:
     """all-reduce the accumulators of a modeling.decoder_train.GradStore, visiting `parameters` in their (rank-independent) order"""
     allreduce_gradients([store.g[p] for p in parameters if p in store.g], **kw)

@@ -79,6 +79,18 @@ def main():
     report["allreduce_rel_err"] = max(errs)
     assert max(errs) < 1e-5, errs
     report["grad_tensors"] = len(params)
+    # the same step with the reduction OVERLAPPED with the backward pass (parallel.GradientReducer: decoder, then each adapter as the encoder
+    # walk finishes it, then text_hidden_fcs, all-reduced on a side stream): equals the mean of the per-rank gradients up to the run-to-run
+    # noise of the step itself (a few float atomics, ~1e-4 of a gradient's norm)
+    red = parallel.GradientReducer()
+    _, _, grads2 = gbt.grounding_loss_and_grads(images.to(torch.bfloat16), hidden.to(torch.bfloat16), mask, gt_boxes, gt_obj, apply=False, reducer=red)
+    torch.cuda.synchronize()
+    errs2 = []
+    for p, lst in zip(probe, gathered):
+        mean = torch.stack(lst).mean(0)
+        errs2.append(float((grads2.g[p] - mean).norm() / (mean.norm() + 1e-30)))
+    report["overlapped_rel_err"], report["overlapped_calls"], report["overlapped_elems"] = max(errs2), red.calls, red.reduced_elems
+    assert max(errs2) < 2e-3 and red.calls >= 6, (errs2, red.calls)
     dist.barrier()
     if rank == 0:
         print("NCCL_WORKER_OK " + json.dumps(report), flush=True)

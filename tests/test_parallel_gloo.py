@@ -72,6 +72,43 @@ def _grad_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+def _reducer_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(200 + rank)
+        groups = [[torch.randn(40, 3, generator=g), torch.randn(7, generator=g)], [torch.randn(500, generator=g)], [torch.randn(1, generator=g)]]
+        red = parallel.GradientReducer(bucket_elems=100)
+        for grp in groups:                 # handed over group by group, as the backward pass produces them
+            red.ready(grp)
+        red.finish()
+        ret[rank] = (groups, red.calls, red.reduced_elems)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_reducer_groups():
+    """config 4: the overlapped reducer (here on CPU tensors: synchronous) averages every group it is handed"""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_reducer_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    per_rank = []
+    for r in range(world):
+        g = torch.Generator().manual_seed(200 + r)
+        per_rank.append([[torch.randn(40, 3, generator=g), torch.randn(7, generator=g)], [torch.randn(500, generator=g)], [torch.randn(1, generator=g)]])
+    for r in range(world):
+        groups, calls, elems = ret[r]
+        assert calls == 3 and elems == 120 + 7 + 500 + 1
+        for gi, grp in enumerate(groups):
+            for ti, t in enumerate(grp):
+                assert torch.allclose(t, (per_rank[0][gi][ti] + per_rank[1][gi][ti]) / 2, atol=1e-6)
+    single = parallel.GradientReducer()    # no process group: a no-op
+    x = torch.ones(3)
+    single.ready([x]); single.finish()
+    assert torch.equal(x, torch.ones(3)) and single.calls == 0
+
+
 def test_gradient_allreduce_buckets():
     """config 4's data-parallel gradient averaging: bucketed all-reduce equals the mean of the per-rank gradients"""
     world = 2
