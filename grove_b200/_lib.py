@@ -48,11 +48,9 @@ SIGNATURES = {
     "grove_im2col_patch16": [_P, _P, _I, _I, _I, _I, _P],
     "grove_layernorm": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "grove_layernorm_bf16in": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
-    "grove_attn_window_relpos_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_attn_window_relpos_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd_lse": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "grove_attn_global_relpos_fwd_mma": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_cast_f32_bf16": [_P, _P, _LL, _P],
     "grove_tokens_to_nchw_bf16": [_P, _P, _I, _I, _I, _P],
     "grove_adaptive_avgpool3d_tokens": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -102,7 +100,31 @@ SIGNATURES = {
 _RESTYPES = {"grove_last_error": C.c_char_p, "grove_launch_count": C.c_longlong, "grove_reset_launch_count": None, "grove_add_launch_count": None,
              "grove_attn_relpos_bwd_workspace_bytes": C.c_longlong}
 
+# test-only cross-check kernels (libgrove_b200_legacy.so, include/grove_b200_legacy.h)
+LEGACY_LIB_PATH = os.path.join(_HERE, "libgrove_b200_legacy.so")
+LEGACY_SIGNATURES = {
+    "grove_attn_window_relpos_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_attn_global_relpos_fwd_mma": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "grove_last_error": [],
+}
+
 _lib = None
+_legacy = None
+
+
+def lib_legacy() -> C.CDLL:
+    """the test-only library with the round-1 mma.sync forward attention kernels"""
+    global _legacy
+    if _legacy is None:
+        if not os.path.exists(LEGACY_LIB_PATH):
+            raise RuntimeError(f"{LEGACY_LIB_PATH} is missing: build it with `python -m grove_b200.build`")
+        l = C.CDLL(LEGACY_LIB_PATH)
+        for name, args in LEGACY_SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = C.c_char_p if name == "grove_last_error" else C.c_int
+        _legacy = l
+    return _legacy
 
 
 def lib() -> C.CDLL:

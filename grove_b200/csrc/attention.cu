@@ -8,7 +8,7 @@
 //   * window blocks: per CTA one (frame, window, head); operates on the UNPARTITIONED token-major qkv — pad
 //     tokens (grid 64 -> 70) are synthesised in shared memory as k = b_k, v = b_v, pad queries are skipped.
 #include "common.cuh"
-#include "grove_b200.h"
+#include "grove_b200_legacy.h"
 
 namespace grove {
 

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(128) t2i_attention_kernel(const float* __restr
   }
 }
 
+constexpr int kI2tIter = 4;
 // ---------------------------------------------------------------- image -> token attention (per key row, T tokens)
 // thread = (row n, head h), head fastest so a warp reads 4 contiguous 256-byte rows.
 // qi bf16 [*,N,H*DH] (row block src_of[b]); kt,vt fp32 [B,T,H*DH]; out bf16 [B,N,H*DH].
@@ -159,42 +160,47 @@ __global__ void __launch_bounds__(256) i2t_attention_kernel(const __nv_bfloat16*
     vs[(t * heads + c / DH) * HS + c % DH] = vt[(size_t)b * T * HD + i];
   }
   __syncthreads();
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = gid / heads, h = gid % heads;
-  if (n >= N) return;
-  const size_t qoff = ((size_t)(src_of ? src_of[b] : b) * N + n) * HD + h * DH;
-  const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(qi + qoff)), q1 = __ldg(reinterpret_cast<const uint4*>(qi + qoff) + 1);
-  const uint32_t qu[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-  float qf[DH];
+  // kI2tIter (row, head) pairs per thread: the 6 KB k/v preload above is amortised over 4x the rows (4096 CTAs of one pair each spent
+  // most of their time on it)
+#pragma unroll 1
+  for (int it = 0; it < kI2tIter; ++it) {
+    const int gid = (blockIdx.x * kI2tIter + it) * blockDim.x + threadIdx.x;
+    const int n = gid / heads, h = gid % heads;
+    if (n >= N) return;
+    const size_t qoff = ((size_t)(src_of ? src_of[b] : b) * N + n) * HD + h * DH;
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(qi + qoff)), q1 = __ldg(reinterpret_cast<const uint4*>(qi + qoff) + 1);
+    const uint32_t qu[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float qf[DH];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { const float2 a = unpack_bf16(qu[i]); qf[2 * i] = a.x; qf[2 * i + 1] = a.y; }
-  float s[T], mx = -INFINITY;
+    for (int i = 0; i < 8; ++i) { const float2 a = unpack_bf16(qu[i]); qf[2 * i] = a.x; qf[2 * i + 1] = a.y; }
+    float s[T], mx = -INFINITY;
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
-    float a = 0.f;
+    for (int t = 0; t < T; ++t) {
+      float a = 0.f;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) a += qf[d] * ks[(t * heads + h) * HS + d];
-    s[t] = a;
-    mx = fmaxf(mx, a);
+      for (int d = 0; d < DH; ++d) a += qf[d] * ks[(t * heads + h) * HS + d];
+      s[t] = a;
+      mx = fmaxf(mx, a);
+    }
+    float l = 0.f, o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float p = exp2f(s[t] - mx);
+      l += p;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) o[d] += p * vs[(t * heads + h) * HS + d];
+    }
+    const float inv = 1.f / l;
+    uint4 w0 = make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv), pack_bf16(o[4] * inv, o[5] * inv),
+                          pack_bf16(o[6] * inv, o[7] * inv));
+    uint4 w1 = make_uint4(pack_bf16(o[8] * inv, o[9] * inv), pack_bf16(o[10] * inv, o[11] * inv), pack_bf16(o[12] * inv, o[13] * inv),
+                          pack_bf16(o[14] * inv, o[15] * inv));
+    uint4* op = reinterpret_cast<uint4*>(out + ((size_t)b * N + n) * HD + h * DH);
+    op[0] = w0;
+    op[1] = w1;
   }
-  float l = 0.f, o[DH];
-#pragma unroll
-  for (int d = 0; d < DH; ++d) o[d] = 0.f;
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const float p = exp2f(s[t] - mx);
-    l += p;
-#pragma unroll
-    for (int d = 0; d < DH; ++d) o[d] += p * vs[(t * heads + h) * HS + d];
-  }
-  const float inv = 1.f / l;
-  uint4 w0 = make_uint4(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv), pack_bf16(o[4] * inv, o[5] * inv),
-                        pack_bf16(o[6] * inv, o[7] * inv));
-  uint4 w1 = make_uint4(pack_bf16(o[8] * inv, o[9] * inv), pack_bf16(o[10] * inv, o[11] * inv), pack_bf16(o[12] * inv, o[13] * inv),
-                        pack_bf16(o[14] * inv, o[15] * inv));
-  uint4* op = reinterpret_cast<uint4*>(out + ((size_t)b * N + n) * HD + h * DH);
-  op[0] = w0;
-  op[1] = w1;
 }
 
 // keys_out[b,n,:] = bf16( LN( keys_in[src_of[b],n,:] + delta[b,n,:] ) ), C = 256, one warp per row (norm4, transformer.py:180)
@@ -445,7 +451,7 @@ extern "C" int grove_decoder_i2t_attention(const void* qi, const float* kt, cons
   GROVE_CHECK_ARG(qi && kt && vt && out && B > 0 && N > 0 && heads > 0 && B <= 65535);
   if (T != 6 || dh != 16) { grove_set_error("i2t attention is built for T=6 tokens, 16-dim heads (got T=%d dh=%d)", T, dh); return GROVE_ERR_UNSUPPORTED; }
   const int smem = 2 * T * heads * (dh + 1) * sizeof(float);
-  i2t_attention_kernel<6, 16><<<dim3((N * heads + 255) / 256, B), 256, smem, stream>>>((const __nv_bfloat16*)qi, kt, vt, src_of,
+  i2t_attention_kernel<6, 16><<<dim3((N * heads + 256 * kI2tIter - 1) / (256 * kI2tIter), B), 256, smem, stream>>>((const __nv_bfloat16*)qi, kt, vt, src_of,
                                                                                        (__nv_bfloat16*)out, N, heads);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();

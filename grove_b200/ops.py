@@ -6,7 +6,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import GemmEpilogue, TwoWayAParams, TwoWayBParams, check, lib
+from ._lib import GemmEpilogue, TwoWayAParams, TwoWayBParams, check, lib, lib_legacy
 
 BF16, F32 = torch.bfloat16, torch.float32
 ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "sigmoid": 3}
@@ -138,11 +138,13 @@ def layernorm(x, gamma, beta, out, eps):
 
 
 def attn_window(qkv, qkv_bias_bf16, rel_h, rel_w, out, *, F, G, heads, hd, ws=14):
+    """TEST-ONLY: the round-1 mma.sync window attention (libgrove_b200_legacy.so), cross-check of attn_window_tc"""
     for t, n in ((qkv, "qkv"), (qkv_bias_bf16, "qkv_bias"), (rel_h, "rel_pos_h"), (rel_w, "rel_pos_w"), (out, "out")):
         _req(t, BF16, n)
     assert qkv.numel() == F * G * G * 3 * heads * hd and rel_h.shape == (2 * ws - 1, hd)
-    check(lib().grove_attn_window_relpos_fwd(_p(qkv), _p(qkv_bias_bf16), _p(rel_h), _p(rel_w), _p(out), F, G, heads, hd, ws, _stream(qkv)),
-          "grove_attn_window_relpos_fwd")
+    rc = lib_legacy().grove_attn_window_relpos_fwd(_p(qkv), _p(qkv_bias_bf16), _p(rel_h), _p(rel_w), _p(out), F, G, heads, hd, ws, _stream(qkv))
+    if rc:
+        raise RuntimeError(f"grove_attn_window_relpos_fwd (legacy) failed: {lib_legacy().grove_last_error().decode(errors='replace')}")
     return out
 
 
@@ -173,8 +175,12 @@ def attn_global(qkv, rel_h, rel_w, out, *, F, G, heads, hd, legacy_mma=False, ls
         check(lib().grove_attn_global_relpos_fwd_lse(_p(qkv), _p(rel_h), _p(rel_w), _p(out), _p(_req(lse, F32, "lse")), F, G, heads, hd,
                                                      _stream(qkv)), "grove_attn_global_relpos_fwd_lse")
         return out
-    fn = lib().grove_attn_global_relpos_fwd_mma if legacy_mma else lib().grove_attn_global_relpos_fwd
-    check(fn(_p(qkv), _p(rel_h), _p(rel_w), _p(out), F, G, heads, hd, _stream(qkv)), "grove_attn_global_relpos_fwd")
+    if legacy_mma:      # test-only cross-check kernel
+        rc = lib_legacy().grove_attn_global_relpos_fwd_mma(_p(qkv), _p(rel_h), _p(rel_w), _p(out), F, G, heads, hd, _stream(qkv))
+        if rc:
+            raise RuntimeError(f"grove_attn_global_relpos_fwd_mma (legacy) failed: {lib_legacy().grove_last_error().decode(errors='replace')}")
+        return out
+    check(lib().grove_attn_global_relpos_fwd(_p(qkv), _p(rel_h), _p(rel_w), _p(out), F, G, heads, hd, _stream(qkv)), "grove_attn_global_relpos_fwd")
     return out
 
 

@@ -98,30 +98,21 @@ int grove_layernorm_bf16in(const void* x, const float* gamma, const float* beta,
                            grove_stream_t stream);
 int grove_layernorm(const float* x, const float* gamma, const float* beta, void* y, int y_f32, int rows, int D, float eps,
                     grove_stream_t stream);
-/* Windowed attention with decomposed rel-pos bias on the UNPARTITIONED token-major qkv[F,G,G,3,heads,hd]
- * (bf16): window_partition's zero padding after norm1 (image_encoder.py:245-249,344-348) is reproduced by
- * giving pad tokens k = b_k, v = b_v (qkv_bias, bf16) — they receive softmax mass like in the reference —
- * and window_unpartition's crop (:382-383) by not computing pad queries.  rel_pos_h/w: [2*ws-1, hd] bf16.
- * out[F,G,G,heads*hd] bf16.  Replaces Attention.forward :301-326 + add_decomposed_rel_pos :420-458.
- * (legacy warp-level mma.sync implementation, kept as an independent cross-check for the tests) */
-int grove_attn_window_relpos_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w,
-                                 void* out, int F, int G, int heads, int hd, int ws, grove_stream_t stream);
-/* The same contract on tcgen05/TMEM/TMA (attention_win_tc.cu): persistent CTAs over (frame, window, head) units, one 4-D TMA
- * box per operand, pad tokens patched in shared memory, P kept in tensor memory.  rel_table: bf16 [64, hd] with rows 0..26 =
- * rel_pos_h, rows 32..58 = rel_pos_w, other rows zero.  This is the kernel the modules call. */
+/* Windowed attention with decomposed rel-pos bias on the UNPARTITIONED token-major qkv[F,G,G,3,heads,hd] (bf16), tcgen05/TMEM/TMA
+ * (attention_win_tc.cu): window_partition's zero padding after norm1 (image_encoder.py:245-249,344-348) is reproduced by giving pad
+ * tokens k = b_k, v = b_v (qkv_bias, bf16) — they receive softmax mass like in the reference — and window_unpartition's crop (:382-383)
+ * by not computing pad queries.  Persistent CTAs over (frame, window, head) units, one 4-D TMA box per operand, pad tokens patched in
+ * shared memory, P kept in tensor memory.  rel_table: bf16 [64, hd] with rows 0..26 = rel_pos_h, rows 32..58 = rel_pos_w, other rows
+ * zero.  out[F,G,G,heads*hd] bf16.  Replaces Attention.forward :301-326 + add_decomposed_rel_pos :420-458 on windowed blocks. */
 int grove_attn_window_relpos_tc_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_table, void* out, int F, int G, int heads,
                                     int hd, int ws, grove_stream_t stream);
 /* Global attention over one frame's G*G tokens with decomposed rel-pos bias (tables [2G-1, hd] bf16): tcgen05/TMEM/TMA
- * kernel (attention_tc.cu), exact two-phase softmax, scores never leave the SM.  qkv [F,G,G,3,heads,hd], out [F,G,G,heads*hd]. */
+ * kernel (attention_tc.cu), single-pass softmax with a lazily raised running maximum, scores never leave the SM.  qkv [F,G,G,3,heads,hd], out [F,G,G,heads*hd]. */
 int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
                                  int heads, int hd, grove_stream_t stream);
 /* Same, additionally writing lse[F*G*G, heads] fp32 = log2-domain log-sum-exp of every query row (max + log2 sum, scale and bias
  * included) — saved by the training forward so that grove_attn_relpos_bwd can skip its own log-sum-exp sweep (lse may be NULL). */
 int grove_attn_global_relpos_fwd_lse(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, float* lse, int F, int G,
-                                     int heads, int hd, grove_stream_t stream);
-/* Same contract on the legacy warp-level tensor path (mma.sync flash kernel, attention.cu) — kept as an independent
- * cross-check for the tests; the modules never call it. */
-int grove_attn_global_relpos_fwd_mma(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,
                                      int heads, int hd, grove_stream_t stream);
 /* fp32 -> bf16 cast (n % 8 == 0) and token-major [F,N,C] bf16 -> NCHW [F,C,N] transposition helpers */
 int grove_cast_f32_bf16(const float* x, void* y, long long n, grove_stream_t stream);

@@ -19,6 +19,14 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(l, name), f"{name} is declared in include/grove_b200.h but not exported by libgrove_b200.so"
     assert declared == set(SIGNATURES), (declared ^ set(SIGNATURES))
     assert l.grove_abi_version() == 5
+    # the test-only cross-check kernels live in their own header / library and are NOT part of the product library
+    from grove_b200._lib import LEGACY_SIGNATURES, lib_legacy
+    lhdr = open(os.path.join(ROOT, "include", "grove_b200_legacy.h")).read()
+    ldecl = set(re.findall(r"\b(grove_[a-z0-9_]+)\s*\(", lhdr))
+    assert ldecl == set(LEGACY_SIGNATURES) - {"grove_last_error"}
+    ll = lib_legacy()
+    for name in ldecl:
+        assert hasattr(ll, name) and not hasattr(l, name), name
 
 
 @pytest.mark.parametrize("vit", ["vit_b", "vit_l", "vit_h"])
