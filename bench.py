@@ -474,6 +474,8 @@ def bench_config5(gb, dev_sets, dev, world, dist, parallel, ops, frames=128, phr
     best = min(clip_ms)
     return {"workload": f"1 clip x {frames} frames x {phrases} phrases, ViT-B at {IMG}^2, {frames // 8} windows split over {world} GPU(s)",
             "clip_ms": best, "frames_per_s": frames / (best * 1e-3), "allgather_us": (min(ag_us) if ag_us else None),
+            "allgather_us_note": "CUDA events around the collective on the compute stream: includes waiting for the slowest rank's last window "
+                                 "(the transfer itself is ~13 us for 20 KB per rank, profiles/r2_nccl_2gpu.json)",
             "allgather_bytes_per_rank": (frames // 8 + world - 1) // world * 8 * phrases * 5 * 4, "scaling": "strong",
             "records_shape": list(out.shape), "collective": "dist.all_gather_into_tensor (NCCL) on the compute stream" if world > 1 else None}
 

@@ -201,20 +201,23 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       PROBE(1002 + 3 * kit);
       ++kit; ++sit;
     };
-    // S(b+1) is issued before P(b).V(b) so the softmax of block b+1 overlaps the P.V of block b
+    // Issue schedule.  Back-to-back UMMAs that accumulate into the SAME tensor-memory tile were measured at about twice their nominal
+    // duration (125 clk per 128x128x16, 56 clk per 128x64x16: the accumulator read-modify-write of one instruction does not overlap the
+    // next), so Q.K^T(b+2) and P(b).V(b) -- independent accumulators -- are issued INTERLEAVED (one Q.K^T k-step, two P.V k-steps, ...).
+    // S is produced two blocks ahead: S(b+1) is already complete when the softmax warps finish block b, and the S buffer that block b+2
+    // reuses (b & 1) was drained at the very start of softmax(b).  GROVE_ATT_SEQ=1 at build time restores the sequential order (A/B).
+#ifdef GROVE_ATT_SEQ
     issue_qk();
     for (int b = 0; b < NB; ++b, ++vit) {
       if (b + 1 < NB) issue_qk();
       const uint32_t pb = b & 1u;
       const int v = vit % kVStages;
-      PROBE(1300 + 3 * b);
       mbar_wait2(bar(V_FULL + v), (vit / kVStages) & 1u, bar(P_FULL + pb), (b >> 1) & 1u);
-      PROBE(1301 + 3 * b);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t ta = tP0 + pb * 64 + kk * 8;        // P[:, 16 keys] = 8 packed columns of tensor memory
+          const uint32_t ta = tP0 + pb * 64 + kk * 8;
           const uint64_t db = umma_desc_sw128(sV + v * TS + kk * 2048);
           tc_mma_f16_ts(tO, ta, db, idesc_o, (b | kk) != 0);
           if (kX) tc_mma_f16_ts(tO + 64, ta, umma_desc_sw32(sV + v * TS + 16384 + kk * 512), idesc_ox, (b | kk) != 0);
@@ -224,8 +227,44 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
         if (b == NB - 1) tc_commit(bar(O_FULL));
       }
       __syncwarp();
+    }
+#else
+    issue_qk();
+    if (NB > 1) issue_qk();
+    for (int b = 0; b < NB; ++b, ++vit) {
+      const uint32_t pb = b & 1u;
+      const int v = vit % kVStages;
+      const bool more = b + 2 < NB;
+      const int s = kit % kKStages;
+      const uint32_t sb = sit & 1u;
+      PROBE(1300 + 3 * b);
+      mbar_wait2(bar(V_FULL + v), (vit / kVStages) & 1u, bar(P_FULL + pb), (b >> 1) & 1u);
+      if (more) mbar_wait2(bar(K_FULL + s), (kit / kKStages) & 1u, bar(S_EMPTY + sb), s_empty_par());
+      PROBE(1301 + 3 * b);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t b_smem = sK + s * TS;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (more) tc_mma_f16_ts(tS0 + sb * 128, tQ + k * 8, umma_desc_sw128(b_smem + k * 32), idesc_s, k != 0);
+#pragma unroll
+          for (int kk = 2 * k; kk < 2 * k + 2; ++kk) {
+            const uint32_t ta = tP0 + pb * 64 + kk * 8;        // P[:, 16 keys] = 8 packed columns of tensor memory
+            tc_mma_f16_ts(tO, ta, umma_desc_sw128(sV + v * TS + kk * 2048), idesc_o, (b | kk) != 0);
+            if (kX) tc_mma_f16_ts(tO + 64, ta, umma_desc_sw32(sV + v * TS + 16384 + kk * 512), idesc_ox, (b | kk) != 0);
+          }
+        }
+        if (kX && more) tc_mma_f16_ts(tS0 + sb * 128, tQ + 32, umma_desc_sw32(b_smem + 16384), idesc_s, 1);
+        tc_commit(bar(V_EMPTY + v));
+        tc_commit(bar(P_EMPTY + pb));
+        if (b == NB - 1) tc_commit(bar(O_FULL));
+        if (more) { tc_commit(bar(K_EMPTY + s)); tc_commit(bar(S_FULL + sb)); }
+      }
+      __syncwarp();
+      if (more) { ++kit; ++sit; }
       PROBE(1302 + 3 * b);
     }
+#endif
   } else {
     // ===================== softmax warps: two threads per query row =====================
     const int quad = warp & 3;
