@@ -201,12 +201,11 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
       PROBE(1002 + 3 * kit);
       ++kit; ++sit;
     };
-    // Issue schedule.  Back-to-back UMMAs that accumulate into the SAME tensor-memory tile were measured at about twice their nominal
-    // duration (125 clk per 128x128x16, 56 clk per 128x64x16: the accumulator read-modify-write of one instruction does not overlap the
-    // next), so Q.K^T(b+2) and P(b).V(b) -- independent accumulators -- are issued INTERLEAVED (one Q.K^T k-step, two P.V k-steps, ...).
-    // S is produced two blocks ahead: S(b+1) is already complete when the softmax warps finish block b, and the S buffer that block b+2
-    // reuses (b & 1) was drained at the very start of softmax(b).  GROVE_ATT_SEQ=1 at build time restores the sequential order (A/B).
-#ifdef GROVE_ATT_SEQ
+    // Issue schedule: S(b+1) is issued before P(b).V(b) so the softmax of block b+1 overlaps the P.V of block b.
+    // (Round-2 experiment, -DGROVE_ATT_INTERLEAVE: back-to-back UMMAs into the same accumulator run at about twice their nominal duration,
+    // so Q.K^T(b+2) and P(b).V(b) -- independent accumulators -- were issued interleaved, S two blocks ahead.  Bit-identical results,
+    // but 929 us instead of 704 us per layer: alternating instruction shapes costs more than the accumulator dependency.)
+#ifndef GROVE_ATT_INTERLEAVE
     issue_qk();
     for (int b = 0; b < NB; ++b, ++vit) {
       if (b + 1 < NB) issue_qk();
