@@ -14,6 +14,8 @@
 // Steps 2-3 run on warp-level mma.sync (m16n8k16 bf16, fp32 accumulate); scores never reach HBM.  Windowed blocks address the
 // UNPARTITIONED token-major tensors; window positions outside the image are the zero-padded tokens of window_partition
 // (image_encoder.py:344-348): as keys they carry k = b_k, v = b_v and receive softmax mass, as queries they are skipped.
+#include <cstdlib>
+
 #include "grove_b200.h"
 #include "mma_sync.cuh"
 
@@ -607,6 +609,10 @@ __global__ void rowdot_kernel(const bf16_t* __restrict__ a, const bf16_t* __rest
   out[i] = s;
 }
 
+// attention_bwd_tc.cu
+int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* aux, void* dqkv, int F,
+                          int G, int heads, cudaStream_t st);
+
 template <int S, int HD, bool WIN>
 static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t* Rh, const bf16_t* Rw, const bf16_t* O, const bf16_t* dO, bf16_t* dqkv,
                         float* ws, const float* lse_fwd, int F, int G, int heads, cudaStream_t st) {
@@ -644,7 +650,18 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
     }
   }
   if (!fast_q) attn_bwd_q_kernel<S, HD, WIN><<<grid, 128, smem_q, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqc, A, G, heads);
-  attn_bwd_kv_kernel<S, HD, WIN, GFAST><<<grid, 128, smem_kv, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqkv, G, heads);
+  bool kv_done = false;
+  if constexpr (GFAST && HD == 64 && (S == 64 || S == 32)) {
+    // key side on tcgen05 / TMEM (attention_bwd_tc.cu); GROVE_BWD_MMA_SYNC=1 keeps the warp-level kernel (A/B measurements, cross-check)
+    static const bool use_mma_sync = []() { const char* e = getenv("GROVE_BWD_MMA_SYNC"); return e && e[0] == '1'; }();
+    if (!use_mma_sync) {
+      float* aux = dqc + M * heads * HD;
+      const int rc = launch_attn_bwd_kv_tc(qkv, dO, rel, lse, Dsum, aux, dqkv, F, G, heads, st);
+      if (rc) return rc;
+      kv_done = true;
+    }
+  }
+  if (!kv_done) attn_bwd_kv_kernel<S, HD, WIN, GFAST><<<grid, 128, smem_kv, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqkv, G, heads);
   relpos_kernel<S, HD, WIN, 1><<<grid_rel, 256, smem_rel, st>>>(qkv, Rh, Rw, nullptr, A, dqc, dqkv, G, heads);
   grove_count_launch(5);
   GROVE_CHECK_LAUNCH();
@@ -656,7 +673,7 @@ using namespace grove;
 
 extern "C" long long grove_attn_relpos_bwd_workspace_bytes(int F, int G, int heads, int hd, int ws) {
   const long long M = (long long)F * G * G, S = ws > 0 ? ws : G;
-  return (M * heads * 2 * S * 2 + M * heads * 2 + M * heads * hd) * (long long)sizeof(float);
+  return (M * heads * 2 * S * 2 + M * heads * 2 + M * heads * hd + M * heads * 4 /* aux of the tcgen05 key-side kernel */) * (long long)sizeof(float);
 }
 
 extern "C" int grove_attn_relpos_bwd_lse(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, const void* att,

@@ -1,0 +1,287 @@
+// Key side of the GLOBAL attention backward on tcgen05 / TMEM / TMA (image_encoder.py:301-326, 420-458 under autograd; the blocks are
+// frozen, so only d(qkv) is produced).  Replaces the warp-level mma.sync kernel attn_bwd_kv_kernel for head dim 64 on 32x32 / 64x64 grids.
+//
+//   S[q,k] = scale q.k + rel_h[q, kh] + rel_w[q, kw],  P = exp(S - lse_q),  dP = dO V^T,  dS = P (dP - D_q),  dV = P^T dO,  dK = scale dS^T Q
+//
+// One CTA owns 128 keys of one (frame, head) and sweeps the queries in blocks of 128, everything in the TRANSPOSED orientation (TMEM lane =
+// key) so that P^T and dS^T are directly the A operands of the two accumulating products:
+//   MMA1   S^T = K_own Q_i^T,  dP^T = V_own dO_i^T          (SS-mode UMMA 128x128x64, both into tensor memory)
+//   warps  p = exp2(c S^T + (rel_w[q,kw] + rel_h[q,kh]) log2e - lse_q),  ds = p (dP^T - D_q)   -> bf16 P^T, dS^T written back to TMEM
+//   MMA2   dV += P^T dO_i,  dK += dS^T Q_i                  (TS-mode UMMA 128x64x128, B = the same Q_i / dO_i tiles read MN-major)
+// The per-query quantities come from tables the query-side pass already built (attention_bwd.cu): rel[token, head, 2G] (fp32 bias rows,
+// relpos_kernel), the forward's log-sum-exp and D = rowsum(dO * O), packed into aux[token, head, 4]; TMA boxes deliver the 128 x G rel_w
+// slab, the 128 x 4 rel_h slab of this key block's grid rows and the aux rows of every query block.
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2-9 elementwise (two threads per key row, 64 query columns each).
+// TMEM: S^T | dP^T | P^T | dS^T | dV | dK = 128 + 128 + 64 + 64 + 64 + 64 columns.  S^T/dP^T of block i+1 are issued as soon as block i's
+// values are in registers, so MMA1 and MMA2 run under the elementwise phase of the neighbouring blocks.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "grove_b200.h"
+#include "tmem_ldst.cuh"
+
+namespace grove {
+
+struct BwdKvTmaps { CUtensorMap qkv, dO, relw, relh, aux; };
+
+constexpr int kBwdThreads = 320;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int G>
+struct BwdKvCfg {
+  static constexpr int TS = 16384;                       // one [128 x 64] bf16 operand tile
+  static constexpr int kRelW = 128 * G * 4;              // rel_w slab of a query block: [128 q][G] fp32
+  static constexpr int kSmall = 128 * 4 * 4;             // rel_h slab / aux rows / combined rows: [128 q][4] fp32
+  static constexpr int kStage = 2 * TS + kRelW + 4 * kSmall;   // Q_i | dO_i | rel_w | rel_h | aux | comb_h | D
+  static constexpr int kTx = 2 * TS + kRelW + 2 * kSmall;       // bytes the TMA delivers per stage
+  static constexpr int kSmem = 2 * TS + 2 * kStage + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int G>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __restrict__ dqkv, int heads) {
+  using C = BwdKvCfg<G>;
+  constexpr int HD = 64, TS = C::TS, N = G * G, NB = N / 128, RPT = 128 / G;   // RPT: grid rows covered by one 128-key block
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = s0, sVo = s0 + TS;
+  auto sStage = [&](int s) { return s0 + 2 * TS + (uint32_t)s * C::kStage; };
+  const uint32_t bar0 = s0 + 2 * TS + 2 * C::kStage;
+  uint8_t* smem_al = smem_raw + (s0 - smem_u32(smem_raw));
+  enum { OWN_FULL = 0, STAGE_FULL, STAGE_EMPTY = STAGE_FULL + 2, SD_FULL = STAGE_EMPTY + 2, SD_EMPTY, PD_FULL, PD_EMPTY, ACC_FULL, NUM_BARS };
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  const uint32_t tmem_slot = bar0 + 8u * NUM_BARS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jb = blockIdx.x, h = blockIdx.y, f = blockIdx.z;
+  const int D = heads * HD;
+  const int tok0 = f * N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.qkv);
+    mbar_init(bar(OWN_FULL), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(STAGE_FULL + i), 1); mbar_init(bar(STAGE_EMPTY + i), 9); }
+    mbar_init(bar(SD_FULL), 1); mbar_init(bar(SD_EMPTY), 8); mbar_init(bar(PD_FULL), 8); mbar_init(bar(PD_EMPTY), 1); mbar_init(bar(ACC_FULL), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tP = tmem_base + 256, tDS = tmem_base + 320, tDV = tmem_base + 384, tDK = tmem_base + 448;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(bar(OWN_FULL), 2 * TS);
+      tma_load_2d(sK, &tm.qkv, bar(OWN_FULL), D + h * HD, tok0 + jb * 128);
+      tma_load_2d(sVo, &tm.qkv, bar(OWN_FULL), 2 * D + h * HD, tok0 + jb * 128);
+      for (int i = 0; i < NB; ++i) {
+        const int s = i & 1;
+        mbar_wait(bar(STAGE_EMPTY + s), ((i >> 1) & 1u) ^ 1u);
+        const uint32_t st = sStage(s);
+        mbar_expect_tx(bar(STAGE_FULL + s), C::kTx);
+        const int tq = tok0 + i * 128;
+        tma_load_2d(st, &tm.qkv, bar(STAGE_FULL + s), h * HD, tq);                       // Q_i
+        tma_load_2d(st + TS, &tm.dO, bar(STAGE_FULL + s), h * HD, tq);                   // dO_i
+        tma_load_3d(st + 2 * TS, &tm.relw, bar(STAGE_FULL + s), G, h, tq);               // rel_w[q, 0:G]   (columns G..2G of the bias row)
+        tma_load_3d(st + 2 * TS + C::kRelW, &tm.relh, bar(STAGE_FULL + s), jb * RPT, h, tq);           // rel_h[q, kh of this key block]
+        tma_load_3d(st + 2 * TS + C::kRelW + C::kSmall, &tm.aux, bar(STAGE_FULL + s), 0, h, tq);       // (lse, D, -, -)
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B is MN-major (the [q][d] tile read along q)
+    auto mma2 = [&](int i) {           // dV += P^T dO_i, dK += dS^T Q_i
+      const uint32_t st = sStage(i & 1);
+      mbar_wait(bar(PD_FULL), i & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) tc_mma_f16_ts(tDV, tP + kk * 8, umma_desc_sw128(st + TS + kk * 2048), idesc_o, (i | kk) != 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) tc_mma_f16_ts(tDK, tDS + kk * 8, umma_desc_sw128(st + kk * 2048), idesc_o, (i | kk) != 0);
+        tc_commit(bar(PD_EMPTY));
+        tc_commit(bar(STAGE_EMPTY + (i & 1)));
+        if (i == NB - 1) tc_commit(bar(ACC_FULL));
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar(OWN_FULL), 0);
+#pragma unroll 1
+    for (int i = 0; i < NB; ++i) {
+      const int s = i & 1;
+      const uint32_t st = sStage(s);
+      mbar_wait(bar(STAGE_FULL + s), (i >> 1) & 1u);
+      if (i > 0) mbar_wait(bar(SD_EMPTY), (i - 1) & 1u);       // block i-1's S^T / dP^T are in registers
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tS, umma_desc_sw128(sK + k * 32), umma_desc_sw128(st + k * 32), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, umma_desc_sw128(sVo + k * 32), umma_desc_sw128(st + TS + k * 32), idesc_s, k != 0);
+        tc_commit(bar(SD_FULL));
+      }
+      __syncwarp();
+      if (i > 0) mma2(i - 1);
+    }
+    mma2(NB - 1);
+  } else {
+    // ===================== elementwise warps: two threads per key row =====================
+    const int quad = warp & 3;
+    const int hs = (warp - 2) >> 2;                      // this thread owns query chunks {hs, hs + 2} (32 columns each) of every block
+    const int row = quad * 32 + lane;                    // key row inside the block == TMEM lane
+    const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+    const int et = (warp - 2) * 32 + lane;               // 0..255
+    const int kw = row % G, khl = row / G;               // key column; key row inside this block's RPT grid rows
+    constexpr float kL2e = 1.4426950408889634f;
+    const float c_l2 = 0.125f * kL2e;                    // hd^-0.5 * log2(e), hd = 64
+#pragma unroll 1
+    for (int i = 0; i < NB; ++i) {
+      const int s = i & 1;
+      float* stg = reinterpret_cast<float*>(smem_al + (sStage(s) - s0) + 2 * TS);
+      const float* relw_s = stg;                                         // [128][G]
+      const float* relh_s = stg + 128 * G;                               // [128][4]
+      const float* aux_s = relh_s + 128 * 4;                             // [128][4] = lse, D, -, -
+      float* comb_s = stg + 128 * G + 2 * 128 * 4;                       // [128][4] = rel_h * log2e - lse for the block's grid rows
+      float* dsum_s = comb_s + 128 * 4;                                  // [128]
+      mbar_wait(bar(STAGE_FULL + s), (i >> 1) & 1u);
+      if (et < 128) {
+        const float4 rh = *reinterpret_cast<const float4*>(relh_s + et * 4);
+        const float2 ax = *reinterpret_cast<const float2*>(aux_s + et * 4);
+        *reinterpret_cast<float4*>(comb_s + et * 4) = make_float4(fmaf(rh.x, kL2e, -ax.x), fmaf(rh.y, kL2e, -ax.x), fmaf(rh.z, kL2e, -ax.x), fmaf(rh.w, kL2e, -ax.x));
+        dsum_s[et] = ax.y;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(bar(SD_FULL), i & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * cc + hs;
+        uint32_t rs[32], rd[32];
+        tmem_ld_x32(tS + c * 32 + tlane, rs);
+        tmem_ld_x32(tDP + c * 32 + tlane, rd);
+        tmem_ld_wait();
+        if (cc == 1) {                                   // both chunks of S^T / dP^T are in registers: MMA1 of the next block may overwrite them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(SD_EMPTY));
+        }
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const int q = c * 32 + j;
+          const float v0 = fmaf(__uint_as_float(rs[j]), c_l2, fmaf(relw_s[q * G + kw], kL2e, comb_s[q * 4 + khl]));
+          const float v1 = fmaf(__uint_as_float(rs[j + 1]), c_l2, fmaf(relw_s[(q + 1) * G + kw], kL2e, comb_s[(q + 1) * 4 + khl]));
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(v0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(v1));
+          pp[j >> 1] = pack_bf16(p0, p1);
+          pd[j >> 1] = pack_bf16(p0 * (__uint_as_float(rd[j]) - dsum_s[q]), p1 * (__uint_as_float(rd[j + 1]) - dsum_s[q + 1]));
+        }
+        if (cc == 0 && i > 0) { mbar_wait(bar(PD_EMPTY), (i - 1) & 1u); tc_fence_after(); }   // MMA2 of block i-1 has read P^T / dS^T
+        tmem_st_x16(tP + c * 16 + tlane, pp);
+        tmem_st_x16(tDS + c * 16 + tlane, pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(PD_FULL)); mbar_arrive(bar(STAGE_EMPTY + s)); }
+    }
+    // ---- epilogue: dK (x scale), dV -> bf16 into the k / v slots of dqkv; each thread of a row stores 32 of the 64 head dims
+    mbar_wait(bar(ACC_FULL), 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = dqkv + ((size_t)tok0 + jb * 128 + row) * (3 * D) + h * HD + hs * 32;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {            // 0: dK, 1: dV
+      uint32_t r[32];
+      tmem_ld_x32((which == 0 ? tDK : tDV) + hs * 32 + tlane, r);
+      tmem_ld_wait();
+      const float sc = which == 0 ? 0.125f : 1.0f;
+      __nv_bfloat16* o = orow + (which == 0 ? D : 2 * D);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        *reinterpret_cast<uint4*>(o + j) =
+            make_uint4(pack_bf16(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc), pack_bf16(__uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc),
+                       pack_bf16(__uint_as_float(r[j + 4]) * sc, __uint_as_float(r[j + 5]) * sc), pack_bf16(__uint_as_float(r[j + 6]) * sc, __uint_as_float(r[j + 7]) * sc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// aux[i] = (lse[i], D[i], 0, 0) for i over (token, head)
+__global__ void pack_lse_dsum_kernel(const float* __restrict__ lse, const float* __restrict__ dsum, float4* __restrict__ aux, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) aux[i] = make_float4(lse[i], dsum[i], 0.f, 0.f);
+}
+
+int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows);
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp32 tensor [d2][d1][d0] (d0 contiguous), box (b0, 1, b2), no swizzle
+static int make_tmap_f32_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b2) {
+  static EncodeTiledFn2 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      grove_set_error("cuTensorMapEncodeTiled entry point not available");
+      return GROVE_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn2>(p);
+  }
+  cuuint64_t gdim[3] = {d0, d1, d2}, gstr[2] = {d0 * 4, d0 * d1 * 4};
+  cuuint32_t bdim[3] = {b0, 1, b2}, estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { grove_set_error("cuTensorMapEncodeTiled (fp32, 3-D) failed with CUresult %d", (int)r); return GROVE_ERR_CUDA; }
+  return GROVE_OK;
+}
+
+// called from run_attn_bwd (attention_bwd.cu) for global layers with head dim 64 on 32x32 / 64x64 grids.
+// rel: fp32 [M, heads, 2G] bias rows; lse, dsum: fp32 [M, heads]; aux: fp32 scratch [M, heads, 4]
+int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* aux, void* dqkv, int F,
+                          int G, int heads, cudaStream_t st) {
+  const int N = G * G, D = heads * 64;
+  const long long M = (long long)F * N;
+  pack_lse_dsum_kernel<<<(unsigned)((M * heads + 255) / 256), 256, 0, st>>>(lse, dsum, reinterpret_cast<float4*>(aux), M * heads);
+  grove_count_launch();
+  BwdKvTmaps tm;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tm.qkv, qkv, (uint64_t)3 * D, (uint64_t)M, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm.dO, dO, (uint64_t)D, (uint64_t)M, 64, 128))) return rc;
+  if ((rc = make_tmap_f32_3d(&tm.relw, rel, (uint64_t)2 * G, heads, (uint64_t)M, (uint32_t)G, 128))) return rc;
+  if ((rc = make_tmap_f32_3d(&tm.relh, rel, (uint64_t)2 * G, heads, (uint64_t)M, 4, 128))) return rc;
+  if ((rc = make_tmap_f32_3d(&tm.aux, aux, 4, heads, (uint64_t)M, 4, 128))) return rc;
+  cudaError_t e;
+  if (G == 64) {
+    constexpr int smem = BwdKvCfg<64>::kSmem;
+    static_assert(smem <= 232448, "shared memory budget");
+    e = cudaFuncSetAttribute(attn_bwd_kv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
+    attn_bwd_kv_tc_kernel<64><<<dim3(N / 128, heads, F), kBwdThreads, smem, st>>>(tm, (__nv_bfloat16*)dqkv, heads);
+  } else {
+    constexpr int smem = BwdKvCfg<32>::kSmem;
+    e = cudaFuncSetAttribute(attn_bwd_kv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
+    attn_bwd_kv_tc_kernel<32><<<dim3(N / 128, heads, F), kBwdThreads, smem, st>>>(tm, (__nv_bfloat16*)dqkv, heads);
+  }
+  grove_count_launch();
+  GROVE_CHECK_LAUNCH();
+  return GROVE_OK;
+}
+
+}  // namespace grove
