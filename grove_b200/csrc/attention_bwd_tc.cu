@@ -93,7 +93,8 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
         tma_load_2d(st, &tm.qkv, bar(STAGE_FULL + s), h * HD, tq);                       // Q_i
         tma_load_2d(st + TS, &tm.dO, bar(STAGE_FULL + s), h * HD, tq);                   // dO_i
         tma_load_3d(st + 2 * TS, &tm.relw, bar(STAGE_FULL + s), G, h, tq);               // rel_w[q, 0:G]   (columns G..2G of the bias row)
-        tma_load_3d(st + 2 * TS + C::kRelW, &tm.relh, bar(STAGE_FULL + s), jb * RPT, h, tq);           // rel_h[q, kh of this key block]
+        // rel_h[q, kh of this key block]: 4 floats from a 16-byte aligned column (TMA box origins must be; jb * RPT is odd pairs for G = 64)
+        tma_load_3d(st + 2 * TS + C::kRelW, &tm.relh, bar(STAGE_FULL + s), (jb * RPT) & ~3, h, tq);
         tma_load_3d(st + 2 * TS + C::kRelW + C::kSmall, &tm.aux, bar(STAGE_FULL + s), 0, h, tq);       // (lse, D, -, -)
       }
     }
@@ -142,7 +143,7 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
     const int row = quad * 32 + lane;                    // key row inside the block == TMEM lane
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
     const int et = (warp - 2) * 32 + lane;               // 0..255
-    const int kw = row % G, khl = row / G;               // key column; key row inside this block's RPT grid rows
+    const int kw = row % G, khl = row / G + ((jb * RPT) & 3);   // key column; key row relative to the aligned rel_h box
     constexpr float kL2e = 1.4426950408889634f;
     const float c_l2 = 0.125f * kL2e;                    // hd^-0.5 * log2(e), hd = 64
 #pragma unroll 1
