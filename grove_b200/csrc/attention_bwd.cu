@@ -612,6 +612,8 @@ __global__ void rowdot_kernel(const bf16_t* __restrict__ a, const bf16_t* __rest
 // attention_bwd_tc.cu
 int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* aux, void* dqkv, int F,
                           int G, int heads, cudaStream_t st);
+int launch_attn_bwd_q_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* dq_out, float* A_out, int F,
+                         int G, int heads, cudaStream_t st);
 
 template <int S, int HD, bool WIN>
 static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t* Rh, const bf16_t* Rw, const bf16_t* O, const bf16_t* dO, bf16_t* dqkv,
@@ -644,7 +646,16 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
   bool fast_q = false;
   if constexpr (GFAST) {
     if (lse_fwd != nullptr) {      // the forward kernel's log-sum-exp: one key sweep instead of two
-      attn_bwd_q_global_kernel<S, HD><<<dim3(NT, heads, F), 128, smem_qf, st>>>(qkv, dO, rel, Dsum, lse_fwd, dqc, A, heads);
+      bool q_done = false;
+      if constexpr (HD == 64 && (S == 64 || S == 32)) {       // tcgen05 / TMEM query side (attention_bwd_tc.cu)
+        static const bool use_mma_sync = []() { const char* e = getenv("GROVE_BWD_MMA_SYNC"); return e && e[0] == '1'; }();
+        if (!use_mma_sync) {
+          const int rc = launch_attn_bwd_q_tc(qkv, dO, rel, lse_fwd, Dsum, dqc, A, F, G, heads, st);
+          if (rc) return rc;
+          q_done = true;
+        }
+      }
+      if (!q_done) attn_bwd_q_global_kernel<S, HD><<<dim3(NT, heads, F), 128, smem_qf, st>>>(qkv, dO, rel, Dsum, lse_fwd, dqc, A, heads);
       lse = const_cast<float*>(lse_fwd);
       fast_q = true;
     }

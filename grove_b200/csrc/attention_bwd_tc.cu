@@ -221,6 +221,207 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// =====================================================================================================================
+// Query side of the global attention backward on tcgen05: one CTA owns 128 queries of one (frame, head) and sweeps the keys in blocks of 128
+//   MMA1   S = Q_own K_j^T,  dP = dO_own V_j^T               (SS-mode UMMA 128x128x64)
+//   warps  ds = exp2(c S + (rel_w + rel_h) log2e - lse) (dP - D)   -> bf16 dS into tensor memory; the rel-pos bias cotangents
+//          A_w[q, kw] += sum_kh ds (registers), A_h[q, kh] = sum_kw ds (one value per thread and chunk, combined through shared memory)
+//   MMA2   dQ += dS K_j                                       (TS-mode UMMA 128x64x128, K_j read MN-major)
+// Outputs in the layout of attn_bwd_q_global_kernel: dq_core = scale dS K (fp32 [M, D]) and A (fp32 [M, heads, 2G]); relpos_kernel<..,1>
+// turns them into d q.  Two threads per query row: thread hs owns the key chunks {hs, hs+2} of every block, i.e. always the same 32 key
+// columns kw (rel_w and A_w live in registers like in the forward kernel).
+// =====================================================================================================================
+template <int G>
+struct BwdQCfg {
+  static constexpr int TS = 16384;
+  static constexpr int kRelH = G * 128 * 4;               // rel_h [G][128] fp32
+  static constexpr int kAh = 2 * G * 128 * 4;             // A_h partial sums [2][G][128] fp32
+  static constexpr int kSmem = 2 * TS + 4 * TS + kRelH + kAh + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int G>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restrict__ rel, const float* __restrict__ lse, const float* __restrict__ dsum,
+                     float* __restrict__ dq_out, float* __restrict__ A_out, int heads) {
+  using C = BwdQCfg<G>;
+  constexpr int HD = 64, TS = C::TS, N = G * G, NB = N / 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = s0, sDO = s0 + TS;
+  auto sStage = [&](int s) { return s0 + 2 * TS + (uint32_t)s * (2 * TS); };     // K_j | V_j
+  const uint32_t sRelH = s0 + 6 * TS, sAh = sRelH + C::kRelH, bar0 = sAh + C::kAh;
+  uint8_t* smem_al = smem_raw + (s0 - smem_u32(smem_raw));
+  float* relh_s = reinterpret_cast<float*>(smem_al + (sRelH - s0));       // [G][128], x log2 e
+  float* ah_s = reinterpret_cast<float*>(smem_al + (sAh - s0));           // [2][G][128]
+  float* xch_s = reinterpret_cast<float*>(smem_al + 2 * TS);              // epilogue scratch over the K/V stages: [2][32][128]
+  enum { OWN_FULL = 0, STAGE_FULL, STAGE_EMPTY = STAGE_FULL + 2, SD_FULL = STAGE_EMPTY + 2, SD_EMPTY, PD_FULL, PD_EMPTY, ACC_FULL, NUM_BARS };
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  const uint32_t tmem_slot = bar0 + 8u * NUM_BARS;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ib = blockIdx.x, h = blockIdx.y, f = blockIdx.z;
+  const int D = heads * HD;
+  const int tok0 = f * N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.qkv);
+    mbar_init(bar(OWN_FULL), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(STAGE_FULL + i), 1); mbar_init(bar(STAGE_EMPTY + i), 1); }
+    mbar_init(bar(SD_FULL), 1); mbar_init(bar(SD_EMPTY), 8); mbar_init(bar(PD_FULL), 8); mbar_init(bar(PD_EMPTY), 1); mbar_init(bar(ACC_FULL), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDS = tmem_base + 256, tDQ = tmem_base + 320;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(bar(OWN_FULL), 2 * TS);
+      tma_load_2d(sQ, &tm.qkv, bar(OWN_FULL), h * HD, tok0 + ib * 128);
+      tma_load_2d(sDO, &tm.dO, bar(OWN_FULL), h * HD, tok0 + ib * 128);
+      for (int j = 0; j < NB; ++j) {
+        const int s = j & 1;
+        mbar_wait(bar(STAGE_EMPTY + s), ((j >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(bar(STAGE_FULL + s), 2 * TS);
+        tma_load_2d(sStage(s), &tm.qkv, bar(STAGE_FULL + s), D + h * HD, tok0 + j * 128);           // K_j
+        tma_load_2d(sStage(s) + TS, &tm.qkv, bar(STAGE_FULL + s), 2 * D + h * HD, tok0 + j * 128);  // V_j
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= K_j) read MN-major
+    auto mma2 = [&](int j) {           // dQ += dS K_j
+      const uint32_t st = sStage(j & 1);
+      mbar_wait(bar(PD_FULL), j & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) tc_mma_f16_ts(tDQ, tDS + kk * 8, umma_desc_sw128(st + kk * 2048), idesc_o, (j | kk) != 0);
+        tc_commit(bar(PD_EMPTY));
+        tc_commit(bar(STAGE_EMPTY + (j & 1)));
+        if (j == NB - 1) tc_commit(bar(ACC_FULL));
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar(OWN_FULL), 0);
+#pragma unroll 1
+    for (int j = 0; j < NB; ++j) {
+      const int s = j & 1;
+      const uint32_t st = sStage(s);
+      mbar_wait(bar(STAGE_FULL + s), (j >> 1) & 1u);
+      if (j > 0) mbar_wait(bar(SD_EMPTY), (j - 1) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tS, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(st + k * 32), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, umma_desc_sw128(sDO + k * 32), umma_desc_sw128(st + TS + k * 32), idesc_s, k != 0);
+        tc_commit(bar(SD_FULL));
+      }
+      __syncwarp();
+      if (j > 0) mma2(j - 1);
+    }
+    mma2(NB - 1);
+  } else {
+    // ===================== elementwise warps: two threads per query row =====================
+    const int quad = warp & 3;
+    const int hs = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+    constexpr float kL2e = 1.4426950408889634f;
+    const float c_l2 = 0.125f * kL2e;
+    const int kw_base = ((hs & 1) * 32) % G;             // the 32 key columns this thread sees in every chunk
+    const size_t rh = ((size_t)tok0 + ib * 128 + row) * heads + h;       // (token, head) row of rel / lse / D / A
+    const float* relrow = rel + rh * (2 * G);
+    float relw[32], aw[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(relrow + G + kw_base + j);
+      relw[j] = v.x * kL2e; relw[j + 1] = v.y * kL2e; relw[j + 2] = v.z * kL2e; relw[j + 3] = v.w * kL2e;
+      aw[j] = aw[j + 1] = aw[j + 2] = aw[j + 3] = 0.f;
+    }
+    for (int kh = hs * (G / 2); kh < (hs + 1) * (G / 2); ++kh) relh_s[kh * 128 + row] = relrow[kh] * kL2e;
+    for (int kh = 0; kh < G; ++kh) ah_s[(hs * G + kh) * 128 + row] = 0.f;
+    const float my_lse = lse[rh], my_d = dsum[rh];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll 1
+    for (int j = 0; j < NB; ++j) {
+      mbar_wait(bar(SD_FULL), j & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * cc + hs;
+        const int kh = (j * 128 + c * 32) / G;
+        uint32_t rs[32], rd[32];
+        tmem_ld_x32(tS + c * 32 + tlane, rs);
+        tmem_ld_x32(tDP + c * 32 + tlane, rd);
+        tmem_ld_wait();
+        if (cc == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(SD_EMPTY));
+        }
+        const float off = relh_s[kh * 128 + row] - my_lse;
+        float asum = 0.f;
+        uint32_t pd[16];
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 2) {
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(rs[jj]), c_l2, relw[jj]) + off));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(rs[jj + 1]), c_l2, relw[jj + 1]) + off));
+          const float d0 = p0 * (__uint_as_float(rd[jj]) - my_d), d1 = p1 * (__uint_as_float(rd[jj + 1]) - my_d);
+          aw[jj] += d0; aw[jj + 1] += d1;
+          asum += d0 + d1;
+          pd[jj >> 1] = pack_bf16(d0, d1);
+        }
+        ah_s[(hs * G + kh) * 128 + row] += asum;         // G = 64: the only contribution of this thread to (row, kh); G = 32: likewise
+        if (cc == 0 && j > 0) { mbar_wait(bar(PD_EMPTY), (j - 1) & 1u); tc_fence_after(); }
+        tmem_st_x16(tDS + c * 16 + tlane, pd);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PD_FULL));
+    }
+    // ---- epilogue
+    mbar_wait(bar(ACC_FULL), 0);                         // every MMA has retired: the K/V stages can serve as scratch
+    tc_fence_after();
+    {
+      uint32_t r[32];
+      tmem_ld_x32(tDQ + hs * 32 + tlane, r);
+      tmem_ld_wait();
+      float* o = dq_out + ((size_t)tok0 + ib * 128 + row) * D + h * HD + hs * 32;
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 4)
+        *reinterpret_cast<float4*>(o + jj) = make_float4(__uint_as_float(r[jj]) * 0.125f, __uint_as_float(r[jj + 1]) * 0.125f,
+                                                         __uint_as_float(r[jj + 2]) * 0.125f, __uint_as_float(r[jj + 3]) * 0.125f);
+    }
+    float* arow = A_out + rh * (2 * G);
+    if (G == 64) {                                       // the two threads of a row own disjoint halves of the key columns
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 4) *reinterpret_cast<float4*>(arow + G + kw_base + jj) = make_float4(aw[jj], aw[jj + 1], aw[jj + 2], aw[jj + 3]);
+    } else {                                             // G = 32: both threads saw all 32 columns (different key rows): sum the two
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) xch_s[(hs * 32 + jj) * 128 + row] = aw[jj];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // A_h partials (and the G = 32 exchange) are complete
+    if (G != 64) {
+      for (int jj = hs * 16; jj < hs * 16 + 16; ++jj) arow[G + jj] = xch_s[jj * 128 + row] + xch_s[(32 + jj) * 128 + row];
+    }
+    for (int kh = hs * (G / 2); kh < (hs + 1) * (G / 2); ++kh) arow[kh] = ah_s[kh * 128 + row] + ah_s[(G + kh) * 128 + row];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // aux[i] = (lse[i], D[i], 0, 0) for i over (token, head)
 __global__ void pack_lse_dsum_kernel(const float* __restrict__ lse, const float* __restrict__ dsum, float4* __restrict__ aux, long long n) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -279,6 +480,34 @@ int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, con
     e = cudaFuncSetAttribute(attn_bwd_kv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
     attn_bwd_kv_tc_kernel<32><<<dim3(N / 128, heads, F), kBwdThreads, smem, st>>>(tm, (__nv_bfloat16*)dqkv, heads);
+  }
+  grove_count_launch();
+  GROVE_CHECK_LAUNCH();
+  return GROVE_OK;
+}
+
+// query side (see attn_bwd_q_tc_kernel); same preconditions as launch_attn_bwd_kv_tc
+int launch_attn_bwd_q_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* dq_out, float* A_out, int F,
+                         int G, int heads, cudaStream_t st) {
+  const int N = G * G, D = heads * 64;
+  const long long M = (long long)F * N;
+  BwdKvTmaps tm;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tm.qkv, qkv, (uint64_t)3 * D, (uint64_t)M, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm.dO, dO, (uint64_t)D, (uint64_t)M, 64, 128))) return rc;
+  tm.relw = tm.qkv; tm.relh = tm.qkv; tm.aux = tm.qkv;      // unused by this kernel
+  cudaError_t e;
+  if (G == 64) {
+    constexpr int smem = BwdQCfg<64>::kSmem;
+    static_assert(smem <= 232448, "shared memory budget");
+    e = cudaFuncSetAttribute(attn_bwd_q_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
+    attn_bwd_q_tc_kernel<64><<<dim3(N / 128, heads, F), kBwdThreads, smem, st>>>(tm, rel, lse, dsum, dq_out, A_out, heads);
+  } else {
+    constexpr int smem = BwdQCfg<32>::kSmem;
+    e = cudaFuncSetAttribute(attn_bwd_q_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
+    attn_bwd_q_tc_kernel<32><<<dim3(N / 128, heads, F), kBwdThreads, smem, st>>>(tm, rel, lse, dsum, dq_out, A_out, heads);
   }
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
