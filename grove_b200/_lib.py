@@ -49,6 +49,7 @@ SIGNATURES = {
     "grove_layernorm": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "grove_layernorm_bf16in": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "grove_attn_window_relpos_tc_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "grove_attn_window_relpos_tc_fwd_lse": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_attn_global_relpos_fwd_lse": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "grove_cast_f32_bf16": [_P, _P, _LL, _P],

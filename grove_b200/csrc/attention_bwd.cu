@@ -93,8 +93,8 @@ __device__ __forceinline__ void mma_p_y(float (&out)[HD / 8][4], const float (&p
 template <int S, int HD, bool WIN>
 __global__ void __launch_bounds__(128, 1)
 attn_bwd_q_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qkv_bias, const bf16_t* __restrict__ dO, const float* __restrict__ rel,
-                  const float* __restrict__ Dsum, float* __restrict__ lse_out, float* __restrict__ dq_out, float* __restrict__ A_out, int G,
-                  int heads) {
+                  const float* __restrict__ Dsum, const float* __restrict__ lse_in, float* __restrict__ lse_out, float* __restrict__ dq_out,
+                  float* __restrict__ A_out, int G, int heads) {
   constexpr int NT = (S * S + 63) / 64, KS = HD / 16, NTD = HD / 8, TILEB = 64 * HD * 2, RS = RelStride<S>::v;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = ((smem_u32(smem_raw) + 127u) & ~127u) - smem_u32(smem_raw);
@@ -166,7 +166,12 @@ attn_bwd_q_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qkv
       }
   };
 
-  // ---- sweep 1: log-sum-exp per query row
+  // ---- sweep 1: log-sum-exp per query row (skipped when the forward kernel saved it: lse_in)
+  float lse2[2];
+  if (lse_in != nullptr) {
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs) lse2[rs] = tokr[rs] >= 0 ? lse_in[((size_t)f * N + tokr[rs]) * heads + h] : INFINITY;
+  } else {
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   load_tile64<HD>(sK, kptr(0, 1), tid);
   cp_async_commit();
@@ -197,13 +202,13 @@ attn_bwd_q_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qkv
       for (int e = 0; e < 4; ++e) l_run[e >> 1] += exp2f(s[j][e] - m_run[e >> 1]);
     __syncthreads();
   }
-  float lse2[2];
 #pragma unroll
   for (int rs = 0; rs < 2; ++rs) {
     l_run[rs] += __shfl_xor_sync(0xffffffffu, l_run[rs], 1);
     l_run[rs] += __shfl_xor_sync(0xffffffffu, l_run[rs], 2);
     lse2[rs] = tokr[rs] >= 0 ? m_run[rs] + log2f(l_run[rs]) : INFINITY;
     if (t4 == 0 && tokr[rs] >= 0) lse_out[((size_t)f * N + tokr[rs]) * heads + h] = lse2[rs];
+  }
   }
 
   // ---- sweep 2: dS, dq_core, A
@@ -660,7 +665,11 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
       fast_q = true;
     }
   }
-  if (!fast_q) attn_bwd_q_kernel<S, HD, WIN><<<grid, 128, smem_q, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqc, A, G, heads);
+  if (!fast_q) {
+    // windows (and the small global grids): two key sweeps, or one when the forward kernel saved the row log-sum-exp
+    attn_bwd_q_kernel<S, HD, WIN><<<grid, 128, smem_q, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse_fwd, lse, dqc, A, G, heads);
+    if (lse_fwd != nullptr) lse = const_cast<float*>(lse_fwd);
+  }
   bool kv_done = false;
   if constexpr (GFAST && HD == 64 && (S == 64 || S == 32)) {
     // key side on tcgen05 / TMEM (attention_bwd_tc.cu); GROVE_BWD_MMA_SYNC=1 keeps the warp-level kernel (A/B measurements, cross-check)

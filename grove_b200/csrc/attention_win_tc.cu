@@ -33,6 +33,7 @@ struct WinTmaps { CUtensorMap qkv, qkv_x, tab, tab_x; };
 struct WinParams {
   const __nv_bfloat16* qkv_bias;   // [3*D] bf16
   __nv_bfloat16* out;              // [F,G,G,D]
+  float* lse;                      // optional [F*G*G, heads]: log2-domain log-sum-exp of every real query row (training forward)
   int G, heads, nW, units;
 };
 
@@ -50,7 +51,7 @@ struct WinCfg {
 // one query tile of the unit: bias + max + exp for this thread's keys, P -> tensor memory.  HS = 0: keys [0,112), 1: keys [112,196)
 template <int HS>
 __device__ __forceinline__ float win_softmax_tile(uint32_t tS, uint32_t tlane, const float (&relh)[8], const float (&relw)[14], float c_scale,
-                                                  float* xch_max, int row) {
+                                                  float* xch_max, int row, float& row_max) {
   constexpr int NK = HS == 0 ? 112 : 84;
   uint32_t s[112];
   if (HS == 0) {
@@ -75,6 +76,7 @@ __device__ __forceinline__ float win_softmax_tile(uint32_t tS, uint32_t tlane, c
   xch_max[HS * 128 + row] = mx;
   asm volatile("bar.sync 1, 256;" ::: "memory");   // also orders: both threads of the row have read S before P overwrites it
   mx = fmaxf(mx, xch_max[(HS ^ 1) * 128 + row]);
+  row_max = mx;
   float lsum = 0.f;
   uint32_t pk[56];
 #pragma unroll
@@ -302,7 +304,7 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++cnt) {
       int h, wy, wx, f;
       decode(u, h, wy, wx, f);
-      float lsum[2];
+      float lsum[2], rmax[2];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int q = min(t * 128 + row, kWQ - 1);          // rows >= 196 compute on a clamped position and are never stored
@@ -340,7 +342,8 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
         WPROBE(1000 + (warp - 2) * 256 + 32 * (cnt & 7) + 8 * t + 3);
         tc_fence_after();
         const uint32_t tS = tS0 + t * kWK;
-        lsum[t] = hs == 0 ? win_softmax_tile<0>(tS, tlane, relh, relw, c_scale, xch_f, row) : win_softmax_tile<1>(tS, tlane, relh, relw, c_scale, xch_f, row);
+        lsum[t] = hs == 0 ? win_softmax_tile<0>(tS, tlane, relh, relw, c_scale, xch_f, row, rmax[t])
+                          : win_softmax_tile<1>(tS, tlane, relh, relw, c_scale, xch_f, row, rmax[t]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(P_FULL + t));
@@ -361,9 +364,12 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(O_READ));
-        const float inv = 1.f / (lsum[t] + xch_f[256 + (t * 2 + (hs ^ 1)) * 128 + row]);
+        const float ltot = lsum[t] + xch_f[256 + (t * 2 + (hs ^ 1)) * 128 + row];
+        const float inv = 1.f / ltot;
         const int q = t * 128 + row;
         const int gy = wy * kWS + q / kWS, gx = wx * kWS + q % kWS;
+        if (p.lse != nullptr && hs == 0 && q < kWQ && gy < p.G && gx < p.G)
+          p.lse[((size_t)(f * p.G + gy) * p.G + gx) * p.heads + h] = rmax[t] + log2f(ltot);
         if (q < kWQ && gy < p.G && gx < p.G) {
           __nv_bfloat16* orow = p.out + ((size_t)(f * p.G + gy) * p.G + gx) * D + h * HD;
 #pragma unroll
@@ -400,7 +406,7 @@ extern "C" int grove_win_probe_read(long long* host, int n) {
 #endif
 
 template <int HD>
-static int launch_window_tc(const void* qkv, const void* qkv_bias, const void* tab, void* out, int F, int G, int heads, cudaStream_t stream) {
+static int launch_window_tc(const void* qkv, const void* qkv_bias, const void* tab, void* out, float* lse, int F, int G, int heads, cudaStream_t stream) {
   using Cfg = WinCfg<HD>;
   const int D = heads * HD;
   WinTmaps tm;
@@ -419,6 +425,7 @@ static int launch_window_tc(const void* qkv, const void* qkv_bias, const void* t
   WinParams p;
   p.qkv_bias = reinterpret_cast<const __nv_bfloat16*>(qkv_bias);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
   p.G = G; p.heads = heads; p.nW = (G + kWS - 1) / kWS;
   p.units = F * p.nW * p.nW * heads;
   cudaError_t e = cudaFuncSetAttribute(attn_window_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
@@ -433,14 +440,22 @@ static int launch_window_tc(const void* qkv, const void* qkv_bias, const void* t
   return GROVE_OK;
 }
 
+extern "C" int grove_attn_window_relpos_tc_fwd_lse(const void* qkv, const void* qkv_bias_bf16, const void* rel_table, void* out, float* lse, int F, int G,
+                                                   int heads, int hd, int ws, cudaStream_t stream);
+
 extern "C" int grove_attn_window_relpos_tc_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_table, void* out, int F, int G, int heads,
                                                int hd, int ws, cudaStream_t stream) {
+  return grove_attn_window_relpos_tc_fwd_lse(qkv, qkv_bias_bf16, rel_table, out, nullptr, F, G, heads, hd, ws, stream);
+}
+
+extern "C" int grove_attn_window_relpos_tc_fwd_lse(const void* qkv, const void* qkv_bias_bf16, const void* rel_table, void* out, float* lse, int F, int G,
+                                                   int heads, int hd, int ws, cudaStream_t stream) {
   GROVE_CHECK_ARG(qkv && qkv_bias_bf16 && rel_table && out && F > 0 && G > 0 && heads > 0);
   if ((hd != 64 && hd != 80) || ws != kWS) {
     grove_set_error("grove_attn_window_relpos_tc_fwd: head dim 64 / 80 and window 14 are built (got hd=%d ws=%d)", hd, ws);
     return GROVE_ERR_UNSUPPORTED;
   }
   GROVE_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)rel_table & 15) == 0 && ((uintptr_t)qkv_bias_bf16 & 15) == 0 && ((uintptr_t)out & 15) == 0);
-  return hd == 64 ? launch_window_tc<64>(qkv, qkv_bias_bf16, rel_table, out, F, G, heads, stream)
-                  : launch_window_tc<80>(qkv, qkv_bias_bf16, rel_table, out, F, G, heads, stream);
+  return hd == 64 ? launch_window_tc<64>(qkv, qkv_bias_bf16, rel_table, out, lse, F, G, heads, stream)
+                  : launch_window_tc<80>(qkv, qkv_bias_bf16, rel_table, out, lse, F, G, heads, stream);
 }

@@ -73,7 +73,8 @@ def encode_train(enc, x: torch.Tensor):
             bqb = enc._pack.get(k + ".qkvb16", [blk.attn.qkv.bias], bf16)
             tab = enc._pack.get(k + ".reltab", [blk.attn.rel_pos_h, blk.attn.rel_pos_w],
                                 lambda a, b, S=S: ops.window_rel_table(_resize_rel_pos(a, S), _resize_rel_pos(b, S)))
-            ops.attn_window_tc(qkv, bqb, tab, att, F=Fr, G=G, heads=heads, hd=hd, ws=blk.window_size)
+            lse = torch.empty(M, heads, device=dev, dtype=torch.float32) if keep else None   # row log-sum-exp, reused by the backward pass
+            ops.attn_window_tc(qkv, bqb, tab, att, F=Fr, G=G, heads=heads, hd=hd, ws=blk.window_size, lse=lse)
         else:
             rh = enc._pack.get(k + ".rh", [blk.attn.rel_pos_h], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
             rw = enc._pack.get(k + ".rw", [blk.attn.rel_pos_w], lambda t, S=S: bf16(_resize_rel_pos(t, S)))
@@ -93,7 +94,7 @@ def encode_train(enc, x: torch.Tensor):
         x2 = torch.empty(M, D, device=dev, dtype=torch.float32) if keep else x1
         ops.gemm(hid, w2, x2, bias=bb2, resid=x1, out2=xb if (conv or i == last) else None)
         if keep:
-            tape["blocks"][i] = {"x0": xs, "x1": x1, "qkv": qkv, "att": att, "pre": pre, "lse": lse if blk.window_size == 0 else None}
+            tape["blocks"][i] = {"x0": xs, "x1": x1, "qkv": qkv, "att": att, "pre": pre, "lse": lse}
         xs = x2
         if conv:
             kk = gi.index(i)

@@ -157,10 +157,15 @@ def window_rel_table(rel_h, rel_w):
     return t
 
 
-def attn_window_tc(qkv, qkv_bias_bf16, rel_table, out, *, F, G, heads, hd, ws=14):
+def attn_window_tc(qkv, qkv_bias_bf16, rel_table, out, *, F, G, heads, hd, ws=14, lse=None):
     for t, n in ((qkv, "qkv"), (qkv_bias_bf16, "qkv_bias"), (rel_table, "rel_table"), (out, "out")):
         _req(t, BF16, n)
     assert qkv.numel() == F * G * G * 3 * heads * hd and rel_table.shape == (64, hd)
+    if lse is not None:
+        assert lse.numel() == F * G * G * heads
+        check(lib().grove_attn_window_relpos_tc_fwd_lse(_p(qkv), _p(qkv_bias_bf16), _p(rel_table), _p(out), _p(_req(lse, F32, "lse")), F, G, heads, hd,
+                                                        ws, _stream(qkv)), "grove_attn_window_relpos_tc_fwd_lse")
+        return out
     check(lib().grove_attn_window_relpos_tc_fwd(_p(qkv), _p(qkv_bias_bf16), _p(rel_table), _p(out), F, G, heads, hd, ws, _stream(qkv)),
           "grove_attn_window_relpos_tc_fwd")
     return out

@@ -106,6 +106,10 @@ int grove_layernorm(const float* x, const float* gamma, const float* beta, void*
  * zero.  out[F,G,G,heads*hd] bf16.  Replaces Attention.forward :301-326 + add_decomposed_rel_pos :420-458 on windowed blocks. */
 int grove_attn_window_relpos_tc_fwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_table, void* out, int F, int G, int heads,
                                     int hd, int ws, grove_stream_t stream);
+/* Same, additionally writing lse[F*G*G, heads] fp32 = log2-domain log-sum-exp of every real query row (scale, bias and the pad keys of
+ * its window included) -- saved by the training forward so that grove_attn_relpos_bwd_lse can skip its own log-sum-exp sweep. */
+int grove_attn_window_relpos_tc_fwd_lse(const void* qkv, const void* qkv_bias_bf16, const void* rel_table, void* out, float* lse, int F, int G,
+                                        int heads, int hd, int ws, grove_stream_t stream);
 /* Global attention over one frame's G*G tokens with decomposed rel-pos bias (tables [2G-1, hd] bf16): tcgen05/TMEM/TMA
  * kernel (attention_tc.cu), single-pass softmax with a lazily raised running maximum, scores never leave the SM.  qkv [F,G,G,3,heads,hd], out [F,G,G,heads*hd]. */
 int grove_attn_global_relpos_fwd(const void* qkv, const void* rel_pos_h, const void* rel_pos_w, void* out, int F, int G,

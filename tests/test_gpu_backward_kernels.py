@@ -280,6 +280,23 @@ def test_attention_relpos_bwd(ops, G, ws, heads, hd, Fr):
             e = _relerr(dq2[..., i, :, :].float(), ref[..., i, :, :])
             assert e < 2.5e-2, ("fwd-lse path", name, e)
         assert float((dq2.float() - ref).abs().mean() / ref.abs().mean()) < 8e-3
+    if ws == 14:
+        # training path of the windowed blocks: the tcgen05 window forward saves the row log-sum-exp -> the query-side backward skips its
+        # own log-sum-exp sweep
+        lse = torch.full((Fr * G * G, heads), float("nan"), device="cuda")
+        att2 = torch.empty_like(att)
+        tab = ops.window_rel_table(Rh, Rw)
+        ops.attn_window_tc(qkv, bias, tab, att2, F=Fr, G=G, heads=heads, hd=hd, ws=14, lse=lse)
+        torch.cuda.synchronize()
+        assert torch.isfinite(lse).all()
+        dq2 = torch.full_like(qkv, float("nan"))
+        ops.attn_relpos_bwd(qkv, bias, Rh, Rw, att2, datt, dq2, F=Fr, G=G, heads=heads, hd=hd, ws=14, lse=lse)
+        torch.cuda.synchronize()
+        assert torch.isfinite(dq2.float()).all()
+        for i, name in enumerate("qkv"):
+            e = _relerr(dq2[..., i, :, :].float(), ref[..., i, :, :])
+            assert e < 2.5e-2, ("window fwd-lse path", name, e)
+        assert float((dq2.float() - ref).abs().mean() / ref.abs().mean()) < 8e-3
 
 
 # ------------------------------------------------------------------ loss derivative
