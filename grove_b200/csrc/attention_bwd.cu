@@ -126,6 +126,20 @@ attn_bwd_q_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qkv
     sRel[r * RS + c] = t >= 0 ? rel[(((size_t)f * N + t) * heads + h) * (2 * S) + c] * kL2e : 0.f;
     sA[r * RS + c] = 0.f;
   }
+  // S <= 16 (the 14x14 windows): the rel-pos bias cotangents A_h[i, jy] = sum_jx dS, A_w[i, jx] = sum_jy dS are one more tensor-core
+  // product per key tile, dS (16 x 64, already in bf16 A fragments for dq) times a ONE-HOT matrix E_kt [64 key columns][32]: column jy of
+  // the first 16 and column 16 + jx of the second 16 are 1 for key t = kt*64 + c (exact in bf16; the sums accumulate in fp32 fragments).
+  // It replaces a serial two-lanes-per-row loop over the staged dS tile that cost as much as the three real products together.
+  constexpr bool kHot = S <= 16;
+  const uint32_t sE = smem_u32(sDS);                     // kHot: the dS staging area holds the NT one-hot tiles (4 KB each) instead
+  if (kHot) {
+    __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(sDS);
+    for (int i = tid; i < NT * 64 * 32; i += 128) {
+      const int t = (i >> 11) * 64 + ((i >> 5) & 63), col = i & 31;
+      const bool one = t < S * S && (col < 16 ? t / S == col : t % S == col - 16);
+      e[i] = __float2bfloat16(one ? 1.f : 0.f);
+    }
+  }
   cp_async_wait<0>();
   __syncthreads();
 
@@ -212,9 +226,11 @@ attn_bwd_q_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qkv
   }
 
   // ---- sweep 2: dS, dq_core, A
-  float dq[NTD][4];
+  float dq[NTD][4], acc_a[4][4];
 #pragma unroll
   for (int j = 0; j < NTD; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc_a[j][0] = acc_a[j][1] = acc_a[j][2] = acc_a[j][3] = 0.f;
   load_tile64<HD>(sK, kptr(0, 1), tid);
   load_tile64<HD>(sV, kptr(0, 2), tid);
   cp_async_commit();
@@ -239,11 +255,12 @@ attn_bwd_q_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qkv
         const float p = exp2f(s[j][e] - lse2[rs]);   // 0 past the region (s = -inf) and for non-real rows (lse = +inf)
         const float ds = p * (dp[j][e] - drow[rs]);
         s[j][e] = ds;
-        sDS[row_l[rs] * 65 + 8 * j + 2 * t4 + (e & 1)] = ds;
+        if (!kHot) sDS[row_l[rs] * 65 + 8 * j + 2 * t4 + (e & 1)] = ds;
       }
     mma_p_y<HD>(dq, s, sK + buf * TILEB, lane);
+    if (kHot) mma_p_y<32>(acc_a, s, sE + kt * 4096, lane);
     __syncwarp();
-    {  // rel-pos cotangents: two lanes per row — lane&1 == 0 sums runs of equal jy, lane&1 == 1 scatters by jx
+    if (!kHot) {  // rel-pos cotangents: two lanes per row — lane&1 == 0 sums runs of equal jy, lane&1 == 1 scatters by jx
       const int r = r0 + (lane >> 1);
       const float* dsr = sDS + r * 65;
       float* ar = sA + r * RS;
@@ -273,9 +290,24 @@ attn_bwd_q_kernel(const bf16_t* __restrict__ qkv, const bf16_t* __restrict__ qkv
 #pragma unroll
       for (int j = 0; j < NTD; ++j) *reinterpret_cast<float2*>(o + 8 * j) = make_float2(dq[j][2 * rs] * scale, dq[j][2 * rs + 1] * scale);
     }
-  for (int i = tid; i < 64 * 2 * S; i += 128) {
-    const int r = i / (2 * S), c = i % (2 * S), t = sTok[r];
-    if (t >= 0) A_out[(((size_t)f * N + t) * heads + h) * (2 * S) + c] = sA[r * RS + c];
+  if (kHot) {
+#pragma unroll
+    for (int rs = 0; rs < 2; ++rs)
+      if (tokr[rs] >= 0) {
+        float* ab = A_out + (((size_t)f * N + tokr[rs]) * heads + h) * (2 * S);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int col = 8 * (nt & 1) + 2 * t4 + e2;       // jy (nt < 2) or jx (nt >= 2)
+            if (col < S) ab[(nt < 2 ? 0 : S) + col] = acc_a[nt][2 * rs + e2];
+          }
+      }
+  } else {
+    for (int i = tid; i < 64 * 2 * S; i += 128) {
+      const int r = i / (2 * S), c = i % (2 * S), t = sTok[r];
+      if (t >= 0) A_out[(((size_t)f * N + t) * heads + h) * (2 * S) + c] = sA[r * RS + c];
+    }
   }
 }
 
