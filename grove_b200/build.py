@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libgrove_b200.so")
 LIB_LEGACY = os.path.join(HERE, "libgrove_b200_legacy.so")
 LEGACY_SOURCES = ["lib.cu", "attention.cu"]
 SOURCES = ["lib.cu", "gemm_tcgen05.cu", "encoder_ops.cu", "attention_tc.cu", "attention_win_tc.cu", "decoder_ops.cu", "decoder_fused.cu", "box_ops.cu",
-           "backward_ops.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "decoder_bwd.cu", "preprocess.cu"]
+           "backward_ops.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "attention_win_bwd_tc.cu", "decoder_bwd.cu", "preprocess.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-I", os.path.join(ROOT, "include"), "-I", CSRC, "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("GROVE_NVCC_EXTRA", "").split()
