@@ -654,7 +654,7 @@ int launch_attn_bwd_q_tc(const void* qkv, const void* dO, const float* rel, cons
 
 // attention_win_bwd_tc.cu
 int launch_attn_window_bwd_tc(const void* qkv, const void* qkv_bias, const void* Rh, const void* Rw, const void* dO, const float* lse, const float* dsum,
-                              void* dqkv, int F, int G, int heads, cudaStream_t st);
+                              void* dqkv, int F, int G, int heads, int hd, cudaStream_t st);
 
 template <int S, int HD, bool WIN>
 static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t* Rh, const bf16_t* Rw, const bf16_t* O, const bf16_t* dO, bf16_t* dqkv,
@@ -680,13 +680,13 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
     cudaFuncSetAttribute(attn_bwd_kv_kernel<S, HD, WIN, GFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv);
     if constexpr (GFAST) cudaFuncSetAttribute(attn_bwd_q_global_kernel<S, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_qf);
   }
-  if constexpr (WIN && HD == 64 && S == 14) {
+  if constexpr (WIN && (HD == 64 || HD == 80) && S == 14) {
     // windows with the forward's log-sum-exp at hand: the whole layer in one persistent tcgen05 kernel (attention_win_bwd_tc.cu)
     static const bool use_mma_sync = []() { const char* e = getenv("GROVE_BWD_MMA_SYNC"); return e && e[0] == '1'; }();
     if (lse_fwd != nullptr && !use_mma_sync) {
       rowdot_kernel<<<(unsigned)((M * heads + 255) / 256), 256, 0, st>>>(dO, O, Dsum, M * heads, HD);
       grove_count_launch();
-      return launch_attn_window_bwd_tc(qkv, qkv_bias, Rh, Rw, dO, lse_fwd, Dsum, dqkv, F, G, heads, st);
+      return launch_attn_window_bwd_tc(qkv, qkv_bias, Rh, Rw, dO, lse_fwd, Dsum, dqkv, F, G, heads, HD, st);
     }
   }
   const dim3 grid_rel((unsigned)(M / 64), heads);

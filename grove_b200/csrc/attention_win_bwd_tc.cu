@@ -31,7 +31,7 @@ constexpr int kWbThreads = 352;
 constexpr int kBS = 14, kBQ = 196, kBK = 208;   // window side, tokens, tokens padded to 13 UMMA k-steps
 constexpr int kRelStride = 29;                  // shared table row: 14 rel_h (x log2 e, - lse) | 14 rel_w (x log2 e) | D
 
-struct WinBwdTmaps { CUtensorMap qkv, dO, rh, rw; };
+struct WinBwdTmaps { CUtensorMap qkv, dO, rh, rw, qkv_x, dO_x, rh_x, rw_x; };   // _x: the 16-wide tail of an 80-wide head (SWIZZLE_32B)
 
 struct WinBwdParams {
   const __nv_bfloat16* qkv_bias;   // [3*D] bf16
@@ -41,13 +41,18 @@ struct WinBwdParams {
   int G, heads, nW, units;
 };
 
+// One operand = 208 rows (196 real, 12 zero) x 64 bf16 with SWIZZLE_128B [+ 208 x 16 bf16 with SWIZZLE_32B for an 80-wide head].  As the A
+// operand of the second 128-row tile it is read 48 rows past its end: those rows only produce TMEM lanes >= 208, which nothing ever reads back.
+template <int HD>
 struct WinBwdCfg {
-  static constexpr int kTile = 256 * 128;                 // one operand: 256 rows (196 real) x 64 bf16, SWIZZLE_128B
-  static constexpr int kTab = 64 * 128, kDT = 128 * 128, kStage = 128 * 64 * 4;
+  static constexpr bool kX = HD > 64;
+  static constexpr int kMain = kBK * 128, kOp = kMain + (kX ? 7 * 1024 : 0);
+  static constexpr int kTabMain = 64 * 128, kTab = kTabMain + (kX ? 64 * 32 : 0);
+  static constexpr int kDT = 128 * 128, kStage = 128 * 64 * 4;
   static constexpr int kRel = (kBK * kRelStride * 4 + 1023) / 1024 * 1024;
-  static constexpr int kXch = 2 * 14 * 128 * 4;
-  static constexpr int kTx = 4 * kBQ * 128;               // bytes the four window boxes deliver
-  static constexpr int kSmem = 4 * kTile + kTab + kDT + kStage + kRel + kXch + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int kXch = 2 * 7 * 128 * 4;
+  static constexpr int kTx = 4 * (kBQ * 128 + (kX ? kBQ * 32 : 0));     // bytes the window boxes of Q, K, V, dO deliver
+  static constexpr int kSmem = 4 * kOp + kTab + kDT + kStage + kRel + kXch + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 template <int W>
@@ -68,8 +73,8 @@ __device__ __forceinline__ float wb_ex2(float x) {
 
 // query pass, one chunk of W key columns starting at key BASE; relh[i] belongs to key row KH0 + i.  scale*dS -> columns PCOL.. of the dP region
 template <int BASE, int W, int PCOL, int KH0>
-__device__ __forceinline__ void wb_q_chunk(uint32_t tS, uint32_t tDP, uint32_t tlane, const float (&relh)[8], const float (&relw)[14], float c_l2, float my_d,
-                                           float (&ah)[8], float (&aw)[14]) {
+__device__ __forceinline__ void wb_q_chunk(uint32_t tS, uint32_t tDP, uint32_t tlane, const float (&relh)[8], const float (&relw)[14], float c_l2, float scale,
+                                           float my_d, float (&ah)[8], float (&aw)[14]) {
   uint32_t rs[W], rd[W], pd[W / 2];
   wb_ld<W>(tS + BASE + tlane, rs);
   wb_ld<W>(tDP + BASE + tlane, rd);
@@ -90,7 +95,7 @@ __device__ __forceinline__ void wb_q_chunk(uint32_t tS, uint32_t tDP, uint32_t t
         ds[e] = 0.f;                                     // keys 196..207 do not exist
       }
     }
-    pd[j >> 1] = pack_bf16(ds[0] * 0.125f, ds[1] * 0.125f);
+    pd[j >> 1] = pack_bf16(ds[0] * scale, ds[1] * scale);
   }
   wb_st<W / 2>(tDP + PCOL + tlane, pd);
 }
@@ -130,13 +135,21 @@ __device__ __forceinline__ void wb_store32(__nv_bfloat16* o, const uint32_t (&r)
                    pack_bf16(__uint_as_float(r[j + 4]) * sc, __uint_as_float(r[j + 5]) * sc), pack_bf16(__uint_as_float(r[j + 6]) * sc, __uint_as_float(r[j + 7]) * sc));
 }
 
+__device__ __forceinline__ void wb_store8(__nv_bfloat16* o, const uint32_t (&r)[8], float sc) {
+  *reinterpret_cast<uint4*>(o) =
+      make_uint4(pack_bf16(__uint_as_float(r[0]) * sc, __uint_as_float(r[1]) * sc), pack_bf16(__uint_as_float(r[2]) * sc, __uint_as_float(r[3]) * sc),
+                 pack_bf16(__uint_as_float(r[4]) * sc, __uint_as_float(r[5]) * sc), pack_bf16(__uint_as_float(r[6]) * sc, __uint_as_float(r[7]) * sc));
+}
+
+template <int HD>
 __global__ void __launch_bounds__(kWbThreads, 1)
 attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdParams p) {
-  using C = WinBwdCfg;
-  constexpr int HD = 64;
+  using C = WinBwdCfg<HD>;
+  constexpr bool kX = C::kX;
+  constexpr float kScale = HD == 64 ? 0.125f : 0.11180339887498949f;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = s0, sK = sQ + C::kTile, sV = sK + C::kTile, sDO = sV + C::kTile, sTab = sDO + C::kTile, sDT = sTab + C::kTab;
+  const uint32_t sQ = s0, sK = sQ + C::kOp, sV = sK + C::kOp, sDO = sV + C::kOp, sTab = sDO + C::kOp, sDT = sTab + C::kTab;
   const uint32_t sStage = sDT + C::kDT, sRel = sStage + C::kStage, sXch = sRel + C::kRel, bar0 = sXch + C::kXch;
   uint8_t* smem_al = smem_raw + (s0 - smem_u32(smem_raw));
   float* stage_f = reinterpret_cast<float*>(smem_al + (sStage - s0));
@@ -181,9 +194,13 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(bar(TAB_FULL), 2 * 32 * 128);
+      mbar_expect_tx(bar(TAB_FULL), 2 * 32 * 128 + (kX ? 2 * 32 * 32 : 0));
       tma_load_2d(sTab, &tm.rh, bar(TAB_FULL), 0, 0);              // rows 0..26 = Rh, 27..31 zero-filled (out of bounds)
       tma_load_2d(sTab + 32 * 128, &tm.rw, bar(TAB_FULL), 0, 0);   // rows 32..58 = Rw
+      if (kX) {
+        tma_load_2d(sTab + C::kTabMain, &tm.rh_x, bar(TAB_FULL), 64, 0);
+        tma_load_2d(sTab + C::kTabMain + 32 * 32, &tm.rw_x, bar(TAB_FULL), 64, 0);
+      }
     }
     __syncwarp();
     uint32_t cnt = 0;
@@ -197,6 +214,12 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
         tma_load_4d_cta(sDO, &tm.dO, bar(LOAD_FULL), h * HD, wx * kBS, wy * kBS, f);
         tma_load_4d_cta(sK, &tm.qkv, bar(LOAD_FULL), D + h * HD, wx * kBS, wy * kBS, f);
         tma_load_4d_cta(sV, &tm.qkv, bar(LOAD_FULL), 2 * D + h * HD, wx * kBS, wy * kBS, f);
+        if (kX) {
+          tma_load_4d_cta(sQ + C::kMain, &tm.qkv_x, bar(LOAD_FULL), h * HD + 64, wx * kBS, wy * kBS, f);
+          tma_load_4d_cta(sDO + C::kMain, &tm.dO_x, bar(LOAD_FULL), h * HD + 64, wx * kBS, wy * kBS, f);
+          tma_load_4d_cta(sK + C::kMain, &tm.qkv_x, bar(LOAD_FULL), D + h * HD + 64, wx * kBS, wy * kBS, f);
+          tma_load_4d_cta(sV + C::kMain, &tm.qkv_x, bar(LOAD_FULL), 2 * D + h * HD + 64, wx * kBS, wy * kBS, f);
+        }
       }
       __syncwarp();
     }
@@ -204,14 +227,20 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64), idesc_s = umma_idesc_bf16(128, kBK);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);        // B read MN-major ([k][d] tile, d contiguous)
-    auto ss = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc) {        // D = A B^T over the 64-wide head dim, both K-major
+    constexpr uint32_t idesc_ox = umma_idesc_bf16(128, 16) | (1u << 16);
+    // D = A_tile B^T over the head dim, both K-major; a / b are operand bases, `t` picks the 128-row tile of A
+    auto ss = [&](uint32_t d, uint32_t a, int t, uint32_t b, uint32_t b_tail, uint32_t idesc) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tc_mma_f16(d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, k != 0);
+      for (int k = 0; k < 4; ++k) tc_mma_f16(d, umma_desc_sw128(a + t * 16384 + k * 32), umma_desc_sw128(b + k * 32), idesc, k != 0);
+      if (kX) tc_mma_f16(d, umma_desc_sw32(a + C::kMain + t * 4096), umma_desc_sw32(b_tail), idesc, 1);
     };
-    auto ts = [&](uint32_t d, uint32_t a_region, uint32_t b) {                 // D = A[tmem, 128 x 208 packed] B[208 x 64]
+    auto ts = [&](uint32_t d, uint32_t a_region, uint32_t b) {                 // D = A[tmem, 128 x 208 packed] B[208 x HD]
 #pragma unroll
-      for (int kk = 0; kk < kBK / 16; ++kk)
-        tc_mma_f16_ts(d, a_region + (kk < 7 ? kk * 8 : 160 + (kk - 7) * 8), umma_desc_sw128(b + kk * 2048), idesc_o, kk != 0);
+      for (int kk = 0; kk < kBK / 16; ++kk) {
+        const uint32_t ta = a_region + (kk < 7 ? kk * 8 : 160 + (kk - 7) * 8);
+        tc_mma_f16_ts(d, ta, umma_desc_sw128(b + kk * 2048), idesc_o, kk != 0);
+        if (kX) tc_mma_f16_ts(d + 64, ta, umma_desc_sw32(b + C::kMain + kk * 512), idesc_ox, kk != 0);
+      }
     };
     mbar_wait(bar(TAB_FULL), 0);
     uint32_t cnt = 0;
@@ -219,18 +248,18 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
       mbar_wait2(bar(LOAD_FULL), cnt & 1u, bar(FIX_DONE), cnt & 1u);
 #pragma unroll 1
       for (int ps = 0; ps < 4; ++ps) {
-        const uint32_t t16 = (uint32_t)(ps & 1) * 16384u;
+        const int t = ps & 1;
         if (cnt > 0 || ps > 0) mbar_wait(bar(ACC_READ), (uint32_t)(ps + 3) & 1u);     // the previous pass' accumulators have been read
         tc_fence_after();
         if (elect_one()) {
           if (ps < 2) {
-            ss(tTO, sQ + t16, sTab, idesc_t);
+            ss(tTO, sQ, t, sTab, sTab + C::kTabMain, idesc_t);
             tc_commit(bar(T_FULL));
-            ss(tS, sQ + t16, sK, idesc_s);
-            ss(tDP, sDO + t16, sV, idesc_s);
+            ss(tS, sQ, t, sK, sK + C::kMain, idesc_s);
+            ss(tDP, sDO, t, sV, sV + C::kMain, idesc_s);
           } else {
-            ss(tS, sK + t16, sQ, idesc_s);
-            ss(tDP, sV + t16, sDO, idesc_s);
+            ss(tS, sK, t, sQ, sQ + C::kMain, idesc_s);
+            ss(tDP, sV, t, sDO, sDO + C::kMain, idesc_s);
           }
           tc_commit(bar(S_FULL));
         }
@@ -241,7 +270,10 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
           if (ps < 2) {
             ts(tTO, tDP, sK);                                                  // dQ = (scale dS) K
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_f16(tTO, umma_desc_sw128(sDT + k * 32), umma_desc_sw128(sTab + k * 2048), idesc_o, 1);   // + dT Tab
+            for (int k = 0; k < 4; ++k) {                                       // + dT Tab
+              tc_mma_f16(tTO, umma_desc_sw128(sDT + k * 32), umma_desc_sw128(sTab + k * 2048), idesc_o, 1);
+              if (kX) tc_mma_f16(tTO + 64, umma_desc_sw128(sDT + k * 32), umma_desc_sw32(sTab + C::kTabMain + k * 512), idesc_ox, 1);
+            }
           } else {
             ts(tTO, tS, sDO);                                                  // dV = P^T dO
             ts(tDK, tDP, sQ);                                                  // dK = dS^T Q
@@ -272,6 +304,14 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(bsrc + c * 8));
                 asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + r * 128 + ((c ^ (r & 7)) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
               }
+              if (kX) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  const uint4 v = __ldg(reinterpret_cast<const uint4*>(bsrc + 64 + c * 8));
+                  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + C::kMain + r * 32 + ((c ^ ((r >> 2) & 1)) << 4)), "r"(v.x), "r"(v.y),
+                               "r"(v.z), "r"(v.w) : "memory");
+                }
+              }
             }
           }
         }
@@ -288,7 +328,7 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
     const int et = (warp - 2) * 32 + lane;                    // 0..255
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
     constexpr float kL2e = 1.4426950408889634f;
-    const float c_l2 = 0.125f * kL2e;
+    const float c_l2 = kScale * kL2e;
     auto sync256 = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     auto stage_at = [&](int e) { return stage_f[row * 64 + ((((e >> 2) ^ (row & 7)) << 2) | (e & 3))]; };
     auto dt_put = [&](int col, float v) {                     // dT[row, col] (bf16, the SWIZZLE_128B K-major tile the UMMA reads)
@@ -346,29 +386,29 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
         mbar_wait(bar(S_FULL), (uint32_t)t);
         tc_fence_after();
         if (hs == 0) {
-          wb_q_chunk<0, 32, 0, 0>(tS, tDP, tlane, relh, relw, c_l2, my_d, ah, aw);
-          wb_q_chunk<32, 32, 16, 0>(tS, tDP, tlane, relh, relw, c_l2, my_d, ah, aw);
-          wb_q_chunk<64, 32, 32, 0>(tS, tDP, tlane, relh, relw, c_l2, my_d, ah, aw);
-          wb_q_chunk<96, 16, 48, 0>(tS, tDP, tlane, relh, relw, c_l2, my_d, ah, aw);
+          wb_q_chunk<0, 32, 0, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
+          wb_q_chunk<32, 32, 16, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
+          wb_q_chunk<64, 32, 32, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
+          wb_q_chunk<96, 16, 48, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
         } else {
-          wb_q_chunk<176, 32, 192, 8>(tS, tDP, tlane, relh, relw, c_l2, my_d, ah, aw);
-          wb_q_chunk<144, 32, 176, 8>(tS, tDP, tlane, relh, relw, c_l2, my_d, ah, aw);
-          wb_q_chunk<112, 32, 160, 8>(tS, tDP, tlane, relh, relw, c_l2, my_d, ah, aw);
+          wb_q_chunk<176, 32, 192, 8>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
+          wb_q_chunk<144, 32, 176, 8>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
+          wb_q_chunk<112, 32, 160, 8>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
         }
 #pragma unroll
-        for (int i = 0; i < 14; ++i) xch_f[(hs * 14 + i) * 128 + row] = aw[i];
+        for (int i = 0; i < 7; ++i) xch_f[(hs * 7 + i) * 128 + row] = aw[hs == 0 ? 7 + i : i];     // the partial sums the partner thread finishes
         sync256();
         // dT[q, qh + 13 - kh] = A_h[q, kh],  dT[q, 32 + qw + 13 - kw] = A_w[q, kw]: the cotangent of T = Q Tab^T
         if (hs == 0) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) dt_put(qh + (kBS - 1) - i, ah[i]);
 #pragma unroll
-          for (int i = 0; i < 7; ++i) dt_put(32 + qw + (kBS - 1) - i, aw[i] + xch_f[(14 + i) * 128 + row]);
+          for (int i = 0; i < 7; ++i) dt_put(32 + qw + (kBS - 1) - i, aw[i] + xch_f[(7 + i) * 128 + row]);
         } else {
 #pragma unroll
           for (int i = 0; i < 6; ++i) dt_put(qh + (kBS - 1) - (8 + i), ah[i]);
 #pragma unroll
-          for (int i = 7; i < 14; ++i) dt_put(32 + qw + (kBS - 1) - i, aw[i] + xch_f[i * 128 + row]);
+          for (int i = 7; i < 14; ++i) dt_put(32 + qw + (kBS - 1) - i, aw[i] + xch_f[(i - 7) * 128 + row]);
         }
         tmem_st_wait();
         fence_proxy_async();
@@ -378,13 +418,18 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
         // ---- dQ
         mbar_wait(bar(O_FULL), (uint32_t)t);
         tc_fence_after();
-        uint32_t r[32];
+        uint32_t r[32], rx[8];
         tmem_ld_x32(tTO + hs * 32 + tlane, r);
+        if (kX) tmem_ld_x8(tTO + 64 + hs * 8 + tlane, rx);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(ACC_READ));
-        if (valid) wb_store32(p.dqkv + tok * (3 * D) + h * HD + hs * 32, r, 1.0f);
+        if (valid) {
+          __nv_bfloat16* o = p.dqkv + tok * (3 * D) + h * HD;
+          wb_store32(o + hs * 32, r, 1.0f);
+          if (kX) wb_store8(o + 64 + hs * 8, rx, 1.0f);
+        }
       }
       sync256();                                              // the bias table of this unit is complete
       // ---------------- key passes ----------------
@@ -415,17 +460,19 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
         // ---- dV, dK
         mbar_wait(bar(O_FULL), (uint32_t)t);
         tc_fence_after();
-        uint32_t rv[32], rk[32];
+        uint32_t rv[32], rk[32], rvx[8], rkx[8];
         tmem_ld_x32(tTO + hs * 32 + tlane, rv);
         tmem_ld_x32(tDK + hs * 32 + tlane, rk);
+        if (kX) { tmem_ld_x8(tTO + 64 + hs * 8 + tlane, rvx); tmem_ld_x8(tDK + 64 + hs * 8 + tlane, rkx); }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(ACC_READ));
         if (valid) {
-          __nv_bfloat16* o = p.dqkv + tok * (3 * D) + h * HD + hs * 32;
-          wb_store32(o + D, rk, 0.125f);
-          wb_store32(o + 2 * D, rv, 1.0f);
+          __nv_bfloat16* o = p.dqkv + tok * (3 * D) + h * HD;
+          wb_store32(o + D + hs * 32, rk, kScale);
+          wb_store32(o + 2 * D + hs * 32, rv, 1.0f);
+          if (kX) { wb_store8(o + D + 64 + hs * 8, rkx, kScale); wb_store8(o + 2 * D + 64 + hs * 8, rvx, 1.0f); }
         }
       }
     }
@@ -438,12 +485,13 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
 int make_tmap_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner, uint32_t box_rows);
 int make_tmap_bf16_nd(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
 
-// called from run_attn_bwd (attention_bwd.cu) for windowed layers with head dim 64 when the forward saved its log-sum-exp.
-// Rh, Rw: bf16 [27, 64]; lse, dsum: fp32 [M, heads]; writes all three slots of dqkv [M, 3*D] for every token.
-int launch_attn_window_bwd_tc(const void* qkv, const void* qkv_bias, const void* Rh, const void* Rw, const void* dO, const float* lse, const float* dsum,
-                              void* dqkv, int F, int G, int heads, cudaStream_t st) {
-  using C = WinBwdCfg;
-  const int D = heads * 64;
+// called from run_attn_bwd (attention_bwd.cu) for windowed layers with head dim 64 / 80 when the forward saved its log-sum-exp.
+// Rh, Rw: bf16 [27, HD]; lse, dsum: fp32 [M, heads]; writes all three slots of dqkv [M, 3*D] for every token.
+template <int HD>
+static int launch_window_bwd(const void* qkv, const void* qkv_bias, const void* Rh, const void* Rw, const void* dO, const float* lse, const float* dsum,
+                             void* dqkv, int F, int G, int heads, cudaStream_t st) {
+  using C = WinBwdCfg<HD>;
+  const int D = heads * HD;
   WinBwdTmaps tm;
   int rc;
   uint64_t dims[4] = {(uint64_t)3 * D, (uint64_t)G, (uint64_t)G, (uint64_t)F};
@@ -451,8 +499,17 @@ int launch_attn_window_bwd_tc(const void* qkv, const void* qkv_bias, const void*
   uint32_t box[4] = {64, kBS, kBS, 1};
   if ((rc = make_tmap_bf16_nd(&tm.qkv, qkv, 4, dims, box))) return rc;
   if ((rc = make_tmap_bf16_nd(&tm.dO, dO, 4, dims_o, box))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tm.rh, Rh, 64, 2 * kBS - 1, 64, 32))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tm.rw, Rw, 64, 2 * kBS - 1, 64, 32))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm.rh, Rh, HD, 2 * kBS - 1, 64, 32))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm.rw, Rw, HD, 2 * kBS - 1, 64, 32))) return rc;
+  if (HD > 64) {
+    uint32_t boxx[4] = {16, kBS, kBS, 1};
+    if ((rc = make_tmap_bf16_nd(&tm.qkv_x, qkv, 4, dims, boxx))) return rc;
+    if ((rc = make_tmap_bf16_nd(&tm.dO_x, dO, 4, dims_o, boxx))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm.rh_x, Rh, HD, 2 * kBS - 1, 16, 32))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm.rw_x, Rw, HD, 2 * kBS - 1, 16, 32))) return rc;
+  } else {
+    tm.qkv_x = tm.qkv; tm.dO_x = tm.dO; tm.rh_x = tm.rh; tm.rw_x = tm.rw;
+  }
   WinBwdParams p;
   p.qkv_bias = reinterpret_cast<const __nv_bfloat16*>(qkv_bias);
   p.lse = lse; p.dsum = dsum;
@@ -460,16 +517,22 @@ int launch_attn_window_bwd_tc(const void* qkv, const void* qkv_bias, const void*
   p.G = G; p.heads = heads; p.nW = (G + kBS - 1) / kBS;
   p.units = F * p.nW * p.nW * heads;
   static_assert(C::kSmem <= 232448, "shared memory budget");
-  cudaError_t e = cudaFuncSetAttribute(attn_window_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+  cudaError_t e = cudaFuncSetAttribute(attn_window_bwd_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
   if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", C::kSmem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.units < sms ? p.units : sms;
-  attn_window_bwd_tc_kernel<<<grid, kWbThreads, C::kSmem, st>>>(tm, p);
+  attn_window_bwd_tc_kernel<HD><<<grid, kWbThreads, C::kSmem, st>>>(tm, p);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
+}
+
+int launch_attn_window_bwd_tc(const void* qkv, const void* qkv_bias, const void* Rh, const void* Rw, const void* dO, const float* lse, const float* dsum,
+                              void* dqkv, int F, int G, int heads, int hd, cudaStream_t st) {
+  return hd == 64 ? launch_window_bwd<64>(qkv, qkv_bias, Rh, Rw, dO, lse, dsum, dqkv, F, G, heads, st)
+                  : launch_window_bwd<80>(qkv, qkv_bias, Rh, Rw, dO, lse, dsum, dqkv, F, G, heads, st);
 }
 
 }  // namespace grove

@@ -247,7 +247,7 @@ def _ref_attention(qkv, bias, Rh, Rw, heads, hd, G, ws):
 
 
 @pytest.mark.parametrize("G,ws,heads,hd,Fr", [(16, 0, 2, 64, 2), (32, 0, 2, 80, 1), (32, 0, 3, 64, 2), (64, 0, 1, 64, 1), (64, 0, 2, 80, 1), (32, 14, 2, 64, 2),
-                                              (64, 14, 2, 80, 1), (16, 14, 3, 64, 1), (64, 14, 3, 64, 2)])
+                                              (64, 14, 2, 80, 1), (16, 14, 3, 64, 1), (64, 14, 3, 64, 2), (32, 14, 2, 80, 2)])
 def test_attention_relpos_bwd(ops, G, ws, heads, hd, Fr):
     S = ws if ws else G
     qkv = _rand((Fr, G, G, 3, heads, hd), 43, 0.8, dtype=torch.bfloat16)
