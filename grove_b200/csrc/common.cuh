@@ -122,6 +122,30 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   return __fdividef(1.0f, 1.0f + e) + x * 0.3989422804014327f * g;
 }
 
+// d/dx of gelu_fast on a pair (packed fp32): with s = sigmoid(u), u = x (a + b x^2 + c x^4), the derivative is s + x s (1 - s) u'(x) -- the
+// exact derivative of the function the forward epilogue applies, 2 MUFU (ex2, rcp) and ~8.5 issue slots per value.  The three-MUFU
+// gelu_grad_fast made the fc2 input-gradient GEMM epilogue MUFU-bound: 3 x 128 x 256 per tile at 16 / clk = the tile's whole MMA time.
+__device__ __forceinline__ float2 gelu_grad_fast2(float2 x) {
+  const float2 xx = __fmul2_rn(x, x);
+  const float2 x2 = make_float2(fminf(xx.x, 50.0f), fminf(xx.y, 50.0f));
+  float2 q = __ffma2_rn(x2, make_float2(0.0010142630f, 0.0010142630f), make_float2(-0.10677572f, -0.10677572f));
+  q = __ffma2_rn(q, x2, make_float2(-2.3011214f, -2.3011214f));
+  const float2 t = __fmul2_rn(q, x);                    // -log2(e) u
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
+  const float2 d = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+  float2 s;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s.y) : "f"(d.y));
+  // u'(x) = -ln 2 * (A + 3 B x^2 + 5 C x^4) with the log2-scaled coefficients above
+  float2 w = __ffma2_rn(x2, make_float2(-0.0035151677f, -0.0035151677f), make_float2(0.22203387f, 0.22203387f));
+  w = __ffma2_rn(w, x2, make_float2(1.5950158f, 1.5950158f));
+  const float2 wx = __fmul2_rn(w, x);
+  const float2 sm = __ffma2_rn(make_float2(-s.x, -s.y), s, s);      // s (1 - s)
+  return __ffma2_rn(wx, sm, s);
+}
+
 // One leader lane of a fully converged warp (elect.sync).  tcgen05.mma / tcgen05.commit / TMA are uniform-datapath instructions:
 // issued under `if (lane == 0)` ptxas wraps EVERY one of them in a serialising ELECT ... BRA.U.ANY loop with R2UR moves (~60-100 clk
 // per instruction, measured), which made the single MMA-issuing warp the bottleneck of the attention kernels; under an elect.sync

@@ -667,7 +667,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 z = unpack_bf16(pu[j]);
-                if (p.dact == 1) { v[2 * j] *= gelu_grad_fast(z.x); v[2 * j + 1] *= gelu_grad_fast(z.y); }
+                if (p.dact == 1) { const float2 g = gelu_grad_fast2(z); v[2 * j] *= g.x; v[2 * j + 1] *= g.y; }
                 else             { v[2 * j] = z.x > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = z.y > 0.f ? v[2 * j + 1] : 0.f; }
               }
             }
