@@ -648,9 +648,9 @@ __global__ void rowdot_kernel(const bf16_t* __restrict__ a, const bf16_t* __rest
 
 // attention_bwd_tc.cu
 int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* aux, void* dqkv, int F,
-                          int G, int heads, cudaStream_t st);
+                          int G, int heads, int hd, cudaStream_t st);
 int launch_attn_bwd_q_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* dq_out, float* A_out, int F,
-                         int G, int heads, cudaStream_t st);
+                         int G, int heads, int hd, cudaStream_t st);
 
 // attention_win_bwd_tc.cu
 int launch_attn_window_bwd_tc(const void* qkv, const void* qkv_bias, const void* Rh, const void* Rw, const void* dO, const float* lse, const float* dsum,
@@ -697,10 +697,10 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
   if constexpr (GFAST) {
     if (lse_fwd != nullptr) {      // the forward kernel's log-sum-exp: one key sweep instead of two
       bool q_done = false;
-      if constexpr (HD == 64 && (S == 64 || S == 32)) {       // tcgen05 / TMEM query side (attention_bwd_tc.cu)
+      if constexpr ((HD == 64 || HD == 80) && (S == 64 || S == 32)) {       // tcgen05 / TMEM query side (attention_bwd_tc.cu)
         static const bool use_mma_sync = []() { const char* e = getenv("GROVE_BWD_MMA_SYNC"); return e && e[0] == '1'; }();
         if (!use_mma_sync) {
-          const int rc = launch_attn_bwd_q_tc(qkv, dO, rel, lse_fwd, Dsum, dqc, A, F, G, heads, st);
+          const int rc = launch_attn_bwd_q_tc(qkv, dO, rel, lse_fwd, Dsum, dqc, A, F, G, heads, HD, st);
           if (rc) return rc;
           q_done = true;
         }
@@ -716,12 +716,12 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
     if (lse_fwd != nullptr) lse = const_cast<float*>(lse_fwd);
   }
   bool kv_done = false;
-  if constexpr (GFAST && HD == 64 && (S == 64 || S == 32)) {
+  if constexpr (GFAST && (HD == 64 || HD == 80) && (S == 64 || S == 32)) {
     // key side on tcgen05 / TMEM (attention_bwd_tc.cu); GROVE_BWD_MMA_SYNC=1 keeps the warp-level kernel (A/B measurements, cross-check)
     static const bool use_mma_sync = []() { const char* e = getenv("GROVE_BWD_MMA_SYNC"); return e && e[0] == '1'; }();
     if (!use_mma_sync) {
       float* aux = dqc + M * heads * HD;
-      const int rc = launch_attn_bwd_kv_tc(qkv, dO, rel, lse, Dsum, aux, dqkv, F, G, heads, st);
+      const int rc = launch_attn_bwd_kv_tc(qkv, dO, rel, lse, Dsum, aux, dqkv, F, G, heads, HD, st);
       if (rc) return rc;
       kv_done = true;
     }

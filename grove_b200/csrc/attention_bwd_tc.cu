@@ -22,7 +22,9 @@
 
 namespace grove {
 
-struct BwdKvTmaps { CUtensorMap qkv, dO, relw, relh, aux; };
+// qkv / dO: 128-row boxes of the 64-wide main part; *_x: the 16-wide tail of an 80-wide head (SWIZZLE_32B); *_b: the same two with
+// BQ-row boxes (the key-side kernel's query blocks)
+struct BwdKvTmaps { CUtensorMap qkv, dO, relw, relh, aux, qkv_x, dO_x, qkv_b, dO_b, qkv_bx, dO_bx; };
 
 constexpr int kBwdThreads = 320;
 
@@ -33,21 +35,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
-template <int G>
+template <int G, int HD>
 struct BwdKvCfg {
-  static constexpr int TS = 16384;                       // one [128 x 64] bf16 operand tile
-  static constexpr int kRelW = 128 * G * 4;              // rel_w slab of a query block: [128 q][G] fp32
-  static constexpr int kSmall = 128 * 4 * 4;             // rel_h slab / aux rows / combined rows: [128 q][4] fp32
-  static constexpr int kStage = 2 * TS + kRelW + 4 * kSmall;   // Q_i | dO_i | rel_w | rel_h | aux | comb_h | D
-  static constexpr int kTx = 2 * TS + kRelW + 2 * kSmall;       // bytes the TMA delivers per stage
+  static constexpr bool kX = HD > 64;
+  // 64-wide heads sweep the queries in blocks of 128; 80-wide heads in blocks of 64, because S^T | dP^T | P^T | dS^T of a 128-query block
+  // (384 columns) plus two 80-column accumulators would not fit the 512 columns of tensor memory
+  static constexpr int BQ = kX ? 64 : 128;
+  static constexpr int TS = 16384 + (kX ? 4096 : 0);     // own K / V: [128 x 64] bf16 (SWIZZLE_128B) [+ 128 x 16 tail, SWIZZLE_32B]
+  static constexpr int TQM = BQ * 128, TQ = TQM + (kX ? BQ * 32 : 0);   // Q_i / dO_i of a query block
+  static constexpr int kRelW = BQ * G * 4;               // rel_w slab of a query block: [BQ q][G] fp32
+  static constexpr int kSmall = BQ * 4 * 4;              // rel_h slab / aux rows / combined rows: [BQ q][4] fp32
+  static constexpr int kStage = 2 * TQ + kRelW + 4 * kSmall;   // Q_i | dO_i | rel_w | rel_h | aux | comb_h | D
+  static constexpr int kTx = 2 * TQ + kRelW + 2 * kSmall;       // bytes the TMA delivers per stage
   static constexpr int kSmem = 2 * TS + 2 * kStage + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int G>
+template <int G, int HD>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __restrict__ dqkv, int heads) {
-  using C = BwdKvCfg<G>;
-  constexpr int HD = 64, TS = C::TS, N = G * G, NB = N / 128, RPT = 128 / G;   // RPT: grid rows covered by one 128-key block
+  using C = BwdKvCfg<G, HD>;
+  constexpr bool kX = C::kX;
+  constexpr int TS = C::TS, TQ = C::TQ, TQM = C::TQM, BQ = C::BQ, N = G * G, NB = N / BQ, RPT = 128 / G;   // RPT: grid rows covered by one 128-key block
+  constexpr int NCC = BQ / 64;                           // 32-column chunks per elementwise thread and block
+  constexpr float kScale = HD == 64 ? 0.125f : 0.11180339887498949f;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = s0, sVo = s0 + TS;
@@ -76,7 +86,8 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tP = tmem_base + 256, tDS = tmem_base + 320, tDV = tmem_base + 384, tDK = tmem_base + 448;
+  const uint32_t tS = tmem_base, tDP = tmem_base + BQ, tP = tmem_base + 2 * BQ, tDS = tP + BQ / 2, tDV = tmem_base + 3 * BQ, tDK = tDV + HD;
+  static_assert(3 * BQ + 2 * HD <= 512, "tensor memory budget");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -84,33 +95,48 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
       mbar_expect_tx(bar(OWN_FULL), 2 * TS);
       tma_load_2d(sK, &tm.qkv, bar(OWN_FULL), D + h * HD, tok0 + jb * 128);
       tma_load_2d(sVo, &tm.qkv, bar(OWN_FULL), 2 * D + h * HD, tok0 + jb * 128);
+      if (kX) {
+        tma_load_2d(sK + 16384, &tm.qkv_x, bar(OWN_FULL), D + h * HD + 64, tok0 + jb * 128);
+        tma_load_2d(sVo + 16384, &tm.qkv_x, bar(OWN_FULL), 2 * D + h * HD + 64, tok0 + jb * 128);
+      }
       for (int i = 0; i < NB; ++i) {
         const int s = i & 1;
         mbar_wait(bar(STAGE_EMPTY + s), ((i >> 1) & 1u) ^ 1u);
         const uint32_t st = sStage(s);
         mbar_expect_tx(bar(STAGE_FULL + s), C::kTx);
-        const int tq = tok0 + i * 128;
-        tma_load_2d(st, &tm.qkv, bar(STAGE_FULL + s), h * HD, tq);                       // Q_i
-        tma_load_2d(st + TS, &tm.dO, bar(STAGE_FULL + s), h * HD, tq);                   // dO_i
-        tma_load_3d(st + 2 * TS, &tm.relw, bar(STAGE_FULL + s), G, h, tq);               // rel_w[q, 0:G]   (columns G..2G of the bias row)
+        const int tq = tok0 + i * BQ;
+        tma_load_2d(st, &tm.qkv_b, bar(STAGE_FULL + s), h * HD, tq);                     // Q_i
+        tma_load_2d(st + TQ, &tm.dO_b, bar(STAGE_FULL + s), h * HD, tq);                 // dO_i
+        if (kX) {
+          tma_load_2d(st + TQM, &tm.qkv_bx, bar(STAGE_FULL + s), h * HD + 64, tq);
+          tma_load_2d(st + TQ + TQM, &tm.dO_bx, bar(STAGE_FULL + s), h * HD + 64, tq);
+        }
+        tma_load_3d(st + 2 * TQ, &tm.relw, bar(STAGE_FULL + s), G, h, tq);               // rel_w[q, 0:G]   (columns G..2G of the bias row)
         // rel_h[q, kh of this key block]: 4 floats from a 16-byte aligned column (TMA box origins must be; jb * RPT is odd pairs for G = 64)
-        tma_load_3d(st + 2 * TS + C::kRelW, &tm.relh, bar(STAGE_FULL + s), (jb * RPT) & ~3, h, tq);
-        tma_load_3d(st + 2 * TS + C::kRelW + C::kSmall, &tm.aux, bar(STAGE_FULL + s), 0, h, tq);       // (lse, D, -, -)
+        tma_load_3d(st + 2 * TQ + C::kRelW, &tm.relh, bar(STAGE_FULL + s), (jb * RPT) & ~3, h, tq);
+        tma_load_3d(st + 2 * TQ + C::kRelW + C::kSmall, &tm.aux, bar(STAGE_FULL + s), 0, h, tq);       // (lse, D, -, -)
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, BQ);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B is MN-major (the [q][d] tile read along q)
+    constexpr uint32_t idesc_ox = umma_idesc_bf16(128, 16) | (1u << 16);
     auto mma2 = [&](int i) {           // dV += P^T dO_i, dK += dS^T Q_i
       const uint32_t st = sStage(i & 1);
       mbar_wait(bar(PD_FULL), i & 1u);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) tc_mma_f16_ts(tDV, tP + kk * 8, umma_desc_sw128(st + TS + kk * 2048), idesc_o, (i | kk) != 0);
+        for (int kk = 0; kk < BQ / 16; ++kk) {
+          tc_mma_f16_ts(tDV, tP + kk * 8, umma_desc_sw128(st + TQ + kk * 2048), idesc_o, (i | kk) != 0);
+          if (kX) tc_mma_f16_ts(tDV + 64, tP + kk * 8, umma_desc_sw32(st + TQ + TQM + kk * 512), idesc_ox, (i | kk) != 0);
+        }
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) tc_mma_f16_ts(tDK, tDS + kk * 8, umma_desc_sw128(st + kk * 2048), idesc_o, (i | kk) != 0);
+        for (int kk = 0; kk < BQ / 16; ++kk) {
+          tc_mma_f16_ts(tDK, tDS + kk * 8, umma_desc_sw128(st + kk * 2048), idesc_o, (i | kk) != 0);
+          if (kX) tc_mma_f16_ts(tDK + 64, tDS + kk * 8, umma_desc_sw32(st + TQM + kk * 512), idesc_ox, (i | kk) != 0);
+        }
         tc_commit(bar(PD_EMPTY));
         tc_commit(bar(STAGE_EMPTY + (i & 1)));
         if (i == NB - 1) tc_commit(bar(ACC_FULL));
@@ -128,8 +154,10 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) tc_mma_f16(tS, umma_desc_sw128(sK + k * 32), umma_desc_sw128(st + k * 32), idesc_s, k != 0);
+        if (kX) tc_mma_f16(tS, umma_desc_sw32(sK + 16384), umma_desc_sw32(st + TQM), idesc_s, 1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, umma_desc_sw128(sVo + k * 32), umma_desc_sw128(st + TS + k * 32), idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, umma_desc_sw128(sVo + k * 32), umma_desc_sw128(st + TQ + k * 32), idesc_s, k != 0);
+        if (kX) tc_mma_f16(tDP, umma_desc_sw32(sVo + 16384), umma_desc_sw32(st + TQ + TQM), idesc_s, 1);
         tc_commit(bar(SD_FULL));
       }
       __syncwarp();
@@ -145,18 +173,18 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
     const int et = (warp - 2) * 32 + lane;               // 0..255
     const int kw = row % G, khl = row / G + ((jb * RPT) & 3);   // key column; key row relative to the aligned rel_h box
     constexpr float kL2e = 1.4426950408889634f;
-    const float c_l2 = 0.125f * kL2e;                    // hd^-0.5 * log2(e), hd = 64
+    const float c_l2 = kScale * kL2e;                    // hd^-0.5 * log2(e)
 #pragma unroll 1
     for (int i = 0; i < NB; ++i) {
       const int s = i & 1;
-      float* stg = reinterpret_cast<float*>(smem_al + (sStage(s) - s0) + 2 * TS);
-      const float* relw_s = stg;                                         // [128][G]
-      const float* relh_s = stg + 128 * G;                               // [128][4]
-      const float* aux_s = relh_s + 128 * 4;                             // [128][4] = lse, D, -, -
-      float* comb_s = stg + 128 * G + 2 * 128 * 4;                       // [128][4] = rel_h * log2e - lse for the block's grid rows
-      float* dsum_s = comb_s + 128 * 4;                                  // [128]
+      float* stg = reinterpret_cast<float*>(smem_al + (sStage(s) - s0) + 2 * TQ);
+      const float* relw_s = stg;                                         // [BQ][G]
+      const float* relh_s = stg + BQ * G;                                // [BQ][4]
+      const float* aux_s = relh_s + BQ * 4;                              // [BQ][4] = lse, D, -, -
+      float* comb_s = stg + BQ * G + 2 * BQ * 4;                         // [BQ][4] = rel_h * log2e - lse for the block's grid rows
+      float* dsum_s = comb_s + BQ * 4;                                   // [BQ]
       mbar_wait(bar(STAGE_FULL + s), (i >> 1) & 1u);
-      if (et < 128) {
+      if (et < BQ) {
         const float4 rh = *reinterpret_cast<const float4*>(relh_s + et * 4);
         const float2 ax = *reinterpret_cast<const float2*>(aux_s + et * 4);
         *reinterpret_cast<float4*>(comb_s + et * 4) = make_float4(fmaf(rh.x, kL2e, -ax.x), fmaf(rh.y, kL2e, -ax.x), fmaf(rh.z, kL2e, -ax.x), fmaf(rh.w, kL2e, -ax.x));
@@ -166,13 +194,13 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
       mbar_wait(bar(SD_FULL), i & 1u);
       tc_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+      for (int cc = 0; cc < NCC; ++cc) {
         const int c = 2 * cc + hs;
         uint32_t rs[32], rd[32];
         tmem_ld_x32(tS + c * 32 + tlane, rs);
         tmem_ld_x32(tDP + c * 32 + tlane, rd);
         tmem_ld_wait();
-        if (cc == 1) {                                   // both chunks of S^T / dP^T are in registers: MMA1 of the next block may overwrite them
+        if (cc == NCC - 1) {                             // all chunks of S^T / dP^T are in registers: MMA1 of the next block may overwrite them
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(SD_EMPTY));
@@ -201,19 +229,24 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
     // ---- epilogue: dK (x scale), dV -> bf16 into the k / v slots of dqkv; each thread of a row stores 32 of the 64 head dims
     mbar_wait(bar(ACC_FULL), 0);
     tc_fence_after();
-    __nv_bfloat16* orow = dqkv + ((size_t)tok0 + jb * 128 + row) * (3 * D) + h * HD + hs * 32;
+    __nv_bfloat16* orow = dqkv + ((size_t)tok0 + jb * 128 + row) * (3 * D) + h * HD;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {            // 0: dK, 1: dV
-      uint32_t r[32];
+      uint32_t r[32], rx[8];
       tmem_ld_x32((which == 0 ? tDK : tDV) + hs * 32 + tlane, r);
+      if (kX) tmem_ld_x8((which == 0 ? tDK : tDV) + 64 + hs * 8 + tlane, rx);
       tmem_ld_wait();
-      const float sc = which == 0 ? 0.125f : 1.0f;
+      const float sc = which == 0 ? kScale : 1.0f;
       __nv_bfloat16* o = orow + (which == 0 ? D : 2 * D);
 #pragma unroll
       for (int j = 0; j < 32; j += 8)
-        *reinterpret_cast<uint4*>(o + j) =
+        *reinterpret_cast<uint4*>(o + hs * 32 + j) =
             make_uint4(pack_bf16(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc), pack_bf16(__uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc),
                        pack_bf16(__uint_as_float(r[j + 4]) * sc, __uint_as_float(r[j + 5]) * sc), pack_bf16(__uint_as_float(r[j + 6]) * sc, __uint_as_float(r[j + 7]) * sc));
+      if (kX)
+        *reinterpret_cast<uint4*>(o + 64 + hs * 8) =
+            make_uint4(pack_bf16(__uint_as_float(rx[0]) * sc, __uint_as_float(rx[1]) * sc), pack_bf16(__uint_as_float(rx[2]) * sc, __uint_as_float(rx[3]) * sc),
+                       pack_bf16(__uint_as_float(rx[4]) * sc, __uint_as_float(rx[5]) * sc), pack_bf16(__uint_as_float(rx[6]) * sc, __uint_as_float(rx[7]) * sc));
     }
   }
   tc_fence_before();
@@ -232,20 +265,23 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
 // turns them into d q.  Two threads per query row: thread hs owns the key chunks {hs, hs+2} of every block, i.e. always the same 32 key
 // columns kw (rel_w and A_w live in registers like in the forward kernel).
 // =====================================================================================================================
-template <int G>
+template <int G, int HD>
 struct BwdQCfg {
-  static constexpr int TS = 16384;
+  static constexpr bool kX = HD > 64;
+  static constexpr int TS = 16384 + (kX ? 4096 : 0);      // [128 x 64] bf16 (SWIZZLE_128B) [+ 128 x 16 tail, SWIZZLE_32B]
   static constexpr int kRelH = G * 128 * 4;               // rel_h [G][128] fp32
   static constexpr int kAh = 2 * G * 128 * 4;             // A_h partial sums [2][G][128] fp32
   static constexpr int kSmem = 2 * TS + 4 * TS + kRelH + kAh + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int G>
+template <int G, int HD>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restrict__ rel, const float* __restrict__ lse, const float* __restrict__ dsum,
                      float* __restrict__ dq_out, float* __restrict__ A_out, int heads) {
-  using C = BwdQCfg<G>;
-  constexpr int HD = 64, TS = C::TS, N = G * G, NB = N / 128;
+  using C = BwdQCfg<G, HD>;
+  constexpr bool kX = C::kX;
+  constexpr int TS = C::TS, N = G * G, NB = N / 128;
+  constexpr float kScale = HD == 64 ? 0.125f : 0.11180339887498949f;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = s0, sDO = s0 + TS;
@@ -285,25 +321,37 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
       mbar_expect_tx(bar(OWN_FULL), 2 * TS);
       tma_load_2d(sQ, &tm.qkv, bar(OWN_FULL), h * HD, tok0 + ib * 128);
       tma_load_2d(sDO, &tm.dO, bar(OWN_FULL), h * HD, tok0 + ib * 128);
+      if (kX) {
+        tma_load_2d(sQ + 16384, &tm.qkv_x, bar(OWN_FULL), h * HD + 64, tok0 + ib * 128);
+        tma_load_2d(sDO + 16384, &tm.dO_x, bar(OWN_FULL), h * HD + 64, tok0 + ib * 128);
+      }
       for (int j = 0; j < NB; ++j) {
         const int s = j & 1;
         mbar_wait(bar(STAGE_EMPTY + s), ((j >> 1) & 1u) ^ 1u);
         mbar_expect_tx(bar(STAGE_FULL + s), 2 * TS);
         tma_load_2d(sStage(s), &tm.qkv, bar(STAGE_FULL + s), D + h * HD, tok0 + j * 128);           // K_j
         tma_load_2d(sStage(s) + TS, &tm.qkv, bar(STAGE_FULL + s), 2 * D + h * HD, tok0 + j * 128);  // V_j
+        if (kX) {
+          tma_load_2d(sStage(s) + 16384, &tm.qkv_x, bar(STAGE_FULL + s), D + h * HD + 64, tok0 + j * 128);
+          tma_load_2d(sStage(s) + TS + 16384, &tm.qkv_x, bar(STAGE_FULL + s), 2 * D + h * HD + 64, tok0 + j * 128);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= K_j) read MN-major
+    constexpr uint32_t idesc_ox = umma_idesc_bf16(128, 16) | (1u << 16);
     auto mma2 = [&](int j) {           // dQ += dS K_j
       const uint32_t st = sStage(j & 1);
       mbar_wait(bar(PD_FULL), j & 1u);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) tc_mma_f16_ts(tDQ, tDS + kk * 8, umma_desc_sw128(st + kk * 2048), idesc_o, (j | kk) != 0);
+        for (int kk = 0; kk < 8; ++kk) {
+          tc_mma_f16_ts(tDQ, tDS + kk * 8, umma_desc_sw128(st + kk * 2048), idesc_o, (j | kk) != 0);
+          if (kX) tc_mma_f16_ts(tDQ + 64, tDS + kk * 8, umma_desc_sw32(st + 16384 + kk * 512), idesc_ox, (j | kk) != 0);
+        }
         tc_commit(bar(PD_EMPTY));
         tc_commit(bar(STAGE_EMPTY + (j & 1)));
         if (j == NB - 1) tc_commit(bar(ACC_FULL));
@@ -321,8 +369,10 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) tc_mma_f16(tS, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(st + k * 32), idesc_s, k != 0);
+        if (kX) tc_mma_f16(tS, umma_desc_sw32(sQ + 16384), umma_desc_sw32(st + 16384), idesc_s, 1);
 #pragma unroll
         for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, umma_desc_sw128(sDO + k * 32), umma_desc_sw128(st + TS + k * 32), idesc_s, k != 0);
+        if (kX) tc_mma_f16(tDP, umma_desc_sw32(sDO + 16384), umma_desc_sw32(st + TS + 16384), idesc_s, 1);
         tc_commit(bar(SD_FULL));
       }
       __syncwarp();
@@ -336,7 +386,7 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
     const int row = quad * 32 + lane;
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
     constexpr float kL2e = 1.4426950408889634f;
-    const float c_l2 = 0.125f * kL2e;
+    const float c_l2 = kScale * kL2e;
     const int kw_base = ((hs & 1) * 32) % G;             // the 32 key columns this thread sees in every chunk
     const size_t rh = ((size_t)tok0 + ib * 128 + row) * heads + h;       // (token, head) row of rel / lse / D / A
     const float* relrow = rel + rh * (2 * G);
@@ -394,14 +444,21 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
     mbar_wait(bar(ACC_FULL), 0);                         // every MMA has retired: the K/V stages can serve as scratch
     tc_fence_after();
     {
-      uint32_t r[32];
+      uint32_t r[32], rx[8];
       tmem_ld_x32(tDQ + hs * 32 + tlane, r);
+      if (kX) tmem_ld_x8(tDQ + 64 + hs * 8 + tlane, rx);
       tmem_ld_wait();
-      float* o = dq_out + ((size_t)tok0 + ib * 128 + row) * D + h * HD + hs * 32;
+      float* o = dq_out + ((size_t)tok0 + ib * 128 + row) * D + h * HD;
 #pragma unroll
       for (int jj = 0; jj < 32; jj += 4)
-        *reinterpret_cast<float4*>(o + jj) = make_float4(__uint_as_float(r[jj]) * 0.125f, __uint_as_float(r[jj + 1]) * 0.125f,
-                                                         __uint_as_float(r[jj + 2]) * 0.125f, __uint_as_float(r[jj + 3]) * 0.125f);
+        *reinterpret_cast<float4*>(o + hs * 32 + jj) = make_float4(__uint_as_float(r[jj]) * kScale, __uint_as_float(r[jj + 1]) * kScale,
+                                                                   __uint_as_float(r[jj + 2]) * kScale, __uint_as_float(r[jj + 3]) * kScale);
+      if (kX) {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj += 4)
+          *reinterpret_cast<float4*>(o + 64 + hs * 8 + jj) = make_float4(__uint_as_float(rx[jj]) * kScale, __uint_as_float(rx[jj + 1]) * kScale,
+                                                                         __uint_as_float(rx[jj + 2]) * kScale, __uint_as_float(rx[jj + 3]) * kScale);
+      }
     }
     float* arow = A_out + rh * (2 * G);
     if (G == 64) {                                       // the two threads of a row own disjoint halves of the key columns
@@ -453,34 +510,62 @@ static int make_tmap_f32_3d(CUtensorMap* m, const void* base, uint64_t d0, uint6
   return GROVE_OK;
 }
 
-// called from run_attn_bwd (attention_bwd.cu) for global layers with head dim 64 on 32x32 / 64x64 grids.
-// rel: fp32 [M, heads, 2G] bias rows; lse, dsum: fp32 [M, heads]; aux: fp32 scratch [M, heads, 4]
-int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* aux, void* dqkv, int F,
-                          int G, int heads, cudaStream_t st) {
-  const int N = G * G, D = heads * 64;
-  const long long M = (long long)F * N;
-  pack_lse_dsum_kernel<<<(unsigned)((M * heads + 255) / 256), 256, 0, st>>>(lse, dsum, reinterpret_cast<float4*>(aux), M * heads);
-  grove_count_launch();
-  BwdKvTmaps tm;
+static int make_bwd_tmaps(BwdKvTmaps& tm, const void* qkv, const void* dO, int hd, int heads, long long M, int bq) {
+  const int D = heads * hd;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tm.qkv, qkv, (uint64_t)3 * D, (uint64_t)M, 64, 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&tm.dO, dO, (uint64_t)D, (uint64_t)M, 64, 128))) return rc;
-  if ((rc = make_tmap_f32_3d(&tm.relw, rel, (uint64_t)2 * G, heads, (uint64_t)M, (uint32_t)G, 128))) return rc;
-  if ((rc = make_tmap_f32_3d(&tm.relh, rel, (uint64_t)2 * G, heads, (uint64_t)M, 4, 128))) return rc;
-  if ((rc = make_tmap_f32_3d(&tm.aux, aux, 4, heads, (uint64_t)M, 4, 128))) return rc;
-  cudaError_t e;
-  if (G == 64) {
-    constexpr int smem = BwdKvCfg<64>::kSmem;
-    static_assert(smem <= 232448, "shared memory budget");
-    e = cudaFuncSetAttribute(attn_bwd_kv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-    attn_bwd_kv_tc_kernel<64><<<dim3(N / 128, heads, F), kBwdThreads, smem, st>>>(tm, (__nv_bfloat16*)dqkv, heads);
+  if ((rc = make_tmap_bf16_2d(&tm.qkv_b, qkv, (uint64_t)3 * D, (uint64_t)M, 64, bq))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm.dO_b, dO, (uint64_t)D, (uint64_t)M, 64, bq))) return rc;
+  if (hd > 64) {
+    if ((rc = make_tmap_bf16_2d(&tm.qkv_x, qkv, (uint64_t)3 * D, (uint64_t)M, 16, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm.dO_x, dO, (uint64_t)D, (uint64_t)M, 16, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm.qkv_bx, qkv, (uint64_t)3 * D, (uint64_t)M, 16, bq))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm.dO_bx, dO, (uint64_t)D, (uint64_t)M, 16, bq))) return rc;
   } else {
-    constexpr int smem = BwdKvCfg<32>::kSmem;
-    e = cudaFuncSetAttribute(attn_bwd_kv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-    attn_bwd_kv_tc_kernel<32><<<dim3(N / 128, heads, F), kBwdThreads, smem, st>>>(tm, (__nv_bfloat16*)dqkv, heads);
+    tm.qkv_x = tm.qkv; tm.dO_x = tm.dO; tm.qkv_bx = tm.qkv; tm.dO_bx = tm.dO;
   }
+  return GROVE_OK;
+}
+
+template <int G, int HD>
+static int launch_kv(const BwdKvTmaps& tm, void* dqkv, int F, int heads, cudaStream_t st) {
+  constexpr int smem = BwdKvCfg<G, HD>::kSmem;
+  static_assert(smem <= 232448, "shared memory budget");
+  cudaError_t e = cudaFuncSetAttribute(attn_bwd_kv_tc_kernel<G, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
+  attn_bwd_kv_tc_kernel<G, HD><<<dim3(G * G / 128, heads, F), kBwdThreads, smem, st>>>(tm, (__nv_bfloat16*)dqkv, heads);
+  return GROVE_OK;
+}
+
+template <int G, int HD>
+static int launch_q(const BwdKvTmaps& tm, const float* rel, const float* lse, const float* dsum, float* dq_out, float* A_out, int F, int heads, cudaStream_t st) {
+  constexpr int smem = BwdQCfg<G, HD>::kSmem;
+  static_assert(smem <= 232448, "shared memory budget");
+  cudaError_t e = cudaFuncSetAttribute(attn_bwd_q_tc_kernel<G, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
+  attn_bwd_q_tc_kernel<G, HD><<<dim3(G * G / 128, heads, F), kBwdThreads, smem, st>>>(tm, rel, lse, dsum, dq_out, A_out, heads);
+  return GROVE_OK;
+}
+
+// called from run_attn_bwd (attention_bwd.cu) for global layers with head dim 64 / 80 on 32x32 / 64x64 grids.
+// rel: fp32 [M, heads, 2G] bias rows; lse, dsum: fp32 [M, heads]; aux: fp32 scratch [M, heads, 4]
+int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* aux, void* dqkv, int F,
+                          int G, int heads, int hd, cudaStream_t st) {
+  const int N = G * G;
+  const long long M = (long long)F * N;
+  pack_lse_dsum_kernel<<<(unsigned)((M * heads + 255) / 256), 256, 0, st>>>(lse, dsum, reinterpret_cast<float4*>(aux), M * heads);
+  grove_count_launch();
+  const int bq = hd > 64 ? 64 : 128;
+  BwdKvTmaps tm;
+  int rc;
+  if ((rc = make_bwd_tmaps(tm, qkv, dO, hd, heads, M, bq))) return rc;
+  if ((rc = make_tmap_f32_3d(&tm.relw, rel, (uint64_t)2 * G, heads, (uint64_t)M, (uint32_t)G, bq))) return rc;
+  if ((rc = make_tmap_f32_3d(&tm.relh, rel, (uint64_t)2 * G, heads, (uint64_t)M, 4, bq))) return rc;
+  if ((rc = make_tmap_f32_3d(&tm.aux, aux, 4, heads, (uint64_t)M, 4, bq))) return rc;
+  if (G == 64) rc = hd == 64 ? launch_kv<64, 64>(tm, dqkv, F, heads, st) : launch_kv<64, 80>(tm, dqkv, F, heads, st);
+  else rc = hd == 64 ? launch_kv<32, 64>(tm, dqkv, F, heads, st) : launch_kv<32, 80>(tm, dqkv, F, heads, st);
+  if (rc) return rc;
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
@@ -488,27 +573,15 @@ int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, con
 
 // query side (see attn_bwd_q_tc_kernel); same preconditions as launch_attn_bwd_kv_tc
 int launch_attn_bwd_q_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* dq_out, float* A_out, int F,
-                         int G, int heads, cudaStream_t st) {
-  const int N = G * G, D = heads * 64;
-  const long long M = (long long)F * N;
+                         int G, int heads, int hd, cudaStream_t st) {
+  const long long M = (long long)F * G * G;
   BwdKvTmaps tm;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&tm.qkv, qkv, (uint64_t)3 * D, (uint64_t)M, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tm.dO, dO, (uint64_t)D, (uint64_t)M, 64, 128))) return rc;
+  if ((rc = make_bwd_tmaps(tm, qkv, dO, hd, heads, M, 128))) return rc;
   tm.relw = tm.qkv; tm.relh = tm.qkv; tm.aux = tm.qkv;      // unused by this kernel
-  cudaError_t e;
-  if (G == 64) {
-    constexpr int smem = BwdQCfg<64>::kSmem;
-    static_assert(smem <= 232448, "shared memory budget");
-    e = cudaFuncSetAttribute(attn_bwd_q_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-    attn_bwd_q_tc_kernel<64><<<dim3(N / 128, heads, F), kBwdThreads, smem, st>>>(tm, rel, lse, dsum, dq_out, A_out, heads);
-  } else {
-    constexpr int smem = BwdQCfg<32>::kSmem;
-    e = cudaFuncSetAttribute(attn_bwd_q_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-    attn_bwd_q_tc_kernel<32><<<dim3(N / 128, heads, F), kBwdThreads, smem, st>>>(tm, rel, lse, dsum, dq_out, A_out, heads);
-  }
+  if (G == 64) rc = hd == 64 ? launch_q<64, 64>(tm, rel, lse, dsum, dq_out, A_out, F, heads, st) : launch_q<64, 80>(tm, rel, lse, dsum, dq_out, A_out, F, heads, st);
+  else rc = hd == 64 ? launch_q<32, 64>(tm, rel, lse, dsum, dq_out, A_out, F, heads, st) : launch_q<32, 80>(tm, rel, lse, dsum, dq_out, A_out, F, heads, st);
+  if (rc) return rc;
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;
