@@ -264,15 +264,28 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     const uint32_t stg = epi_base + (warp - 2) * (32 * Cfg::kStageRowF * 4);
     constexpr int kPasses = BN / 2 / 32;
     uint32_t tile_it = 0;
-    if constexpr (EPI == 1 || EPI == 2 || EPI == 5 || EPI == 6) {
-      constexpr bool kFold = EPI >= 5;                     // LayerNorm of the A rows folded in (see GemmParams::ln_stats)
+    if constexpr (EPI == 1 || EPI == 2 || EPI == 5 || EPI == 6 || EPI == 7) {
+      constexpr bool kFold = EPI == 5 || EPI == 6;         // LayerNorm of the A rows folded in (see GemmParams::ln_stats)
       constexpr bool kGelu = EPI == 2 || EPI == 6;
+      constexpr bool kDact = EPI == 7;                     // out = (acc + bias) * gelu'(pre): the fc2 input gradient (backward of the MLP's GELU)
       // ---- bf16 output, bias, optional GELU.  Per warp and pass: one tcgen05.ld of 32 rows x 32 columns (lane = row), bias +
       // activation in registers, pack to bf16, stage 32 rows x 64 B through an XOR-swizzled (conflict-free both ways) private
       // buffer, then 8 rows x 64 B per store instruction.  The accumulator is released right after the last tcgen05.ld.
       const uint32_t bias_s = stg + 2048;                  // this warp's 128 bias values (fp32), 512 B behind the 2 KB staging
       const uint32_t csum_s = stg + 2560;                  // kFold: this warp's 128 column sums of gamma*W
+      const uint32_t pre_s = stg + 2560;                   // kDact: this pass' pre-activation block, 32 rows x 64 B, swizzled like the output staging
       __nv_bfloat16* const outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+      // kDact: the pre-activation rows arrive like the output leaves (8 rows x 64 B per instruction), one pass ahead of their use
+      auto pre_ptr = [&](int tile_, int ps_, int i_) {
+        const int m_blk_ = (p.m_blk0 + tile_ / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk_ = tile_ % p.num_n_blocks;
+        const int row_ = min(m_blk_ * BM + quad * 32 + 8 * i_ + (lane >> 2), p.M - 1);
+        return p.dact_pre + (size_t)row_ * p.N + n_blk_ * BN + half * (BN / 2) + ps_ * 32 + (lane & 3) * 8;
+      };
+      uint4 preg[4];
+      if (kDact && tile0 < num_tiles) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) preg[i] = *reinterpret_cast<const uint4*>(pre_ptr(tile0, 0, i));
+      }
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
         const int m_blk = (p.m_blk0 + tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
         const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
@@ -300,9 +313,31 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
         tc_fence_after();
 #pragma unroll 1
         for (int ps = 0; ps < kPasses; ++ps) {
+          if (kDact) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = 8 * i + (lane >> 2);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(pre_s + rl * 64 + (((lane & 3) ^ ((rl >> 1) & 3)) << 4)), "r"(preg[i].x), "r"(preg[i].y),
+                           "r"(preg[i].z), "r"(preg[i].w) : "memory");
+            }
+            const bool last = ps == kPasses - 1;
+            const int ntile = last ? tile + tile_step : tile;
+            if (ntile < num_tiles) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) preg[i] = *reinterpret_cast<const uint4*>(pre_ptr(ntile, last ? 0 : ps + 1, i));
+            }
+          }
           uint32_t r0[32];
           tmem_ld_32x32b_x32(tmem_base + acc * BN + half * (BN / 2) + ps * 32 + ((uint32_t)(quad * 32) << 16), r0);
           tmem_ld_wait();
+          uint32_t pu[16];
+          if (kDact) {                                     // lane = row: its 32 pre-activations
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(pu[4 * c]), "=r"(pu[4 * c + 1]), "=r"(pu[4 * c + 2]), "=r"(pu[4 * c + 3])
+                           : "r"(pre_s + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)));
+          }
           if (ps == kPasses - 1) {                         // accumulator drained: the MMA warp may start the tile after next
             tc_fence_before();
             __syncwarp();
@@ -330,6 +365,10 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
               v23 = __fadd2_rn(v23, make_float2(b4.z, b4.w));
             }
             if (kGelu) { v01 = gelu_fast2(v01); v23 = gelu_fast2(v23); }
+            if (kDact) {
+              v01 = __fmul2_rn(v01, gelu_grad_fast2(unpack_bf16(pu[j >> 1])));
+              v23 = __fmul2_rn(v23, gelu_grad_fast2(unpack_bf16(pu[(j >> 1) + 1])));
+            }
             const float v0 = v01.x, v1 = v01.y, v2 = v23.x, v3 = v23.y;
             pk[j >> 1] = pack_bf16(v0, v1);
             pk[(j >> 1) + 1] = pack_bf16(v2, v3);
@@ -914,6 +953,10 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
   if (ctas == 2 && plain_bf16 && p.ln_stats)
     return p.act == 1 ? launch_gemm<256, 2, 6>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 5>(p, ta, tb, max_ctas, st);
   if (ctas == 2 && plain_bf16) return p.act == 1 ? launch_gemm<256, 2, 2>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 1>(p, ta, tb, max_ctas, st);
+  // the fc2 input gradient: bf16 output scaled by the GELU derivative of the saved pre-activation
+  const bool dact_bf16 = !p.out_f32 && !p.resid && !p.resid16 && !p.gate_alpha && !p.out2 && p.dact_pre && p.dact == 1 && p.splits == 1 && p.conv != 2 && p.act == 0 &&
+                         !generic_epilogue_only();
+  if (ctas == 2 && dact_bf16) return launch_gemm<256, 2, 7>(p, ta, tb, max_ctas, st);
   const bool resid_f32 = p.out_f32 && p.resid && !p.resid16 && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2_pre &&
                          !generic_epilogue_only();
   const bool resid_b16 = !p.out_f32 && p.resid16 && !p.resid && !p.dact_pre && p.splits == 1 && p.conv != 2 && p.act != 1 && !p.out2 &&

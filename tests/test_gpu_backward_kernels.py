@@ -47,6 +47,13 @@ def test_gemm_dact_and_pre_activation(ops):
         ops.gemm(a, w, g, dact_pre=z, dact=kind)
         (dz,) = torch.autograd.grad(fn(zz).sum(), zz)
         assert _relerr(g.float(), (a.float() @ w.float().t()) * dz) < 6e-3
+    # ragged M (rows past the end are clamped for the pre-activation fetch and never stored) with a bias, on the CTA-pair fast epilogue
+    Mr = 1400
+    g = torch.full((Mr + 8, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a[:Mr], w, g[:Mr], bias=bias, dact_pre=z[:Mr].contiguous(), dact="gelu")
+    (dz,) = torch.autograd.grad(F.gelu(zz).sum(), zz)
+    assert _relerr(g[:Mr].float(), ref[:Mr] * dz[:Mr]) < 6e-3
+    assert bool((g[Mr:] == 7.0).all())
     # fp32 output: out2 = value after the activation, before gate and residual
     alpha = torch.tensor([0.4], device="cuda")
     x = _rand((M, N), 5)
