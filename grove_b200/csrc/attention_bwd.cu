@@ -649,8 +649,8 @@ __global__ void rowdot_kernel(const bf16_t* __restrict__ a, const bf16_t* __rest
 // attention_bwd_tc.cu
 int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* aux, void* dqkv, int F,
                           int G, int heads, int hd, cudaStream_t st);
-int launch_attn_bwd_q_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* dq_out, float* A_out, int F,
-                         int G, int heads, int hd, cudaStream_t st);
+int launch_attn_bwd_q_tc(const void* qkv, const void* dO, const void* Rh, const void* Rw, float* rel, const float* lse, const float* dsum, void* dqkv,
+                         int F, int G, int heads, int hd, cudaStream_t st);
 
 // attention_win_bwd_tc.cu
 int launch_attn_window_bwd_tc(const void* qkv, const void* qkv_bias, const void* Rh, const void* Rw, const void* dO, const float* lse, const float* dsum,
@@ -689,6 +689,20 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
       return launch_attn_window_bwd_tc(qkv, qkv_bias, Rh, Rw, dO, lse_fwd, Dsum, dqkv, F, G, heads, HD, st);
     }
   }
+  if constexpr (GFAST && (HD == 64 || HD == 80) && (S == 64 || S == 32)) {
+    // global layers with the forward's log-sum-exp at hand: query side then key side on tcgen05 / TMEM (attention_bwd_tc.cu).  The query
+    // side also produces the bias rows `rel` the key side reads and back-projects the bias cotangents through the tables itself, so the
+    // two relpos_kernel launches of the warp-level path are gone.  GROVE_BWD_MMA_SYNC=1 keeps the warp-level kernels (A/B, cross-check).
+    static const bool use_mma_sync = []() { const char* e = getenv("GROVE_BWD_MMA_SYNC"); return e && e[0] == '1'; }();
+    if (lse_fwd != nullptr && !use_mma_sync) {
+      rowdot_kernel<<<(unsigned)((M * heads + 255) / 256), 256, 0, st>>>(dO, O, Dsum, M * heads, HD);
+      grove_count_launch();
+      int rc = launch_attn_bwd_q_tc(qkv, dO, Rh, Rw, rel, lse_fwd, Dsum, dqkv, F, G, heads, HD, st);
+      if (rc) return rc;
+      float* aux = dqc + M * heads * HD;
+      return launch_attn_bwd_kv_tc(qkv, dO, rel, lse_fwd, Dsum, aux, dqkv, F, G, heads, HD, st);
+    }
+  }
   const dim3 grid_rel((unsigned)(M / 64), heads);
   relpos_kernel<S, HD, WIN, 0><<<grid_rel, 256, smem_rel, st>>>(qkv, Rh, Rw, rel, nullptr, nullptr, nullptr, G, heads);
   rowdot_kernel<<<(unsigned)((M * heads + 255) / 256), 256, 0, st>>>(dO, O, Dsum, M * heads, HD);
@@ -696,16 +710,7 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
   bool fast_q = false;
   if constexpr (GFAST) {
     if (lse_fwd != nullptr) {      // the forward kernel's log-sum-exp: one key sweep instead of two
-      bool q_done = false;
-      if constexpr ((HD == 64 || HD == 80) && (S == 64 || S == 32)) {       // tcgen05 / TMEM query side (attention_bwd_tc.cu)
-        static const bool use_mma_sync = []() { const char* e = getenv("GROVE_BWD_MMA_SYNC"); return e && e[0] == '1'; }();
-        if (!use_mma_sync) {
-          const int rc = launch_attn_bwd_q_tc(qkv, dO, rel, lse_fwd, Dsum, dqc, A, F, G, heads, HD, st);
-          if (rc) return rc;
-          q_done = true;
-        }
-      }
-      if (!q_done) attn_bwd_q_global_kernel<S, HD><<<dim3(NT, heads, F), 128, smem_qf, st>>>(qkv, dO, rel, Dsum, lse_fwd, dqc, A, heads);
+      attn_bwd_q_global_kernel<S, HD><<<dim3(NT, heads, F), 128, smem_qf, st>>>(qkv, dO, rel, Dsum, lse_fwd, dqc, A, heads);
       lse = const_cast<float*>(lse_fwd);
       fast_q = true;
     }
@@ -715,18 +720,7 @@ static int run_attn_bwd(const bf16_t* qkv, const bf16_t* qkv_bias, const bf16_t*
     attn_bwd_q_kernel<S, HD, WIN><<<grid, 128, smem_q, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse_fwd, lse, dqc, A, G, heads);
     if (lse_fwd != nullptr) lse = const_cast<float*>(lse_fwd);
   }
-  bool kv_done = false;
-  if constexpr (GFAST && (HD == 64 || HD == 80) && (S == 64 || S == 32)) {
-    // key side on tcgen05 / TMEM (attention_bwd_tc.cu); GROVE_BWD_MMA_SYNC=1 keeps the warp-level kernel (A/B measurements, cross-check)
-    static const bool use_mma_sync = []() { const char* e = getenv("GROVE_BWD_MMA_SYNC"); return e && e[0] == '1'; }();
-    if (!use_mma_sync) {
-      float* aux = dqc + M * heads * HD;
-      const int rc = launch_attn_bwd_kv_tc(qkv, dO, rel, lse, Dsum, aux, dqkv, F, G, heads, HD, st);
-      if (rc) return rc;
-      kv_done = true;
-    }
-  }
-  if (!kv_done) attn_bwd_kv_kernel<S, HD, WIN, GFAST><<<grid, 128, smem_kv, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqkv, G, heads);
+  attn_bwd_kv_kernel<S, HD, WIN, GFAST><<<grid, 128, smem_kv, st>>>(qkv, qkv_bias, dO, rel, Dsum, lse, dqkv, G, heads);
   relpos_kernel<S, HD, WIN, 1><<<grid_rel, 256, smem_rel, st>>>(qkv, Rh, Rw, nullptr, A, dqc, dqkv, G, heads);
   grove_count_launch(5);
   GROVE_CHECK_LAUNCH();

@@ -24,7 +24,7 @@ namespace grove {
 
 // qkv / dO: 128-row boxes of the 64-wide main part; *_x: the 16-wide tail of an 80-wide head (SWIZZLE_32B); *_b: the same two with
 // BQ-row boxes (the key-side kernel's query blocks)
-struct BwdKvTmaps { CUtensorMap qkv, dO, relw, relh, aux, qkv_x, dO_x, qkv_b, dO_b, qkv_bx, dO_bx; };
+struct BwdKvTmaps { CUtensorMap qkv, dO, relw, relh, aux, qkv_x, dO_x, qkv_b, dO_b, qkv_bx, dO_bx, rh, rw, rh_x, rw_x; };   // rh / rw: the rel-pos tables (query side)
 
 constexpr int kBwdThreads = 320;
 
@@ -257,27 +257,37 @@ attn_bwd_kv_tc_kernel(const __grid_constant__ BwdKvTmaps tm, __nv_bfloat16* __re
 
 // =====================================================================================================================
 // Query side of the global attention backward on tcgen05: one CTA owns 128 queries of one (frame, head) and sweeps the keys in blocks of 128
-//   MMA1   S = Q_own K_j^T,  dP = dO_own V_j^T               (SS-mode UMMA 128x128x64)
-//   warps  ds = exp2(c S + (rel_w + rel_h) log2e - lse) (dP - D)   -> bf16 dS into tensor memory; the rel-pos bias cotangents
+//   prologue  T_h = Q_own Rh^T, T_w = Q_own Rw^T (UMMA 128 x 2G x HD, the whole rel-pos tables as B) -> the bias rows of the 128 queries:
+//             rel_w[q, kw] = T_w[q, qw-kw+G-1] into registers, rel_h into shared memory (x log2 e), and both, coalesced, into the global
+//             rel [M, heads, 2G] table the key-side kernel reads
+//   MMA1   S = Q_own K_j^T,  dP = dO_own V_j^T               (SS-mode UMMA 128x128xHD)
+//   warps  ds = exp2(c S + (rel_w + rel_h) log2e - lse) (dP - D)   -> scale*ds (bf16) into tensor memory; the rel-pos bias cotangents
 //          A_w[q, kw] += sum_kh ds (registers), A_h[q, kh] = sum_kw ds (one value per thread and chunk, combined through shared memory)
-//   MMA2   dQ += dS K_j                                       (TS-mode UMMA 128x64x128, K_j read MN-major)
-// Outputs in the layout of attn_bwd_q_global_kernel: dq_core = scale dS K (fp32 [M, D]) and A (fp32 [M, heads, 2G]); relpos_kernel<..,1>
-// turns them into d q.  Two threads per query row: thread hs owns the key chunks {hs, hs+2} of every block, i.e. always the same 32 key
-// columns kw (rel_w and A_w live in registers like in the forward kernel).
+//   MMA2   dQ += (scale dS) K_j                               (TS-mode UMMA 128xHDx128, K_j read MN-major)
+//   epilogue  dQ += dT_h Rh + dT_w Rw (SS-mode UMMA 128 x HD x 2G): dT[q, qh-kh+G-1] = A_h[q, kh] is the cotangent of T_h (likewise T_w),
+//             scattered as bf16 into K-major tiles over the retired K / V stages; the tables are re-fetched over the Q / dO tiles.
+//             d q leaves as bf16 straight into the q slot of dqkv.
+// (Round-2 history: the bias rows and the table back-projection were two CUDA-core kernels, relpos_kernel<0/1>, together 1.5 ms per ViT-B
+// layer next to 2.7 ms of attention kernels.)
+// Two threads per query row: thread hs owns the key chunks {hs, hs+2} of every block, i.e. always the same 32 key columns kw.
 // =====================================================================================================================
 template <int G, int HD>
 struct BwdQCfg {
   static constexpr bool kX = HD > 64;
   static constexpr int TS = 16384 + (kX ? 4096 : 0);      // [128 x 64] bf16 (SWIZZLE_128B) [+ 128 x 16 tail, SWIZZLE_32B]
+  static constexpr int kTabMain = 2 * G * 128;            // a rel-pos table as an operand tile: 2G rows (2G-1 real) x HD
+  static constexpr int kTab = kTabMain + (kX ? 2 * G * 32 : 0);
   static constexpr int kRelH = G * 128 * 4;               // rel_h [G][128] fp32
-  static constexpr int kAh = 2 * G * 128 * 4;             // A_h partial sums [2][G][128] fp32
+  static constexpr int kAh = 2 * G * 128 * 4;             // A_h partial sums [2][G][128] fp32; the prologue's [G][129] transpose buffer
+  static constexpr int kDT = (2 * G / 64) * 16384;        // one cotangent tile dT [128][2G] bf16, K-major in 64-column sub-tiles
   static constexpr int kSmem = 2 * TS + 4 * TS + kRelH + kAh + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kTab <= TS && 2 * kDT + (G == 32 ? 32768 : 0) <= 4 * TS && G * 129 * 4 <= kAh, "regions reused by the prologue / epilogue");
 };
 
 template <int G, int HD>
 __global__ void __launch_bounds__(kBwdThreads, 1)
-attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restrict__ rel, const float* __restrict__ lse, const float* __restrict__ dsum,
-                     float* __restrict__ dq_out, float* __restrict__ A_out, int heads) {
+attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, float* __restrict__ rel_out, const float* __restrict__ lse, const float* __restrict__ dsum,
+                     __nv_bfloat16* __restrict__ dqkv, int heads) {
   using C = BwdQCfg<G, HD>;
   constexpr bool kX = C::kX;
   constexpr int TS = C::TS, N = G * G, NB = N / 128;
@@ -287,11 +297,15 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
   const uint32_t sQ = s0, sDO = s0 + TS;
   auto sStage = [&](int s) { return s0 + 2 * TS + (uint32_t)s * (2 * TS); };     // K_j | V_j
   const uint32_t sRelH = s0 + 6 * TS, sAh = sRelH + C::kRelH, bar0 = sAh + C::kAh;
+  const uint32_t sDTh = s0 + 2 * TS, sDTw = sDTh + C::kDT;                         // epilogue: over the K / V stages
   uint8_t* smem_al = smem_raw + (s0 - smem_u32(smem_raw));
   float* relh_s = reinterpret_cast<float*>(smem_al + (sRelH - s0));       // [G][128], x log2 e
   float* ah_s = reinterpret_cast<float*>(smem_al + (sAh - s0));           // [2][G][128]
-  float* xch_s = reinterpret_cast<float*>(smem_al + 2 * TS);              // epilogue scratch over the K/V stages: [2][32][128]
-  enum { OWN_FULL = 0, STAGE_FULL, STAGE_EMPTY = STAGE_FULL + 2, SD_FULL = STAGE_EMPTY + 2, SD_EMPTY, PD_FULL, PD_EMPTY, ACC_FULL, NUM_BARS };
+  float* stg_s = ah_s;                                                    // prologue: [G][129] transpose buffer
+  uint8_t* dt_b = smem_al + 2 * TS;                                       // dT_h | dT_w
+  float* xch_s = reinterpret_cast<float*>(smem_al + 2 * TS + 2 * C::kDT); // G = 32 epilogue exchange: [2][32][128]
+  enum { OWN_FULL = 0, STAGE_FULL, STAGE_EMPTY = STAGE_FULL + 2, SD_FULL = STAGE_EMPTY + 2, SD_EMPTY, PD_FULL, PD_EMPTY, ACC_FULL, TAB_FULL, TAB_FREE,
+         T_FULL, T_READ, DT_FULL, ACC2_FULL, NUM_BARS };
   auto bar = [&](int i) { return bar0 + 8u * i; };
   const uint32_t tmem_slot = bar0 + 8u * NUM_BARS;
 
@@ -305,6 +319,8 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
     mbar_init(bar(OWN_FULL), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(STAGE_FULL + i), 1); mbar_init(bar(STAGE_EMPTY + i), 1); }
     mbar_init(bar(SD_FULL), 1); mbar_init(bar(SD_EMPTY), 8); mbar_init(bar(PD_FULL), 8); mbar_init(bar(PD_EMPTY), 1); mbar_init(bar(ACC_FULL), 1);
+    mbar_init(bar(TAB_FULL), 1); mbar_init(bar(TAB_FREE), 1); mbar_init(bar(T_FULL), 1); mbar_init(bar(T_READ), 8); mbar_init(bar(DT_FULL), 8);
+    mbar_init(bar(ACC2_FULL), 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -318,6 +334,15 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      auto load_tables = [&](uint32_t dst_h, uint32_t dst_w) {           // rows 2G-1.. of the boxes are out of bounds: zero-filled
+        mbar_expect_tx(bar(TAB_FULL), 2 * C::kTab);
+        tma_load_2d(dst_h, &tm.rh, bar(TAB_FULL), 0, 0);
+        tma_load_2d(dst_w, &tm.rw, bar(TAB_FULL), 0, 0);
+        if (kX) {
+          tma_load_2d(dst_h + C::kTabMain, &tm.rh_x, bar(TAB_FULL), 64, 0);
+          tma_load_2d(dst_w + C::kTabMain, &tm.rw_x, bar(TAB_FULL), 64, 0);
+        }
+      };
       mbar_expect_tx(bar(OWN_FULL), 2 * TS);
       tma_load_2d(sQ, &tm.qkv, bar(OWN_FULL), h * HD, tok0 + ib * 128);
       tma_load_2d(sDO, &tm.dO, bar(OWN_FULL), h * HD, tok0 + ib * 128);
@@ -325,8 +350,10 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
         tma_load_2d(sQ + 16384, &tm.qkv_x, bar(OWN_FULL), h * HD + 64, tok0 + ib * 128);
         tma_load_2d(sDO + 16384, &tm.dO_x, bar(OWN_FULL), h * HD + 64, tok0 + ib * 128);
       }
+      load_tables(sStage(1), sStage(1) + TS);                            // the prologue's tables sit in stage 1 until T_h / T_w have retired
       for (int j = 0; j < NB; ++j) {
         const int s = j & 1;
+        if (j == 1) mbar_wait(bar(TAB_FREE), 0);
         mbar_wait(bar(STAGE_EMPTY + s), ((j >> 1) & 1u) ^ 1u);
         mbar_expect_tx(bar(STAGE_FULL + s), 2 * TS);
         tma_load_2d(sStage(s), &tm.qkv, bar(STAGE_FULL + s), D + h * HD, tok0 + j * 128);           // K_j
@@ -336,13 +363,15 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
           tma_load_2d(sStage(s) + TS + 16384, &tm.qkv_x, bar(STAGE_FULL + s), 2 * D + h * HD + 64, tok0 + j * 128);
         }
       }
+      mbar_wait(bar(ACC_FULL), 0);                                       // Q_own / dO_own have served their last product
+      load_tables(sQ, sDO);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= K_j) read MN-major
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_t = umma_idesc_bf16(128, 2 * G);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B read MN-major
     constexpr uint32_t idesc_ox = umma_idesc_bf16(128, 16) | (1u << 16);
-    auto mma2 = [&](int j) {           // dQ += dS K_j
+    auto mma2 = [&](int j) {           // dQ += (scale dS) K_j
       const uint32_t st = sStage(j & 1);
       mbar_wait(bar(PD_FULL), j & 1u);
       tc_fence_after();
@@ -359,6 +388,21 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
       __syncwarp();
     };
     mbar_wait(bar(OWN_FULL), 0);
+    mbar_wait(bar(TAB_FULL), 0);
+    tc_fence_after();
+    if (elect_one()) {                 // T_h -> the S columns, T_w -> the dP columns
+      const uint32_t th = sStage(1), tw = sStage(1) + TS;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc_mma_f16(tS, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(th + k * 32), idesc_t, k != 0);
+      if (kX) tc_mma_f16(tS, umma_desc_sw32(sQ + 16384), umma_desc_sw32(th + C::kTabMain), idesc_t, 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, umma_desc_sw128(sQ + k * 32), umma_desc_sw128(tw + k * 32), idesc_t, k != 0);
+      if (kX) tc_mma_f16(tDP, umma_desc_sw32(sQ + 16384), umma_desc_sw32(tw + C::kTabMain), idesc_t, 1);
+      tc_commit(bar(T_FULL));
+      tc_commit(bar(TAB_FREE));
+    }
+    __syncwarp();
+    mbar_wait(bar(T_READ), 0);
 #pragma unroll 1
     for (int j = 0; j < NB; ++j) {
       const int s = j & 1;
@@ -379,28 +423,79 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
       if (j > 0) mma2(j - 1);
     }
     mma2(NB - 1);
+    // ---- table back-projection: dQ += dT_h Rh + dT_w Rw
+    mbar_wait(bar(DT_FULL), 0);
+    mbar_wait(bar(TAB_FULL), 1);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const uint32_t dt = w == 0 ? sDTh : sDTw, tab = w == 0 ? sQ : sDO;
+#pragma unroll
+        for (int kk = 0; kk < 2 * G / 16; ++kk) {
+          const uint64_t a = umma_desc_sw128(dt + (kk >> 2) * 16384 + (kk & 3) * 32);
+          tc_mma_f16(tDQ, a, umma_desc_sw128(tab + kk * 2048), idesc_o, 1);
+          if (kX) tc_mma_f16(tDQ + 64, a, umma_desc_sw32(tab + C::kTabMain + kk * 512), idesc_ox, 1);
+        }
+      }
+      tc_commit(bar(ACC2_FULL));
+    }
+    __syncwarp();
   } else {
     // ===================== elementwise warps: two threads per query row =====================
     const int quad = warp & 3;
     const int hs = (warp - 2) >> 2;
+    const int wi = warp - 2;
     const int row = quad * 32 + lane;
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
     constexpr float kL2e = 1.4426950408889634f;
     const float c_l2 = kScale * kL2e;
     const int kw_base = ((hs & 1) * 32) % G;             // the 32 key columns this thread sees in every chunk
-    const size_t rh = ((size_t)tok0 + ib * 128 + row) * heads + h;       // (token, head) row of rel / lse / D / A
-    const float* relrow = rel + rh * (2 * G);
-    float relw[32], aw[32];
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(relrow + G + kw_base + j);
-      relw[j] = v.x * kL2e; relw[j + 1] = v.y * kL2e; relw[j + 2] = v.z * kL2e; relw[j + 3] = v.w * kL2e;
-      aw[j] = aw[j + 1] = aw[j + 2] = aw[j + 3] = 0.f;
-    }
-    for (int kh = hs * (G / 2); kh < (hs + 1) * (G / 2); ++kh) relh_s[kh * 128 + row] = relrow[kh] * kL2e;
-    for (int kh = 0; kh < G; ++kh) ah_s[(hs * G + kh) * 128 + row] = 0.f;
+    const int qn = ib * 128 + row, qh = qn / G, qw = qn % G;
+    const size_t rh = ((size_t)tok0 + qn) * heads + h;   // (token, head) row of rel / lse / D
     const float my_lse = lse[rh], my_d = dsum[rh];
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    auto sync256 = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    float relw[32], aw[32];
+    // ---- prologue: the bias rows of the 128 queries from T_w (phase 0) and T_h (phase 1)
+    mbar_wait(bar(T_FULL), 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {
+      const int q0 = ph == 0 ? qw : qh;
+#pragma unroll 1
+      for (int c = hs; c < 2 * G / 32; c += 2) {         // T[q, a] with a = q0 - k + G - 1: scatter to [k][row]
+        uint32_t r[32];
+        tmem_ld_x32((ph == 0 ? tDP : tS) + c * 32 + tlane, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int k = q0 + G - 1 - (c * 32 + jj);
+          if ((unsigned)k < (unsigned)G) stg_s[k * 129 + row] = __uint_as_float(r[jj]);
+        }
+      }
+      if (ph == 1) {                                     // T_h / T_w are out of tensor memory: the first S / dP may overwrite them
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(T_READ));
+      }
+      sync256();
+      if (ph == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { relw[j] = stg_s[(kw_base + j) * 129 + row] * kL2e; aw[j] = 0.f; }
+      } else {
+        for (int kh = hs * (G / 2); kh < (hs + 1) * (G / 2); ++kh) relh_s[kh * 128 + row] = stg_s[kh * 129 + row] * kL2e;
+      }
+      // the key-side kernel reads these rows from the global table: 16 rows per warp, one coalesced row segment per instruction
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = wi * 16 + rr;
+        float* dst = rel_out + (((size_t)tok0 + ib * 128 + r) * heads + h) * (2 * G) + (ph == 0 ? G : 0);
+        if (G == 64) *reinterpret_cast<float2*>(dst + 2 * lane) = make_float2(stg_s[(2 * lane) * 129 + r], stg_s[(2 * lane + 1) * 129 + r]);
+        else dst[lane] = stg_s[lane * 129 + r];
+      }
+      sync256();                                         // the transpose buffer is rewritten by the next phase / zeroed below
+    }
+    for (int kh = 0; kh < G; ++kh) ah_s[(hs * G + kh) * 128 + row] = 0.f;
+    sync256();
 #pragma unroll 1
     for (int j = 0; j < NB; ++j) {
       mbar_wait(bar(SD_FULL), j & 1u);
@@ -429,7 +524,7 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
           const float d0 = p0 * (__uint_as_float(rd[jj]) - my_d), d1 = p1 * (__uint_as_float(rd[jj + 1]) - my_d);
           aw[jj] += d0; aw[jj + 1] += d1;
           asum += d0 + d1;
-          pd[jj >> 1] = pack_bf16(d0, d1);
+          pd[jj >> 1] = pack_bf16(d0 * kScale, d1 * kScale);
         }
         ah_s[(hs * G + kh) * 128 + row] += asum;         // G = 64: the only contribution of this thread to (row, kh); G = 32: likewise
         if (cc == 0 && j > 0) { mbar_wait(bar(PD_EMPTY), (j - 1) & 1u); tc_fence_after(); }
@@ -440,39 +535,52 @@ attn_bwd_q_tc_kernel(const __grid_constant__ BwdKvTmaps tm, const float* __restr
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(PD_FULL));
     }
-    // ---- epilogue
-    mbar_wait(bar(ACC_FULL), 0);                         // every MMA has retired: the K/V stages can serve as scratch
+    // ---- epilogue: the cotangents of T_h / T_w as bf16 operand tiles over the retired K / V stages
+    mbar_wait(bar(ACC_FULL), 0);
+    tc_fence_after();
+    {
+      const int et = wi * 32 + lane;
+      constexpr int kZ = 2 * C::kDT / 256;                // bytes per thread
+#pragma unroll
+      for (int i = 0; i < kZ / 16; ++i) *reinterpret_cast<uint4*>(dt_b + et * kZ + i * 16) = make_uint4(0, 0, 0, 0);
+    }
+    if (G != 64) {                                       // G = 32: both threads saw all 32 columns (different key rows)
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) xch_s[(hs * 32 + jj) * 128 + row] = aw[jj];
+    }
+    sync256();
+    auto dt_put = [&](int tile, int col, float v) {      // dT[row, col] in 64-column sub-tiles of 128-byte rows, SWIZZLE_128B
+      *reinterpret_cast<__nv_bfloat16*>(dt_b + tile * C::kDT + (col >> 6) * 16384 + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4) + (col & 7) * 2) =
+          __float2bfloat16(v);
+    };
+    for (int kh = hs * (G / 2); kh < (hs + 1) * (G / 2); ++kh) dt_put(0, qh + G - 1 - kh, ah_s[kh * 128 + row] + ah_s[(G + kh) * 128 + row]);
+    if (G == 64) {                                       // the two threads of a row own disjoint halves of the key columns
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) dt_put(1, qw + G - 1 - (kw_base + jj), aw[jj]);
+    } else {
+      for (int jj = hs * 16; jj < hs * 16 + 16; ++jj) dt_put(1, qw + G - 1 - jj, xch_s[jj * 128 + row] + xch_s[(32 + jj) * 128 + row]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar(DT_FULL));
+    mbar_wait(bar(ACC2_FULL), 0);
     tc_fence_after();
     {
       uint32_t r[32], rx[8];
       tmem_ld_x32(tDQ + hs * 32 + tlane, r);
       if (kX) tmem_ld_x8(tDQ + 64 + hs * 8 + tlane, rx);
       tmem_ld_wait();
-      float* o = dq_out + ((size_t)tok0 + ib * 128 + row) * D + h * HD;
+      __nv_bfloat16* o = dqkv + ((size_t)tok0 + qn) * (3 * D) + h * HD;
 #pragma unroll
-      for (int jj = 0; jj < 32; jj += 4)
-        *reinterpret_cast<float4*>(o + hs * 32 + jj) = make_float4(__uint_as_float(r[jj]) * kScale, __uint_as_float(r[jj + 1]) * kScale,
-                                                                   __uint_as_float(r[jj + 2]) * kScale, __uint_as_float(r[jj + 3]) * kScale);
-      if (kX) {
-#pragma unroll
-        for (int jj = 0; jj < 8; jj += 4)
-          *reinterpret_cast<float4*>(o + 64 + hs * 8 + jj) = make_float4(__uint_as_float(rx[jj]) * kScale, __uint_as_float(rx[jj + 1]) * kScale,
-                                                                         __uint_as_float(rx[jj + 2]) * kScale, __uint_as_float(rx[jj + 3]) * kScale);
-      }
+      for (int jj = 0; jj < 32; jj += 8)
+        *reinterpret_cast<uint4*>(o + hs * 32 + jj) =
+            make_uint4(pack_bf16(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1])), pack_bf16(__uint_as_float(r[jj + 2]), __uint_as_float(r[jj + 3])),
+                       pack_bf16(__uint_as_float(r[jj + 4]), __uint_as_float(r[jj + 5])), pack_bf16(__uint_as_float(r[jj + 6]), __uint_as_float(r[jj + 7])));
+      if (kX)
+        *reinterpret_cast<uint4*>(o + 64 + hs * 8) =
+            make_uint4(pack_bf16(__uint_as_float(rx[0]), __uint_as_float(rx[1])), pack_bf16(__uint_as_float(rx[2]), __uint_as_float(rx[3])),
+                       pack_bf16(__uint_as_float(rx[4]), __uint_as_float(rx[5])), pack_bf16(__uint_as_float(rx[6]), __uint_as_float(rx[7])));
     }
-    float* arow = A_out + rh * (2 * G);
-    if (G == 64) {                                       // the two threads of a row own disjoint halves of the key columns
-#pragma unroll
-      for (int jj = 0; jj < 32; jj += 4) *reinterpret_cast<float4*>(arow + G + kw_base + jj) = make_float4(aw[jj], aw[jj + 1], aw[jj + 2], aw[jj + 3]);
-    } else {                                             // G = 32: both threads saw all 32 columns (different key rows): sum the two
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) xch_s[(hs * 32 + jj) * 128 + row] = aw[jj];
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");      // A_h partials (and the G = 32 exchange) are complete
-    if (G != 64) {
-      for (int jj = hs * 16; jj < hs * 16 + 16; ++jj) arow[G + jj] = xch_s[jj * 128 + row] + xch_s[(32 + jj) * 128 + row];
-    }
-    for (int kh = hs * (G / 2); kh < (hs + 1) * (G / 2); ++kh) arow[kh] = ah_s[kh * 128 + row] + ah_s[(G + kh) * 128 + row];
   }
   tc_fence_before();
   __syncthreads();
@@ -539,12 +647,12 @@ static int launch_kv(const BwdKvTmaps& tm, void* dqkv, int F, int heads, cudaStr
 }
 
 template <int G, int HD>
-static int launch_q(const BwdKvTmaps& tm, const float* rel, const float* lse, const float* dsum, float* dq_out, float* A_out, int F, int heads, cudaStream_t st) {
+static int launch_q(const BwdKvTmaps& tm, float* rel, const float* lse, const float* dsum, void* dqkv, int F, int heads, cudaStream_t st) {
   constexpr int smem = BwdQCfg<G, HD>::kSmem;
   static_assert(smem <= 232448, "shared memory budget");
   cudaError_t e = cudaFuncSetAttribute(attn_bwd_q_tc_kernel<G, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-  attn_bwd_q_tc_kernel<G, HD><<<dim3(G * G / 128, heads, F), kBwdThreads, smem, st>>>(tm, rel, lse, dsum, dq_out, A_out, heads);
+  attn_bwd_q_tc_kernel<G, HD><<<dim3(G * G / 128, heads, F), kBwdThreads, smem, st>>>(tm, rel, lse, dsum, (__nv_bfloat16*)dqkv, heads);
   return GROVE_OK;
 }
 
@@ -563,6 +671,7 @@ int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, con
   if ((rc = make_tmap_f32_3d(&tm.relw, rel, (uint64_t)2 * G, heads, (uint64_t)M, (uint32_t)G, bq))) return rc;
   if ((rc = make_tmap_f32_3d(&tm.relh, rel, (uint64_t)2 * G, heads, (uint64_t)M, 4, bq))) return rc;
   if ((rc = make_tmap_f32_3d(&tm.aux, aux, 4, heads, (uint64_t)M, 4, bq))) return rc;
+  tm.rh = tm.qkv; tm.rw = tm.qkv; tm.rh_x = tm.qkv; tm.rw_x = tm.qkv;      // unused by this kernel
   if (G == 64) rc = hd == 64 ? launch_kv<64, 64>(tm, dqkv, F, heads, st) : launch_kv<64, 80>(tm, dqkv, F, heads, st);
   else rc = hd == 64 ? launch_kv<32, 64>(tm, dqkv, F, heads, st) : launch_kv<32, 80>(tm, dqkv, F, heads, st);
   if (rc) return rc;
@@ -571,16 +680,25 @@ int launch_attn_bwd_kv_tc(const void* qkv, const void* dO, const float* rel, con
   return GROVE_OK;
 }
 
-// query side (see attn_bwd_q_tc_kernel); same preconditions as launch_attn_bwd_kv_tc
-int launch_attn_bwd_q_tc(const void* qkv, const void* dO, const float* rel, const float* lse, const float* dsum, float* dq_out, float* A_out, int F,
-                         int G, int heads, int hd, cudaStream_t st) {
+// query side (see attn_bwd_q_tc_kernel); same preconditions as launch_attn_bwd_kv_tc.  Rh, Rw: bf16 [2G-1, hd].  Writes the bias rows
+// rel [M, heads, 2G] (fp32, read by the key side) and the q slot of dqkv.
+int launch_attn_bwd_q_tc(const void* qkv, const void* dO, const void* Rh, const void* Rw, float* rel, const float* lse, const float* dsum, void* dqkv,
+                         int F, int G, int heads, int hd, cudaStream_t st) {
   const long long M = (long long)F * G * G;
   BwdKvTmaps tm;
   int rc;
   if ((rc = make_bwd_tmaps(tm, qkv, dO, hd, heads, M, 128))) return rc;
   tm.relw = tm.qkv; tm.relh = tm.qkv; tm.aux = tm.qkv;      // unused by this kernel
-  if (G == 64) rc = hd == 64 ? launch_q<64, 64>(tm, rel, lse, dsum, dq_out, A_out, F, heads, st) : launch_q<64, 80>(tm, rel, lse, dsum, dq_out, A_out, F, heads, st);
-  else rc = hd == 64 ? launch_q<32, 64>(tm, rel, lse, dsum, dq_out, A_out, F, heads, st) : launch_q<32, 80>(tm, rel, lse, dsum, dq_out, A_out, F, heads, st);
+  if ((rc = make_tmap_bf16_2d(&tm.rh, Rh, (uint64_t)hd, (uint64_t)2 * G - 1, 64, 2 * G))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm.rw, Rw, (uint64_t)hd, (uint64_t)2 * G - 1, 64, 2 * G))) return rc;
+  if (hd > 64) {
+    if ((rc = make_tmap_bf16_2d(&tm.rh_x, Rh, (uint64_t)hd, (uint64_t)2 * G - 1, 16, 2 * G))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm.rw_x, Rw, (uint64_t)hd, (uint64_t)2 * G - 1, 16, 2 * G))) return rc;
+  } else {
+    tm.rh_x = tm.rh; tm.rw_x = tm.rw;
+  }
+  if (G == 64) rc = hd == 64 ? launch_q<64, 64>(tm, rel, lse, dsum, dqkv, F, heads, st) : launch_q<64, 80>(tm, rel, lse, dsum, dqkv, F, heads, st);
+  else rc = hd == 64 ? launch_q<32, 64>(tm, rel, lse, dsum, dqkv, F, heads, st) : launch_q<32, 80>(tm, rel, lse, dsum, dqkv, F, heads, st);
   if (rc) return rc;
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
