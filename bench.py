@@ -579,11 +579,16 @@ def _bench_config4(gh, dev, world, dist, parallel, g, frames=32, img=512, steps=
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     e0.record()
-    for _ in range(steps):
+    evs[0].record()
+    for i in range(steps):
         losses, _, grads = step()
+        evs[i + 1].record()
     e1.record()
     torch.cuda.synchronize()
+    if os.environ.get("GROVE_BENCH_DEBUG"):
+        print("config4 per-step ms:", [round(evs[i].elapsed_time(evs[i + 1]), 1) for i in range(steps)], file=sys.stderr)
     ms = _max_over_ranks(e0.elapsed_time(e1), dev, world, dist) / steps
     trainable = sum(t.numel() for t in grads.g.values())
     return {"workload": f"training step of the grounding branch (forward + backward, GIoU + L1 + objectness), SAM ViT-H, 1 clip x {frames} frames at "

@@ -1,6 +1,7 @@
 // Backward of the WINDOWED attention (14x14 windows, decomposed rel-pos bias) on tcgen05 / TMEM / TMA: image_encoder.py:243-259 window
 // path, 301-326, 329-384, 420-458 under autograd; the blocks are frozen (train.py:254-255), so only d(qkv) is produced.  Replaces the
-// four warp-level launches of attention_bwd.cu (relpos_kernel<0>, attn_bwd_q_kernel, attn_bwd_kv_kernel, relpos_kernel<1>) for head dim 64.
+// four warp-level launches of attention_bwd.cu (relpos_kernel<0>, attn_bwd_q_kernel, attn_bwd_kv_kernel, relpos_kernel<1>) for head dims 64 and 80
+// (80 = 64 + a 16-wide tail: SWIZZLE_32B operand tiles, one extra k-step / one extra N = 16 product per UMMA group).
 //
 //   S[q,k] = scale q.k + q.Rh[qh-kh+13] + q.Rw[qw-kw+13],  P = exp(S - lse_q),  dP = dO V^T,  dS = P (dP - D_q)
 //   dQ = scale dS K + sum_c A[q,c] R[idx(q,c)]  (A_h[q,kh] = sum_kw dS, A_w[q,kw] = sum_kh dS),  dK = scale dS^T Q,  dV = P^T dO
@@ -17,8 +18,8 @@
 //     S^T = K_t Q^T, dP^T = V_t dO^T (128x208x64) -> P^T, dS^T (bf16) back into tensor memory (bias / lse / D from the shared table)
 //     dV = P^T dO, dK = dS^T Q  (TS-mode, 128x64x208)
 // Warp roles: 0 TMA producer, 1 MMA issuer, 2-9 elementwise (two threads per row: columns [0,112) | [112,208)), 10 pad-token fixer.
-// TMEM: S | dP | T/dQ/dV = 208 + 208 + 64 columns; packed bf16 results overwrite the fp32 columns their own thread has already read
-// (thread 0 ascending into [0,56), thread 1 descending into [160,208)), which leaves [64,128) of the S region free for dK.
+// TMEM: S | dP | T/dQ/dV = 208 + 208 + HD columns; packed bf16 results overwrite the fp32 columns their own thread has already read
+// (thread 0 ascending into [0,56), thread 1 descending into [160,208)), which leaves [64, 64 + HD) of the S region free for dK.
 #include <cuda.h>
 
 #include "common.cuh"

@@ -307,8 +307,12 @@ int grove_batch_sum_bf16(const void* x, float* out, int B, long long n, grove_st
 long long grove_attn_relpos_bwd_workspace_bytes(int F, int G, int heads, int hd, int ws);
 int grove_attn_relpos_bwd(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, const void* att,
                           const void* datt, void* dqkv, void* workspace, int F, int G, int heads, int hd, int ws, grove_stream_t stream);
-/* Same with the forward kernel's log-sum-exp (grove_attn_global_relpos_fwd_lse; fp32 [F*G*G, heads], may be NULL): global layers on
- * 32x32 / 64x64 grids then take a single key sweep with the rel-pos terms in registers instead of recomputing the row statistics. */
+/* Same with the forward kernel's log-sum-exp (grove_attn_global_relpos_fwd_lse / grove_attn_window_relpos_tc_fwd_lse; fp32
+ * [F*G*G, heads], log2 domain, may be NULL).  With it the backward runs on tcgen05 / TMEM: global layers on 32x32 / 64x64 grids as a
+ * query-side and a key-side kernel (attention_bwd_tc.cu; the query side also computes the bias rows and back-projects the bias
+ * cotangents through the rel-pos tables), windowed layers as one persistent kernel over (frame, window, head) units
+ * (attention_win_bwd_tc.cu); head dims 64 and 80.  Without it (or on 16x16 grids) the warp-level kernels of attention_bwd.cu run.
+ * rel_pos_h / rel_pos_w must then be 16-byte aligned (TMA). */
 int grove_attn_relpos_bwd_lse(const void* qkv, const void* qkv_bias_bf16, const void* rel_pos_h, const void* rel_pos_w, const void* att,
                               const void* datt, void* dqkv, void* workspace, const float* lse_fwd, int F, int G, int heads, int hd, int ws,
                               grove_stream_t stream);
