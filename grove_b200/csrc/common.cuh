@@ -307,6 +307,17 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank)
       : "memory");
 }
+// The same without release semantics, for hand-offs that publish NO memory: an epilogue warp telling the MMA warp of the pair's leader that
+// its tcgen05.ld reads of an accumulator have completed (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order those).  The .release
+// form compiles to MEMBAR.ALL.CTA + ERRBAR, which waits for every global store and prefetch load the warp has in flight -- ~12 % of the
+// epilogue warps' stall samples on the K = 768 residual GEMM (profiles/r2_gemm_proj_summary.txt).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),

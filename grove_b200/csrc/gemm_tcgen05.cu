@@ -264,10 +264,17 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
     const uint32_t stg = epi_base + (warp - 2) * (32 * Cfg::kStageRowF * 4);
     constexpr int kPasses = BN / 2 / 32;
     uint32_t tile_it = 0;
-    if constexpr (EPI == 1 || EPI == 2 || EPI == 5 || EPI == 6 || EPI == 7) {
+    if constexpr (EPI == 1 || EPI == 2 || EPI == 5 || EPI == 6 || EPI == 7 || EPI == 8) {
       constexpr bool kFold = EPI == 5 || EPI == 6;         // LayerNorm of the A rows folded in (see GemmParams::ln_stats)
       constexpr bool kGelu = EPI == 2 || EPI == 6;
       constexpr bool kDact = EPI == 7;                     // out = (acc + bias) * gelu'(pre): the fc2 input gradient (backward of the MLP's GELU)
+      // EPI = 8: out = bf16(resid_bf16 + gate * relu?(acc + bias)) -- the bf16 residual-stream form of EPI = 4 in the lane = row layout of
+      // this block (no fp32 staging, no shuffles for the row statistics: a thread owns its row's 128 columns of the tile)
+      constexpr bool kRes = EPI == 8;
+      constexpr bool kSide = kDact || kRes;                // a bf16 [M, N] side input fetched coalesced, one pass ahead
+      const __nv_bfloat16* const side = kRes ? p.resid16 : p.dact_pre;
+      const float2 gate2 = make_float2(gate, gate);
+      const float relu_floor = (kRes && p.act == 2) ? 0.f : -INFINITY;
       // ---- bf16 output, bias, optional GELU.  Per warp and pass: one tcgen05.ld of 32 rows x 32 columns (lane = row), bias +
       // activation in registers, pack to bf16, stage 32 rows x 64 B through an XOR-swizzled (conflict-free both ways) private
       // buffer, then 8 rows x 64 B per store instruction.  The accumulator is released right after the last tcgen05.ld.
@@ -279,13 +286,15 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
       auto pre_ptr = [&](int tile_, int ps_, int i_) {
         const int m_blk_ = (p.m_blk0 + tile_ / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk_ = tile_ % p.num_n_blocks;
         const int row_ = min(m_blk_ * BM + quad * 32 + 8 * i_ + (lane >> 2), p.M - 1);
-        return p.dact_pre + (size_t)row_ * p.N + n_blk_ * BN + half * (BN / 2) + ps_ * 32 + (lane & 3) * 8;
+        return side + (size_t)row_ * p.N + n_blk_ * BN + half * (BN / 2) + ps_ * 32 + (lane & 3) * 8;
       };
-      uint4 preg[4];
-      if (kDact && tile0 < num_tiles) {
+      // fetched TWO passes ahead (a pass is ~1k clk, an HBM access under load ~2k): preg = the coming pass, preg2 = the one after
+      uint4 preg[4], preg2[4];
+      if (kSide && tile0 < num_tiles) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) preg[i] = *reinterpret_cast<const uint4*>(pre_ptr(tile0, 0, i));
+        for (int i = 0; i < 4; ++i) { preg[i] = *reinterpret_cast<const uint4*>(pre_ptr(tile0, 0, i)); preg2[i] = *reinterpret_cast<const uint4*>(pre_ptr(tile0, 1, i)); }
       }
+      static_assert(!kSide || kPasses >= 2, "two-pass look-ahead");
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tile_it) {
         const int m_blk = (p.m_blk0 + tile / p.num_n_blocks) * CTAS + (int)cta_rank, n_blk = tile % p.num_n_blocks;
         const uint32_t acc = tile_it & 1u, acc_ph = (tile_it >> 1) & 1u;
@@ -311,27 +320,30 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
         __syncwarp();
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
+        float st_s = 0.f, st_q = 0.f;                      // kRes + ln_stats_out: sum / sum of squares of this thread's row (rounded values)
 #pragma unroll 1
         for (int ps = 0; ps < kPasses; ++ps) {
-          if (kDact) {
+          if (kSide) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rl = 8 * i + (lane >> 2);
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(pre_s + rl * 64 + (((lane & 3) ^ ((rl >> 1) & 3)) << 4)), "r"(preg[i].x), "r"(preg[i].y),
                            "r"(preg[i].z), "r"(preg[i].w) : "memory");
             }
-            const bool last = ps == kPasses - 1;
-            const int ntile = last ? tile + tile_step : tile;
+            const bool wrap = ps + 2 >= kPasses;           // pass ps + 2 belongs to the next tile
+            const int ntile = wrap ? tile + tile_step : tile;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) preg[i] = preg2[i];
             if (ntile < num_tiles) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) preg[i] = *reinterpret_cast<const uint4*>(pre_ptr(ntile, last ? 0 : ps + 1, i));
+              for (int i = 0; i < 4; ++i) preg2[i] = *reinterpret_cast<const uint4*>(pre_ptr(ntile, wrap ? ps + 2 - kPasses : ps + 2, i));
             }
           }
           uint32_t r0[32];
           tmem_ld_32x32b_x32(tmem_base + acc * BN + half * (BN / 2) + ps * 32 + ((uint32_t)(quad * 32) << 16), r0);
           tmem_ld_wait();
           uint32_t pu[16];
-          if (kDact) {                                     // lane = row: its 32 pre-activations
+          if (kSide) {                                     // lane = row: its 32 pre-activations / residual values
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -342,7 +354,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (CTAS == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+              if (CTAS == 2) mbar_arrive_cluster_relaxed(tempty_bar(acc), 0);
               else mbar_arrive(tempty_bar(acc));
             }
           }
@@ -369,9 +381,20 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
               v01 = __fmul2_rn(v01, gelu_grad_fast2(unpack_bf16(pu[j >> 1])));
               v23 = __fmul2_rn(v23, gelu_grad_fast2(unpack_bf16(pu[(j >> 1) + 1])));
             }
+            if (kRes) {
+              v01 = make_float2(fmaxf(v01.x, relu_floor), fmaxf(v01.y, relu_floor));
+              v23 = make_float2(fmaxf(v23.x, relu_floor), fmaxf(v23.y, relu_floor));
+              v01 = __ffma2_rn(v01, gate2, unpack_bf16(pu[j >> 1]));
+              v23 = __ffma2_rn(v23, gate2, unpack_bf16(pu[(j >> 1) + 1]));
+            }
             const float v0 = v01.x, v1 = v01.y, v2 = v23.x, v3 = v23.y;
             pk[j >> 1] = pack_bf16(v0, v1);
             pk[(j >> 1) + 1] = pack_bf16(v2, v3);
+            if (kRes) {                                    // statistics of the ROUNDED values: what the consuming GEMM reads
+              const float2 q01 = unpack_bf16(pk[j >> 1]), q23 = unpack_bf16(pk[(j >> 1) + 1]);
+              st_s += (q01.x + q01.y) + (q23.x + q23.y);
+              st_q = fmaf(q01.x, q01.x, fmaf(q01.y, q01.y, fmaf(q23.x, q23.x, fmaf(q23.y, q23.y, st_q))));
+            }
           }
           // lane = row: four 16-byte chunks (8 columns each), chunk c stored at position c ^ ((row >> 1) & 3) of the 64-byte row
           const uint32_t wrow = stg + lane * 64;
@@ -392,6 +415,8 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
           }
           __syncwarp();                                    // staging is rewritten by the next pass
         }
+        if (kRes && p.ln_stats_out && row_base + lane < p.M)
+          reinterpret_cast<float2*>(p.ln_stats_out)[(size_t)(row_base + lane) * (2 * p.num_n_blocks) + n_blk * 2 + half] = make_float2(st_s, st_q);
       }
     } else if constexpr (EPI == 3) {
       // ---- fp32 output = resid + gate * act(acc + bias) (+ bf16 copy): the residual-stream GEMMs (proj, fc2, Conv3d adapter).
@@ -432,7 +457,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
               tc_fence_before();
               __syncwarp();
               if (lane == 0) {
-                if (CTAS == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+                if (CTAS == 2) mbar_arrive_cluster_relaxed(tempty_bar(acc), 0);
                 else mbar_arrive(tempty_bar(acc));
               }
             }
@@ -514,7 +539,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
               tc_fence_before();
               __syncwarp();
               if (lane == 0) {
-                if (CTAS == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+                if (CTAS == 2) mbar_arrive_cluster_relaxed(tempty_bar(acc), 0);
                 else mbar_arrive(tempty_bar(acc));
               }
             }
@@ -728,7 +753,7 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CTAS == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+        if (CTAS == 2) mbar_arrive_cluster_relaxed(tempty_bar(acc), 0);
         else mbar_arrive(tempty_bar(acc));
       }
     }
@@ -839,6 +864,10 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& ta, const CUtenso
   return GROVE_OK;
 }
 
+static bool epi4_staged() {   // GROVE_GEMM_EPI4=1: the fp32-staged bf16 residual epilogue (EPI = 4) instead of the lane = row form (EPI = 8); A/B measurements
+  static const bool v = []() { const char* e = getenv("GROVE_GEMM_EPI4"); return e && e[0] == '1'; }();
+  return v;
+}
 static bool tail_split_disabled() {   // GROVE_GEMM_NO_TAIL_SPLIT=1 (A/B measurements)
   static int v = -1;
   if (v < 0) v = getenv("GROVE_GEMM_NO_TAIL_SPLIT") != nullptr;
@@ -985,7 +1014,8 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
       if (s >= 2 && t < p.num_m_blocks && need <= workspace_bytes) {
         GemmParams pa = p;
         pa.num_m_blocks = p.num_m_blocks - t;
-        int rc = resid_b16 ? launch_gemm<256, 2, 4>(pa, ta, tb, max_ctas, st) : launch_gemm<256, 2, 3>(pa, ta, tb, max_ctas, st);
+        int rc = resid_b16 ? (epi4_staged() ? launch_gemm<256, 2, 4>(pa, ta, tb, max_ctas, st) : launch_gemm<256, 2, 8>(pa, ta, tb, max_ctas, st))
+                           : launch_gemm<256, 2, 3>(pa, ta, tb, max_ctas, st);
         if (rc) return rc;
         GemmParams pb = p;
         pb.m_blk0 = p.num_m_blocks - t; pb.num_m_blocks = t;
@@ -1010,7 +1040,8 @@ static int dispatch_gemm(GemmParams& p, const void* A_or_X, const void* W, int K
         return GROVE_OK;
       }
     }
-    return resid_b16 ? launch_gemm<256, 2, 4>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 3>(p, ta, tb, max_ctas, st);
+    if (resid_b16) return epi4_staged() ? launch_gemm<256, 2, 4>(p, ta, tb, max_ctas, st) : launch_gemm<256, 2, 8>(p, ta, tb, max_ctas, st);
+    return launch_gemm<256, 2, 3>(p, ta, tb, max_ctas, st);
   }
   if (ctas == 2) return launch_gemm<256, 2>(p, ta, tb, max_ctas, st);
   return BN == 256 ? launch_gemm<256, 1>(p, ta, tb, max_ctas, st) : launch_gemm<128, 1>(p, ta, tb, max_ctas, st);

@@ -14,7 +14,11 @@ a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
 w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
 bias = torch.randn(N, device="cuda")
 for _ in range(4):
-    if kind == "res":
+    if kind == "res16":                                  # bf16 residual stream + row statistics (EPI = 8; GROVE_GEMM_EPI4=1: EPI = 4)
+        xs = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+        stats = torch.empty(M, N // 128, 2, device="cuda")
+        ops.gemm(a, w, xs, bias=bias, resid=xs, ln_stats_out=stats, force_ctas=fc)
+    elif kind == "res":
         out = torch.randn(M, N, device="cuda")
         ops.gemm(a, w, out, bias=bias, resid=out, force_ctas=fc)
     else:
