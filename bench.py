@@ -25,10 +25,13 @@ import torch  # noqa: E402
 IMG, FRAMES, PHRASES, SEQ_L, VIT = 1024, 8, 4, 640, "vit_b"
 VIDEOS = 1   # videos per GPU per step (config 3: 2)
 METRIC, UNIT = "grounding_path_frames_per_s", "frames/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch of the dominant kernel (qkv GEMM, M=32768 N=2304 K=768),
-# from the `ncu --set full` capture summarised in profiles/r1_ncu_full_summary.txt (algorithmic bytes of that launch: 205 MB)
-NCU_TRAFFIC_BYTES = 152701696
-NCU_TRAFFIC_NOTE = "qkv GEMM launch (M=32768,N=2304,K=768): 53.9 MB read + 98.8 MB written vs 205 MB algorithmic (profiles/r1_ncu_full_summary.txt)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch of the dominant kernel: the residual-stream GEMM form that takes
+# 38 % of the step (proj, M=32768 N=768 K=768, bf16 residual + row statistics, EPI=8), from the round-2 `ncu --set full` capture summarised in
+# profiles/r2_gemm_proj_summary.txt.  Algorithmic bytes of that launch: A 50.3 + residual 50.3 + output 50.3 + W 1.2 + statistics 1.6 = 153.7 MB;
+# the 126 MB L2 still holds most of the 50 MB output when the kernel ends, hence the small write figure.
+NCU_TRAFFIC_BYTES = 101887488 + 10890752
+NCU_TRAFFIC_NOTE = ("proj GEMM launch (M=32768,N=768,K=768, bf16 residual stream): 101.9 MB read + 10.9 MB written vs 153.7 MB algorithmic "
+                    "(output still dirty in L2 at kernel end; profiles/r2_gemm_proj_summary.txt)")
 
 
 def useful_flops_per_frame(D, depth, n_glob, G):
