@@ -423,7 +423,11 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
           float2 p;
           // 3 pairs in 8 take the packed FMA-pipe polynomial (10 issue slots per pair), the rest the MUFU (2 slots, 16 XU clocks per pair):
           // balances the sub-partition's issue port against its 4-lane-per-clock exponential unit
-          if (((j >> 1) & 7) == 1 || ((j >> 1) & 7) == 4 || ((j >> 1) & 7) == 6) {
+#ifndef GROVE_ATT_POLY
+#define GROVE_ATT_POLY 0x52                               /* bit i: pair i of every 8 takes the polynomial (pairs 1, 4, 6).  Measured, 8 x 12 x 4096^2: */
+                                                          /* 0x00 (all MUFU) 779 us, 0x12 745, 0x52 719, 0x5A 727-733; four row-sum chains: no change  */
+#endif
+          if ((GROVE_ATT_POLY >> ((j >> 1) & 7)) & 1) {
             p = ex2_fma2(e);
           } else {
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p.x) : "f"(e.x));

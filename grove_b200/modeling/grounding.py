@@ -235,7 +235,7 @@ class GroundingBranch(nn.Module):
         ge = self.grounding_encoder
         dev = images.device
         T = self.config.num_frames
-        grads = GradStore()
+        grads = GradStore(getattr(self, "_grad_arena_elems", 0), next(self.parameters()).device)
         # ---- forward
         emb_tok, enc_tape = encode_train(ge.image_encoder, images)
         V, L, Hd = last_hidden_state.shape
@@ -321,6 +321,7 @@ class GroundingBranch(nn.Module):
             reducer.finish()
         if apply:
             grads.apply(upstream)
+        self._grad_arena_elems = grads.elems                        # the next step's accumulators are views of one zero-filled buffer
         return losses, d_hidden.view(V, L, Hd), grads
 
     def grounding_loss(self, images, last_hidden_state, det_token_mask, gt_bboxes_list, gt_temp_objectness_list):
