@@ -30,35 +30,6 @@ __device__ long long g_att_probe[8192];
 #define PROBE(slot) do { } while (0)
 #endif
 
-// 2^x for x <= 0 on the FMA pipe (Cody-Waite split with the 1.5 * 2^23 rounding constant, degree-3 minimax of 2^f on [-0.5, 0.5],
-// exponent patched in with an integer add): relative error 2.8e-4, well inside the bf16 rounding of P.  The softmax is bound by
-// the 16 ex2/clk/SM MUFU rate, so one exponential in four is computed here instead (the FlashAttention-4 trick).
-__device__ __forceinline__ float ex2_fma(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(f, 0.0565415754f, 0.242068237f);
-  p = fmaf(p, f, 0.692983806f);
-  p = fmaf(p, f, 0.999953968f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
-// The same polynomial on two values at once with Blackwell's packed fp32 pipe (FFMA2 / FADD2): 10 issue slots per PAIR.  The softmax warps
-// are issue-bound (one instruction per clock per SM sub-partition), so everything per-element in the loops below is written on float2:
-// scale*S + rel_w is one FFMA2 per two scores, the running maximum one FMNMX3, the offset add and the row-sum one FADD2 each.
-__device__ __forceinline__ float2 ex2_fma2(float2 x) {
-  x.x = fmaxf(x.x, -125.0f);
-  x.y = fmaxf(x.y, -125.0f);
-  const float2 kMagic = make_float2(12582912.0f, 12582912.0f);
-  const float2 t = __fadd2_rn(x, kMagic);
-  const float2 u = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = __ffma2_rn(u, make_float2(-1.0f, -1.0f), x);
-  float2 p = __ffma2_rn(f, make_float2(0.0565415754f, 0.0565415754f), make_float2(0.242068237f, 0.242068237f));
-  p = __ffma2_rn(p, f, make_float2(0.692983806f, 0.692983806f));
-  p = __ffma2_rn(p, f, make_float2(0.999953968f, 0.999953968f));
-  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
-                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
-}
 
 // warp 0 TMA, warp 1 MMA, then 4 * SPLIT softmax warps: SPLIT threads per query row (= TMEM lane), each owning 128 / SPLIT keys of a block
 template <int SPLIT> constexpr int att_threads() { return 64 + 128 * SPLIT; }

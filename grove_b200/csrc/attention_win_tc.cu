@@ -67,26 +67,68 @@ __device__ __forceinline__ float win_softmax_tile(uint32_t tS, uint32_t tlane, c
   }
   tmem_ld_wait();
   float mx = -INFINITY;
+#ifndef GROVE_WIN_SCALAR
+  // packed fp32 (FFMA2 / FADD2 / FMNMX3): the softmax warps are issue-bound here (computing exponentials on the FMA pipe instead of the
+  // MUFU, i.e. MORE instructions, measured 123 -> 134-145 us per layer), so every per-element step works on a pair of keys.  A pair
+  // (k, k+1) with k even never straddles a window row (14 is even): one rel_h value, one rel_w pair.
+  const float2 c2 = make_float2(c_scale, c_scale);
+  float mx1 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NK; k += 2) {   // local key k -> window row k/14 (relh is already offset to this thread's first key row), column k%14
+    float2 v = __ffma2_rn(make_float2(__uint_as_float(s[k]), __uint_as_float(s[k + 1])), c2, make_float2(relh[k / kWS], relh[k / kWS]));
+    v = __fadd2_rn(v, make_float2(relw[k % kWS], relw[k % kWS + 1]));
+    s[k] = __float_as_uint(v.x); s[k + 1] = __float_as_uint(v.y);
+    if (k & 2) mx1 = fmaxf(mx1, fmaxf(v.x, v.y));
+    else mx = fmaxf(mx, fmaxf(v.x, v.y));
+  }
+  mx = fmaxf(mx, mx1);
+#else
 #pragma unroll
   for (int k = 0; k < NK; ++k) {   // local key k -> window row k/14 (relh is already offset to this thread's first key row), column k%14
     const float v = fmaf(__uint_as_float(s[k]), c_scale, relh[k / kWS]) + relw[k % kWS];
     s[k] = __float_as_uint(v);
     mx = fmaxf(mx, v);
   }
+#endif
   xch_max[HS * 128 + row] = mx;
   asm volatile("bar.sync 1, 256;" ::: "memory");   // also orders: both threads of the row have read S before P overwrites it
   mx = fmaxf(mx, xch_max[(HS ^ 1) * 128 + row]);
   row_max = mx;
   float lsum = 0.f;
+#ifndef GROVE_WIN_SCALAR
+  float2 lsum2 = make_float2(0.f, 0.f);
+  const float2 nmx2 = make_float2(-mx, -mx);
+#endif
   uint32_t pk[56];
 #pragma unroll
+#ifndef GROVE_WIN_POLY
+#define GROVE_WIN_POLY 0x00                               /* bit i: pair i of every 8 computes 2^x on the FMA pipe (ex2_fma2) instead of the MUFU */
+#endif
   for (int k = 0; k < NK; k += 2) {
     float p0, p1;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(__uint_as_float(s[k]) - mx));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(__uint_as_float(s[k + 1]) - mx));
+    if ((GROVE_WIN_POLY >> ((k >> 1) & 7)) & 1) {
+      const float2 pp = ex2_fma2(make_float2(__uint_as_float(s[k]) - mx, __uint_as_float(s[k + 1]) - mx));
+      p0 = pp.x; p1 = pp.y;
+    } else {
+#ifndef GROVE_WIN_SCALAR
+      const float2 e = __fadd2_rn(make_float2(__uint_as_float(s[k]), __uint_as_float(s[k + 1])), nmx2);
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(e.x));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(e.y));
+#else
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(__uint_as_float(s[k]) - mx));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(__uint_as_float(s[k + 1]) - mx));
+#endif
+    }
+#ifndef GROVE_WIN_SCALAR
+    lsum2 = __fadd2_rn(lsum2, make_float2(p0, p1));
+#else
     lsum += p0 + p1;
+#endif
     pk[k >> 1] = pack_bf16(p0, p1);
   }
+#ifndef GROVE_WIN_SCALAR
+  lsum = lsum2.x + lsum2.y;
+#endif
   if (HS == 0) {     // keys 0..111 -> packed columns 0..55
     tmem_st_x32(tS + 0 + tlane, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
     tmem_st_x16(tS + 32 + tlane, reinterpret_cast<const uint32_t(&)[16]>(pk[32]));
