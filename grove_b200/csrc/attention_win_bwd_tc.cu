@@ -30,7 +30,9 @@ namespace grove {
 
 constexpr int kWbThreads = 352;
 constexpr int kBS = 14, kBQ = 196, kBK = 208;   // window side, tokens, tokens padded to 13 UMMA k-steps
-constexpr int kRelStride = 29;                  // shared table row: 14 rel_h (x log2 e, - lse) | 14 rel_w (x log2 e) | D
+// shared bias table of a unit, TRANSPOSED: row c (0..13: rel_h of key row c, x log2 e, - lse; 14..27: rel_w of key column c - 14, x log2 e;
+// 28: -D), one float per query, so a key-pass thread (fixed kh, kw) reads four consecutive queries with one 16-byte load per row
+constexpr int kRelRows = 29, kRelStride = 212;
 
 struct WinBwdTmaps { CUtensorMap qkv, dO, rh, rw, qkv_x, dO_x, rh_x, rw_x; };   // _x: the 16-wide tail of an 80-wide head (SWIZZLE_32B)
 
@@ -50,7 +52,7 @@ struct WinBwdCfg {
   static constexpr int kMain = kBK * 128, kOp = kMain + (kX ? 7 * 1024 : 0);
   static constexpr int kTabMain = 64 * 128, kTab = kTabMain + (kX ? 64 * 32 : 0);
   static constexpr int kDT = 128 * 128, kStage = 128 * 64 * 4;
-  static constexpr int kRel = (kBK * kRelStride * 4 + 1023) / 1024 * 1024;
+  static constexpr int kRel = (kRelRows * kRelStride * 4 + 1023) / 1024 * 1024;
   static constexpr int kXch = 2 * 7 * 128 * 4;
   static constexpr int kTx = 4 * (kBQ * 128 + (kX ? kBQ * 32 : 0));     // bytes the window boxes of Q, K, V, dO deliver
   static constexpr int kSmem = 4 * kOp + kTab + kDT + kStage + kRel + kXch + 1024 /*align*/ + 512 /*barriers*/;
@@ -72,57 +74,66 @@ __device__ __forceinline__ float wb_ex2(float x) {
   return y;
 }
 
-// query pass, one chunk of W key columns starting at key BASE; relh[i] belongs to key row KH0 + i.  scale*dS -> columns PCOL.. of the dP region
+// query pass, one chunk of W key columns starting at key BASE; relh[i] belongs to key row KH0 + i.  scale*dS -> columns PCOL.. of the dP region.
+// Packed fp32 throughout (the elementwise warps are issue-bound): a pair of keys (k, k+1), k even, never straddles a window row, so it takes
+// one rel_h value and one rel_w pair; the A_h / A_w sums are float2 accumulators (A_h folded at the end).
 template <int BASE, int W, int PCOL, int KH0>
 __device__ __forceinline__ void wb_q_chunk(uint32_t tS, uint32_t tDP, uint32_t tlane, const float (&relh)[8], const float (&relw)[14], float c_l2, float scale,
-                                           float my_d, float (&ah)[8], float (&aw)[14]) {
+                                           float my_d, float2 (&ah2)[8], float2 (&aw2)[7]) {
   uint32_t rs[W], rd[W], pd[W / 2];
   wb_ld<W>(tS + BASE + tlane, rs);
   wb_ld<W>(tDP + BASE + tlane, rd);
   tmem_ld_wait();
+  const float2 c2 = make_float2(c_l2, c_l2), nd2 = make_float2(-my_d, -my_d), sc2 = make_float2(scale, scale);
 #pragma unroll
   for (int j = 0; j < W; j += 2) {
-    float ds[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int k = BASE + j + e;
-      if (k < kBQ) {
-        const int kh = k / kBS - KH0, kw = k % kBS;
-        const float p = wb_ex2(fmaf(__uint_as_float(rs[j + e]), c_l2, relh[kh]) + relw[kw]);
-        ds[e] = p * (__uint_as_float(rd[j + e]) - my_d);
-        ah[kh] += ds[e];
-        aw[kw] += ds[e];
-      } else {
-        ds[e] = 0.f;                                     // keys 196..207 do not exist
-      }
+    const int k = BASE + j;
+    if (k < kBQ) {
+      const int kh = k / kBS - KH0, kw = k % kBS;
+      float2 v = __ffma2_rn(make_float2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), c2, make_float2(relh[kh], relh[kh]));
+      v = __fadd2_rn(v, make_float2(relw[kw], relw[kw + 1]));
+      const float2 p = make_float2(wb_ex2(v.x), wb_ex2(v.y));
+      const float2 ds = __fmul2_rn(p, __fadd2_rn(make_float2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), nd2));
+      ah2[kh] = __fadd2_rn(ah2[kh], ds);
+      aw2[kw >> 1] = __fadd2_rn(aw2[kw >> 1], ds);
+      const float2 o = __fmul2_rn(ds, sc2);
+      pd[j >> 1] = pack_bf16(o.x, o.y);
+    } else {
+      pd[j >> 1] = 0u;                                   // keys 196..207 do not exist
     }
-    pd[j >> 1] = pack_bf16(ds[0] * scale, ds[1] * scale);
   }
   wb_st<W / 2>(tDP + PCOL + tlane, pd);
 }
 
 // key pass, one chunk of W query columns starting at query BASE.  P^T -> the S region, dS^T -> the dP region, columns PCOL..
+// ph / pw / pd: this thread's rel_h row, rel_w row and the -D row of the transposed bias table (four queries per 16-byte load)
 template <int BASE, int W, int PCOL>
-__device__ __forceinline__ void wb_k_chunk(uint32_t tS, uint32_t tDP, uint32_t tlane, const float* rel_kh, const float* rel_kw, const float* rel_d, float c_l2) {
+__device__ __forceinline__ void wb_k_chunk(uint32_t tS, uint32_t tDP, uint32_t tlane, const float* ph, const float* pw, const float* pdn, float c_l2) {
   uint32_t rs[W], rd[W], pp[W / 2], pd[W / 2];
   wb_ld<W>(tS + BASE + tlane, rs);
   wb_ld<W>(tDP + BASE + tlane, rd);
   tmem_ld_wait();
+  const float2 c2 = make_float2(c_l2, c_l2);
 #pragma unroll
-  for (int j = 0; j < W; j += 2) {
-    float p[2], ds[2];
+  for (int j = 0; j < W; j += 4) {
+    const int q = BASE + j;
+    if (q < kBQ) {                                       // 196 is a multiple of four: a group never straddles the end
+      const float4 h4 = *reinterpret_cast<const float4*>(ph + q), w4 = *reinterpret_cast<const float4*>(pw + q);
+      const float4 d4 = *reinterpret_cast<const float4*>(pdn + q);
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int q = BASE + j + e;
-      if (q < kBQ) {
-        p[e] = wb_ex2(fmaf(__uint_as_float(rs[j + e]), c_l2, rel_kh[q * kRelStride] + rel_kw[q * kRelStride]));
-        ds[e] = p[e] * (__uint_as_float(rd[j + e]) - rel_d[q * kRelStride]);
-      } else {
-        p[e] = ds[e] = 0.f;
+      for (int e = 0; e < 4; e += 2) {
+        const float2 b = __fadd2_rn(e == 0 ? make_float2(h4.x, h4.y) : make_float2(h4.z, h4.w), e == 0 ? make_float2(w4.x, w4.y) : make_float2(w4.z, w4.w));
+        const float2 v = __ffma2_rn(make_float2(__uint_as_float(rs[j + e]), __uint_as_float(rs[j + e + 1])), c2, b);
+        const float2 p = make_float2(wb_ex2(v.x), wb_ex2(v.y));
+        const float2 ds = __fmul2_rn(p, __fadd2_rn(make_float2(__uint_as_float(rd[j + e]), __uint_as_float(rd[j + e + 1])),
+                                                   e == 0 ? make_float2(d4.x, d4.y) : make_float2(d4.z, d4.w)));
+        pp[(j + e) >> 1] = pack_bf16(p.x, p.y);
+        pd[(j + e) >> 1] = pack_bf16(ds.x, ds.y);
       }
+    } else {
+      pp[j >> 1] = pp[(j >> 1) + 1] = 0u;
+      pd[j >> 1] = pd[(j >> 1) + 1] = 0u;
     }
-    pp[j >> 1] = pack_bf16(p[0], p[1]);
-    pd[j >> 1] = pack_bf16(ds[0], ds[1]);
   }
   wb_st<W / 2>(tS + PCOL + tlane, pp);
   wb_st<W / 2>(tDP + PCOL + tlane, pd);
@@ -176,7 +187,7 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
   // rows the TMA never writes (196..255 of every operand, the table's unused rows) must be finite: zero everything once
   for (uint32_t a = sQ + threadIdx.x * 16; a < sStage; a += kWbThreads * 16)
     asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
-  for (int i = threadIdx.x; i < kBK * kRelStride; i += kWbThreads) rel_s[i] = 0.f;
+  for (int i = threadIdx.x; i < kRelRows * kRelStride; i += kWbThreads) rel_s[i] = 0.f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -362,40 +373,48 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         }
         sync256();
-        float relh[8], relw[14], ah[8], aw[14];
+        float relh[8], relw[14];
+        float2 ah2[8], aw2[7];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int kh = hs * 8 + i;                          // thread 0 of the row owns key rows 0..7, thread 1 rows 8..13
           relh[i] = kh < kBS ? fmaf(stage_at(qh + (kBS - 1) - kh), kL2e, -my_lse) : 0.f;
-          ah[i] = 0.f;
+          ah2[i] = make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int i = 0; i < 14; ++i) { relw[i] = stage_at(32 + qw + (kBS - 1) - i) * kL2e; aw[i] = 0.f; }
-        if (q < kBK) {                                        // the key passes read bias, lse and D of every query from this table
-          float* rr = rel_s + q * kRelStride;
+        for (int i = 0; i < 14; ++i) relw[i] = stage_at(32 + qw + (kBS - 1) - i) * kL2e;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) aw2[i] = make_float2(0.f, 0.f);
+        if (q < kBK) {                                        // the key passes read bias, lse and D of every query from this (transposed) table
+          float* rr = rel_s + q;
           if (hs == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) rr[i] = relh[i];
+            for (int i = 0; i < 8; ++i) rr[i * kRelStride] = relh[i];
 #pragma unroll
-            for (int i = 0; i < 14; ++i) rr[14 + i] = relw[i];
-            rr[28] = my_d;
+            for (int i = 0; i < 14; ++i) rr[(14 + i) * kRelStride] = relw[i];
+            rr[28 * kRelStride] = -my_d;
           } else {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) rr[8 + i] = relh[i];
+            for (int i = 0; i < 6; ++i) rr[(8 + i) * kRelStride] = relh[i];
           }
         }
         mbar_wait(bar(S_FULL), (uint32_t)t);
         tc_fence_after();
         if (hs == 0) {
-          wb_q_chunk<0, 32, 0, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
-          wb_q_chunk<32, 32, 16, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
-          wb_q_chunk<64, 32, 32, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
-          wb_q_chunk<96, 16, 48, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
+          wb_q_chunk<0, 32, 0, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah2, aw2);
+          wb_q_chunk<32, 32, 16, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah2, aw2);
+          wb_q_chunk<64, 32, 32, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah2, aw2);
+          wb_q_chunk<96, 16, 48, 0>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah2, aw2);
         } else {
-          wb_q_chunk<176, 32, 192, 8>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
-          wb_q_chunk<144, 32, 176, 8>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
-          wb_q_chunk<112, 32, 160, 8>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah, aw);
+          wb_q_chunk<176, 32, 192, 8>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah2, aw2);
+          wb_q_chunk<144, 32, 176, 8>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah2, aw2);
+          wb_q_chunk<112, 32, 160, 8>(tS, tDP, tlane, relh, relw, c_l2, kScale, my_d, ah2, aw2);
         }
+        float ah[8], aw[14];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ah[i] = ah2[i].x + ah2[i].y;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) { aw[2 * i] = aw2[i].x; aw[2 * i + 1] = aw2[i].y; }
 #pragma unroll
         for (int i = 0; i < 7; ++i) xch_f[(hs * 7 + i) * 128 + row] = aw[hs == 0 ? 7 + i : i];     // the partial sums the partner thread finishes
         sync256();
@@ -441,7 +460,7 @@ attn_window_bwd_tc_kernel(const __grid_constant__ WinBwdTmaps tm, const WinBwdPa
         const int gy = wy * kBS + kh, gx = wx * kBS + kw;
         const bool valid = k < kBQ && gy < p.G && gx < p.G;    // pad keys take part in the softmax but their cotangents reach only the frozen biases
         const size_t tok = (size_t)(f * p.G + gy) * p.G + gx;
-        const float *rel_kh = rel_s + kh, *rel_kw = rel_s + 14 + kw, *rel_d = rel_s + 28;
+        const float *rel_kh = rel_s + kh * kRelStride, *rel_kw = rel_s + (14 + kw) * kRelStride, *rel_d = rel_s + 28 * kRelStride;
         mbar_wait(bar(S_FULL), (uint32_t)t);
         tc_fence_after();
         if (hs == 0) {

@@ -333,6 +333,19 @@ def test_gemm_bf16_residual_stream(ops, force_ctas):
     ops.gemm(a, w, y, bias=bias, act="relu", gate_alpha=alpha, resid=resid, force_ctas=force_ctas)
     ref2 = resid.float() + math.tanh(0.5) * F.relu(a.float() @ w.float().t() + bias)
     assert float(((y.float() - ref2).abs() / (ref2.abs() + 1e-3)).max()) < 8e-3
+    if force_ctas == 2:
+        # ragged M on the CTA-pair epilogue (rows past the end: residual fetch clamped, nothing stored) with the row statistics of the
+        # ROUNDED output, one (sum, sum of squares) pair per 128 columns
+        Mr = 1400
+        xr = torch.full((Mr + 8, N), 3.0, device="cuda", dtype=torch.bfloat16)
+        xr[:Mr] = resid[:Mr]
+        stats = torch.zeros(Mr, N // 128, 2, device="cuda")
+        ops.gemm(a[:Mr], w, xr[:Mr], bias=bias, resid=xr[:Mr], ln_stats_out=stats, force_ctas=2)
+        assert bool((xr[Mr:] == 3.0).all())
+        assert torch.equal(xr[:Mr], x[:Mr])
+        v = xr[:Mr].float().view(Mr, N // 128, 128)
+        assert torch.allclose(stats[..., 0], v.sum(-1), rtol=1e-5, atol=2e-3)
+        assert torch.allclose(stats[..., 1], (v * v).sum(-1), rtol=1e-5, atol=2e-3)
     # LayerNorm on a bf16 row equals LayerNorm on its fp32 widening
     g, b = _rand((N,), 7) + 1.0, _rand((N,), 8)
     h16, h32 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
