@@ -92,6 +92,8 @@ attn_global_tc_kernel(const __grid_constant__ AttTmaps tm, __nv_bfloat16* __rest
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                          // barrier init / TMEM allocation above overlapped the predecessor's last wave
+  pdl_launch_dependents();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   // S0|S1 (2x128), O (<=80), Q (HD/2 <= 40: bf16 pairs, the A operand of every Q.K^T), P0|P1 (2x64: bf16 pairs)
@@ -488,7 +490,7 @@ static int launch_att_tc(const void* qkv, const void* rh, const void* rw, void* 
   constexpr int smem = att_tc_smem<G, HD>();
   cudaError_t e = cudaFuncSetAttribute(attn_global_tc_kernel<G, HD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { grove_set_error("cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
-  attn_global_tc_kernel<G, HD, SPLIT><<<dim3(N / 128, heads, F), att_threads<SPLIT>(), smem, stream>>>(tm, (__nv_bfloat16*)out, lse, heads);
+  grove_launch_pdl(attn_global_tc_kernel<G, HD, SPLIT>, dim3(N / 128, heads, F), dim3(att_threads<SPLIT>()), smem, stream, tm, (__nv_bfloat16*)out, lse, heads);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;

@@ -186,6 +186,8 @@ attn_window_tc_kernel(const __grid_constant__ WinTmaps tm, const WinParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                          // barrier init / TMEM allocation / the zero fill above overlapped the predecessor's last wave
+  pdl_launch_dependents();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   const uint32_t tS0 = tmem_base, tTO = tmem_base + 416;
@@ -476,7 +478,7 @@ static int launch_window_tc(const void* qkv, const void* qkv_bias, const void* t
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.units < sms ? p.units : sms;
-  attn_window_tc_kernel<HD><<<grid, kWinThreads, Cfg::kSmem, stream>>>(tm, p);
+  grove_launch_pdl(attn_window_tc_kernel<HD>, dim3(grid), dim3(kWinThreads), Cfg::kSmem, stream, tm, p);
   grove_count_launch();
   GROVE_CHECK_LAUNCH();
   return GROVE_OK;

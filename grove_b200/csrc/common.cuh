@@ -1,5 +1,6 @@
 // Shared device/host helpers for the grove_b200 CUDA library (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -48,6 +49,27 @@ struct GrovePerDeviceOnce {
 };
 
 namespace grove {
+
+// GROVE_PDL=1 launches the GEMM and the two forward attention kernels with programmatic dependent launch (their prologue then overlaps the
+// predecessor's last wave).  OFF by default: same-box A/B on the graph-replayed inference step measured 594.5 / 599.8 frames/s with it and
+// 597.4 / 586.7 without -- inside the noise, so the step is not paying for kernel-boundary gaps and the extra launch mode is not worth
+// carrying on the default path.
+inline bool grove_pdl_enabled() {
+  static const bool v = []() { const char* e = getenv("GROVE_PDL"); return e && e[0] == '1'; }();
+  return v;
+}
+// kernel<<<grid, block, smem, st>>>(args...) with the PDL attribute (the kernel must call pdl_wait() before touching global memory)
+template <class... KArgs, class... Args>
+inline cudaError_t grove_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute a[1];
+  a[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = a;
+  cfg.numAttrs = grove_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 constexpr int kNumSMs = 148;
 
@@ -175,6 +197,14 @@ __device__ __forceinline__ float2 ex2_fma2(float2 x) {
   return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
                      __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (block
+// scheduling, barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream / graph is still draining its last
+// wave; pdl_wait() blocks until the predecessor grid has completed and its memory is visible, so it must precede EVERY global-memory access
+// of the kernel.  pdl_launch_dependents() lets the successor's blocks be scheduled as soon as this grid's blocks have all started.
+// Both are no-ops for kernels launched without the attribute / without a programmatic successor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // One leader lane of a fully converged warp (elect.sync).  tcgen05.mma / tcgen05.commit / TMA are uniform-datapath instructions:
 // issued under `if (lane == 0)` ptxas wraps EVERY one of them in a serialising ELECT ... BRA.U.ANY loop with R2UR moves (~60-100 clk

@@ -127,6 +127,8 @@ gemm_bf16_tcgen05_kernel(const GemmParams p, const __grid_constant__ CUtensorMap
   __syncthreads();
   if (CTAS == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
+  pdl_wait();                          // everything above overlapped the predecessor's last wave; no global memory has been touched yet
+  pdl_launch_dependents();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -852,11 +854,13 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& ta, const CUtenso
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = grove_pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, CTAS, EPI>, p, ta, tb);
   grove_count_launch();
   if (e != cudaSuccess) { grove_set_error("gemm launch failed: %s", cudaGetErrorString(e)); return GROVE_ERR_CUDA; }
