@@ -412,13 +412,16 @@ def main():
     if rank == 0:
         value = world * TOT * args.steps / (ms * 1e-3)
         e2e_v = world * TOT * args.steps / (ms_e2e_sync * 1e-3)
-        h2d = sum(t.numel() * t.element_size() for t in host_sets[0][:2]) + 4 * PHRASES * VIDEOS
+        # what the blocking call uploads: the images, the [DET] rows of the hidden states (gathered on the host: only they are read) and
+        # their row indices
+        h2d = host_sets[0][0].numel() * host_sets[0][0].element_size() + PHRASES * VIDEOS * host_sets[0][1].shape[-1] * host_sets[0][1].element_size() \
+            + 4 * PHRASES * VIDEOS
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": TOT * PHRASES * 5 * 4,
-                        "api": "one GroundingBranch.ground_records() call per step on pinned host inputs: upload (images, hidden states, [DET] row "
-                               "indices), ground, read the packed boxes + objectness back (blocking)",
+                        "api": "one GroundingBranch.ground_records() call per step on pinned host inputs: upload (images, the [DET] rows of the hidden states "
+                               "gathered on the host, their row indices), ground, read the packed boxes + objectness back (blocking)",
                         "pipelined_value": world * TOT * args.steps / (ms_e2e * 1e-3),
                         "pipelined_api": "GroundingBranch.ground_host_stream (next upload / previous read-back overlap the current step)"},
                 "gpu_launches": launches,

@@ -255,6 +255,11 @@ def test_serving_loop_graph_replay_and_host_stream():
     # the whole-step graph of GroundingBranch (encoder + text projection + decoder + heads in one replay)
     gb.enable_cuda_graphs(True)
     whole = [direct(b) for b in batches]
+    # the same replay fed straight from pinned HOST tensors (bench.py's e2e call): only the [DET] rows of the hidden states are uploaded,
+    # gathered on the host -- bit-identical records, also for back-to-back calls without a host sync in between
+    hosted = [gb.ground_records(b[0], b[1], gb._create_det_token_mask(b[2]), copy_out=True)[1] for b in batches]
+    for a, b in zip(eager, hosted):
+        assert torch.equal(a, b.cpu())
     gb.enable_cuda_graphs(False)
     for a, b in zip(eager, whole):
         assert torch.equal(a, b)
