@@ -392,9 +392,19 @@ class GroundingBranch(nn.Module):
         into the static inputs are the step's only host->device traffic)"""
         dev = next(self.parameters()).device
         key = (tuple(images.shape), images.dtype, tuple(hidden.shape), hidden.dtype, tuple(counts), dev)
-        sig = self._param_signature()
         ent = self._graphs.get(key)
+        copied = False
+        if ent is not None:
+            # the uploads into the static inputs go first (they do not depend on the weights): the ~0.5 ms of host work for the parameter
+            # signature below then runs under the 0.9 ms image DMA instead of in front of it
+            st_images, st_hidden, st_idx = ent["in"]
+            st_images.copy_(images, non_blocking=True); st_hidden.copy_(hidden, non_blocking=True)
+            if idx.numel():
+                st_idx[:idx.numel()].copy_(idx, non_blocking=True)
+            copied = True
+        sig = self._param_signature()
         if ent is None or ent["sig"] != sig:
+            copied = False
             enc = self.grounding_encoder.image_encoder
             st_images = torch.empty(images.shape, dtype=images.dtype, device=dev)
             st_hidden = torch.empty(hidden.shape, dtype=hidden.dtype, device=dev)
@@ -420,10 +430,11 @@ class GroundingBranch(nn.Module):
             if len(self._graphs) >= 8:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = ent
-        st_images, st_hidden, st_idx = ent["in"]
-        st_images.copy_(images, non_blocking=True); st_hidden.copy_(hidden, non_blocking=True)
-        if idx.numel():
-            st_idx[:idx.numel()].copy_(idx, non_blocking=True)
+        if not copied:
+            st_images, st_hidden, st_idx = ent["in"]
+            st_images.copy_(images, non_blocking=True); st_hidden.copy_(hidden, non_blocking=True)
+            if idx.numel():
+                st_idx[:idx.numel()].copy_(idx, non_blocking=True)
         ent["graph"].replay()
         ops.add_launch_count(ent["kernels"])
         emb_tok, rec = ent["out"]
